@@ -1,0 +1,1103 @@
+// TEST INFRASTRUCTURE -- CPU oracle for the C-IPC contact hot path ("port" of the reference).
+//
+// Restates, Eigen/Kokkos/Cabana-free, what the reference's 3-D, T=double contact code computes:
+//   Library/Grid/SPATIAL_HASH.h   (static build :28-213, queries :215-381, swept build :432-622,
+//                                  id queries :624-690, voxel index :693-708)
+//   Library/FEM/IPC.h             (Compute_Constraint_Set :19-740, Compute_Barrier :742-941,
+//                                  Compute_Barrier_Gradient :943-1256, Compute_Barrier_Hessian
+//                                  :1258-1731, Compute_Intersection_Free_StepSize :1879-2244,
+//                                  Compute_Min_Dist2 :2246-2388)
+//   Library/Math/Distance/CCD.h   (ACCD kernels :279-483)
+// It keeps the reference's parallel structure so that it can double as the CPU baseline:
+// Par_Each loops are `omp parallel for`; hash-map insertion, the PP/PE merge, the energy, the
+// gradient and min-dist loops are serial exactly as in the reference.
+//
+// PARITY STATUS: the reference ships no tests and cannot be built here (needs Eigen, Kokkos,
+// Cabana, Boost, ...).  The geometric kernels (distances, classifiers, derivatives, barrier, ACCD
+// per pair) are pinned against the reference's OWN headers compiled with a stub Eigen
+// (oracle/_ref, see oracle/ref_build/); the hash / constraint-set / step-size drivers are pinned
+// only by self-consistency (hash == brute force, FD checks): "parity unpinned" for those.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline, --impl reference) may use this.
+#include "geom.h"
+#include "derivs.h"
+#include "eig.h"
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+#include <array>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <unordered_set>
+#include <numeric>
+#include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace cipc_oracle {
+
+typedef std::array<int, 4> I4;
+typedef std::array<double, 2> D2;
+
+struct Scene {
+    int nV = 0;
+    const double* X = nullptr;   // 3*nV
+    const double* X0 = nullptr;  // 3*nV rest positions (nodeAttr.x0)
+    int nBN = 0, nBE = 0, nBT = 0, nRod = 0;
+    const int* BN = nullptr;     // nBN
+    const int* BE = nullptr;     // 2*nBE
+    const int* BT = nullptr;     // 3*nBT
+    int codim0 = 0, codim1 = 0;  // codimBNStartInd
+    const uint8_t* DBC = nullptr; // nV
+    std::map<int, std::set<int>> NNX; // NNExclusion
+    const double *BNArea = nullptr, *BEArea = nullptr, *BTArea = nullptr;
+    V3 x(int v) const { return V3(X + 3 * v); }
+    V3 x0(int v) const { return V3(X0 + 3 * v); }
+};
+
+// ======================================================================= SPATIAL_HASH
+struct SpatialHash {
+    V3 lbc, rtc;
+    double one_div_voxelSize = 0;
+    int vc[3] = {1, 1, 1};
+    int vc01 = 1;
+    int edgeStart = 0, triStart = 0;
+    std::unordered_map<int, std::vector<int>> voxel;
+    std::vector<std::vector<int>> occupancy; // pointAndEdgeOccupancy (CCD)
+
+    // SPATIAL_HASH.h:702-708
+    void axis_index(const V3& pos, int* out) const
+    {
+        out[0] = (int)std::floor((pos.x - lbc.x) * one_div_voxelSize);
+        out[1] = (int)std::floor((pos.y - lbc.y) * one_div_voxelSize);
+        out[2] = (int)std::floor((pos.z - lbc.z) * one_div_voxelSize);
+    }
+    int lin(const int* a) const { return a[0] + a[1] * vc[0] + a[2] * vc01; }
+
+    // SPATIAL_HASH.h:71-86 / :504-519 (shared by both builds)
+    void size_grid(double voxelSize, const char* tag, bool quiet)
+    {
+        const double range[3] = {rtc.x - lbc.x, rtc.y - lbc.y, rtc.z - lbc.z};
+        one_div_voxelSize = 1.0 / voxelSize;
+        long voxelAmt = 1;
+        for (int d = 0; d < 3; ++d) voxelAmt *= std::max(1L, (long)std::ceil(range[d] * one_div_voxelSize));
+        if (voxelAmt > 1e9) {
+            voxelSize *= std::pow(voxelAmt / 1.0e9, 1.0 / 3);
+            one_div_voxelSize = 1.0 / voxelSize;
+        }
+        for (int d = 0; d < 3; ++d) vc[d] = std::max(1, (int)std::ceil(range[d] * one_div_voxelSize));
+        if (!quiet) printf("%s SH voxel count %d\n", tag, vc[0] * vc[1] * vc[2]);
+        if (std::min(vc[0], std::min(vc[1], vc[2])) <= 0) {
+            one_div_voxelSize = 1.0 / (std::max(range[0], std::max(range[1], range[2])) * 1.01);
+            vc[0] = vc[1] = vc[2] = 1;
+        }
+        vc01 = vc[0] * vc[1];
+    }
+
+    static double mean_edge_len(const Scene& s)
+    {
+        // SPATIAL_HASH.h:60-67 / :455-464: eLen.mean().  Eigen's vectorised redux order is not
+        // restated; a plain sequential sum is used (differs by O(n eps), shifts voxel borders only).
+        std::vector<double> eLen(s.nBE);
+#pragma omp parallel for schedule(static)
+        for (int e = 0; e < s.nBE; ++e) eLen[e] = std::sqrt(norm2(s.x(s.BE[2 * e]) - s.x(s.BE[2 * e + 1])));
+        double sum = 0;
+        for (int e = 0; e < s.nBE; ++e) sum += eLen[e];
+        return sum / s.nBE;
+    }
+
+    // SPATIAL_HASH.h:28-213
+    void build_static(const Scene& s, double voxelSize, bool quiet)
+    {
+        if (s.nBE) voxelSize *= mean_edge_len(s);
+        lbc = V3(1e300, 1e300, 1e300); rtc = V3(-1e300, -1e300, -1e300);
+        for (int v = 0; v < s.nV; ++v) { lbc = vmin(lbc, s.x(v)); rtc = vmax(rtc, s.x(v)); }
+        size_grid(voxelSize, "CCS", quiet);
+        edgeStart = s.nBN; triStart = edgeStart + s.nBE;
+
+        std::vector<std::array<int, 3>> svVAI(s.nBN);
+        std::vector<int> vI2SVI(s.nV, 0);
+#pragma omp parallel for schedule(static)
+        for (int svI = 0; svI < s.nBN; ++svI) axis_index(s.x(s.BN[svI]), svVAI[svI].data());
+        for (int svI = 0; svI < s.nBN; ++svI) vI2SVI[s.BN[svI]] = svI;
+
+        voxel.clear();
+        for (int svI = 0; svI < s.nBN; ++svI) voxel[lin(svVAI[svI].data())].emplace_back(svI);
+
+        auto fill = [&](const int* mins, const int* maxs, std::vector<int>& out) {
+            for (int iz = mins[2]; iz <= maxs[2]; ++iz)
+                for (int iy = mins[1]; iy <= maxs[1]; ++iy)
+                    for (int ix = mins[0]; ix <= maxs[0]; ++ix) out.emplace_back(ix + iy * vc[0] + iz * vc01);
+        };
+        std::vector<std::vector<int>> locE(s.nBE), locT(s.nBT);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int e = 0; e < s.nBE; ++e) {
+            const auto& a = svVAI[vI2SVI[s.BE[2 * e]]];
+            const auto& b = svVAI[vI2SVI[s.BE[2 * e + 1]]];
+            int mins[3], maxs[3];
+            for (int d = 0; d < 3; ++d) { mins[d] = std::min(a[d], b[d]); maxs[d] = std::max(a[d], b[d]); }
+            fill(mins, maxs, locE[e]);
+        }
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int t = 0; t < s.nBT; ++t) {
+            const auto& a = svVAI[vI2SVI[s.BT[3 * t]]];
+            const auto& b = svVAI[vI2SVI[s.BT[3 * t + 1]]];
+            const auto& c = svVAI[vI2SVI[s.BT[3 * t + 2]]];
+            int mins[3], maxs[3];
+            for (int d = 0; d < 3; ++d) {
+                mins[d] = std::min(std::min(a[d], b[d]), c[d]);
+                maxs[d] = std::max(std::max(a[d], b[d]), c[d]);
+            }
+            fill(mins, maxs, locT[t]);
+        }
+        for (int e = 0; e < s.nBE; ++e) for (int c : locE[e]) voxel[c].emplace_back(e + edgeStart);
+        for (int t = 0; t < s.nBT; ++t) for (int c : locT[t]) voxel[c].emplace_back(t + triStart);
+    }
+
+    template <class F>
+    void for_range(const V3& lo, const V3& hi, F f) const
+    {
+        int mins[3], maxs[3];
+        axis_index(lo, mins); axis_index(hi, maxs);
+        for (int d = 0; d < 3; ++d) { mins[d] = std::max(mins[d], 0); maxs[d] = std::min(maxs[d], vc[d] - 1); }
+        for (int iz = mins[2]; iz <= maxs[2]; ++iz)
+            for (int iy = mins[1]; iy <= maxs[1]; ++iy)
+                for (int ix = mins[0]; ix <= maxs[0]; ++ix) {
+                    auto it = voxel.find(ix + iy * vc[0] + iz * vc01);
+                    if (it != voxel.end()) for (int ind : it->second) f(ind);
+                }
+    }
+    // SPATIAL_HASH.h:215-241
+    void query_point_for_triangles(const V3& p, double r, std::unordered_set<int>& out) const
+    {
+        out.clear();
+        for_range(V3(p.x - r, p.y - r, p.z - r), V3(p.x + r, p.y + r, p.z + r),
+            [&](int ind) { if (ind >= triStart) out.insert(ind - triStart); });
+    }
+    // SPATIAL_HASH.h:293-336
+    void query_point_for_edges(const V3& p, double r, std::unordered_set<int>& out) const
+    {
+        out.clear();
+        for_range(V3(p.x - r, p.y - r, p.z - r), V3(p.x + r, p.y + r, p.z + r),
+            [&](int ind) { if (ind >= edgeStart && ind < triStart) out.insert(ind - edgeStart); });
+    }
+    // SPATIAL_HASH.h:338-381
+    void query_point_for_points(const V3& p, double r, std::unordered_set<int>& out) const
+    {
+        out.clear();
+        for_range(V3(p.x - r, p.y - r, p.z - r), V3(p.x + r, p.y + r, p.z + r),
+            [&](int ind) { if (ind < edgeStart) out.insert(ind); });
+    }
+    // SPATIAL_HASH.h:243-291
+    void query_edge_for_edges(const V3& a, const V3& b, double r, std::vector<int>& out, int eIq) const
+    {
+        out.resize(0);
+        const V3 lo = vmin(a, b), hi = vmax(a, b);
+        for_range(V3(lo.x - r, lo.y - r, lo.z - r), V3(hi.x + r, hi.y + r, hi.z + r),
+            [&](int ind) { if (ind >= edgeStart && ind < triStart && ind - edgeStart > eIq) out.emplace_back(ind - edgeStart); });
+        std::sort(out.begin(), out.end());
+        out.erase(std::unique(out.begin(), out.end()), out.end());
+    }
+
+    // SPATIAL_HASH.h:432-622 (swept build; may shrink curMaxStepSize)
+    void build_swept(const Scene& s, const double* searchDir, double& curMaxStepSize, double voxelSize,
+        double thickness, bool quiet)
+    {
+        if (s.nBE) voxelSize *= mean_edge_len(s);
+        double pSize = 0;
+        for (int svI = 0; svI < s.nBN; ++svI) {
+            const int vI = s.BN[svI];
+            pSize += std::fabs(searchDir[vI * 3]);
+            pSize += std::fabs(searchDir[vI * 3 + 1]);
+            pSize += std::fabs(searchDir[vI * 3 + 2]);
+        }
+        pSize /= s.nBN * 3;
+        const double spanSize = curMaxStepSize * pSize / voxelSize;
+        if (!quiet) printf("span size = %g\n", spanSize);
+        if (spanSize > 1) {
+            curMaxStepSize /= spanSize;
+            if (!quiet) printf("curMaxStepSize reduced\n");
+        }
+        std::vector<V3> SV(s.nBN), SVt(s.nBN);
+        std::unordered_map<int, int> vI2SVI;
+        for (int svI = 0; svI < s.nBN; ++svI) {
+            const int vI = s.BN[svI];
+            vI2SVI[vI] = svI;
+            SV[svI] = s.x(vI);
+            SVt[svI] = V3(SV[svI].x + curMaxStepSize * searchDir[vI * 3], SV[svI].y + curMaxStepSize * searchDir[vI * 3 + 1],
+                SV[svI].z + curMaxStepSize * searchDir[vI * 3 + 2]);
+        }
+        V3 mnS(1e300, 1e300, 1e300), mxS(-1e300, -1e300, -1e300), mnT = mnS, mxT = mxS;
+        for (int i = 0; i < s.nBN; ++i) {
+            mnS = vmin(mnS, SV[i]); mxS = vmax(mxS, SV[i]);
+            mnT = vmin(mnT, SVt[i]); mxT = vmax(mxT, SVt[i]);
+        }
+        const V3 mn = vmin(mnS, mnT), mx = vmax(mxS, mxT);
+        lbc = V3(mn.x - thickness / 2, mn.y - thickness / 2, mn.z - thickness / 2);
+        rtc = V3(mx.x + thickness / 2, mx.y + thickness / 2, mx.z + thickness / 2);
+        size_grid(voxelSize, "CCD", quiet);
+        edgeStart = s.nBN; triStart = edgeStart + s.nBE;
+
+        std::vector<std::array<int, 3>> svMin(s.nBN), svMax(s.nBN);
+#pragma omp parallel for schedule(static)
+        for (int svI = 0; svI < s.nBN; ++svI) {
+            const V3 lo = vmin(SV[svI], SVt[svI]), hi = vmax(SV[svI], SVt[svI]);
+            axis_index(V3(lo.x - thickness / 2, lo.y - thickness / 2, lo.z - thickness / 2), svMin[svI].data());
+            axis_index(V3(hi.x + thickness / 2, hi.y + thickness / 2, hi.z + thickness / 2), svMax[svI].data());
+        }
+        voxel.clear();
+        occupancy.assign(triStart, std::vector<int>());
+        auto fill = [&](const int* mins, const int* maxs, std::vector<int>& out) {
+            for (int iz = mins[2]; iz <= maxs[2]; ++iz)
+                for (int iy = mins[1]; iy <= maxs[1]; ++iy)
+                    for (int ix = mins[0]; ix <= maxs[0]; ++ix) out.emplace_back(ix + iy * vc[0] + iz * vc01);
+        };
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int svI = 0; svI < s.nBN; ++svI) fill(svMin[svI].data(), svMax[svI].data(), occupancy[svI]);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int e = 0; e < s.nBE; ++e) {
+            const int a = vI2SVI.at(s.BE[2 * e]), b = vI2SVI.at(s.BE[2 * e + 1]);
+            int mins[3], maxs[3];
+            for (int d = 0; d < 3; ++d) { mins[d] = std::min(svMin[a][d], svMin[b][d]); maxs[d] = std::max(svMax[a][d], svMax[b][d]); }
+            fill(mins, maxs, occupancy[e + edgeStart]);
+        }
+        std::vector<std::vector<int>> locT(s.nBT);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int t = 0; t < s.nBT; ++t) {
+            const int a = vI2SVI.at(s.BT[3 * t]), b = vI2SVI.at(s.BT[3 * t + 1]), c = vI2SVI.at(s.BT[3 * t + 2]);
+            int mins[3], maxs[3];
+            for (int d = 0; d < 3; ++d) {
+                mins[d] = std::min(std::min(svMin[a][d], svMin[b][d]), svMin[c][d]);
+                maxs[d] = std::max(std::max(svMax[a][d], svMax[b][d]), svMax[c][d]);
+            }
+            fill(mins, maxs, locT[t]);
+        }
+        for (int i = 0; i < (int)occupancy.size(); ++i) for (int c : occupancy[i]) voxel[c].emplace_back(i);
+        for (int t = 0; t < s.nBT; ++t) for (int c : locT[t]) voxel[c].emplace_back(t + triStart);
+    }
+    // SPATIAL_HASH.h:624-646
+    void query_point_for_primitives(int svI, std::unordered_set<int>& pts, std::unordered_set<int>& edges,
+        std::unordered_set<int>& tris) const
+    {
+        pts.clear(); edges.clear(); tris.clear();
+        for (int c : occupancy[svI]) {
+            auto it = voxel.find(c);
+            for (int ind : it->second) {
+                if (ind >= triStart) tris.insert(ind - triStart);
+                else if (ind >= edgeStart) edges.insert(ind - edgeStart);
+                else pts.insert(ind);
+            }
+        }
+    }
+    // SPATIAL_HASH.h:648-661
+    void query_edge_for_edges(int seI, std::unordered_set<int>& edges) const
+    {
+        edges.clear();
+        for (int c : occupancy[seI + edgeStart]) {
+            auto it = voxel.find(c);
+            for (int ind : it->second)
+                if (ind >= edgeStart && ind < triStart && ind - edgeStart > seI) edges.insert(ind - edgeStart);
+        }
+    }
+};
+
+// ======================================================================= pair filters
+static inline bool nnx_hit(const Scene& s, int v, int a, int b, int c)
+{
+    auto f = s.NNX.find(v);
+    if (f == s.NNX.end()) return false;
+    return f->second.count(a) || f->second.count(b) || (c >= 0 && f->second.count(c));
+}
+// IPC.h:171-181
+static inline bool pt_pair_ok(const Scene& s, int vI, const int* t)
+{
+    if (vI == t[0] || vI == t[1] || vI == t[2]) return false;
+    if (s.DBC[vI] && s.DBC[t[0]] && s.DBC[t[1]] && s.DBC[t[2]]) return false;
+    if (nnx_hit(s, vI, t[0], t[1], t[2])) return false;
+    return true;
+}
+// IPC.h:384-397
+static inline bool ee_pair_ok(const Scene& s, int eI, int eJ, const int* a, const int* b)
+{
+    if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1] || eI > eJ) return false;
+    if (s.DBC[a[0]] && s.DBC[a[1]] && s.DBC[b[0]] && s.DBC[b[1]]) return false;
+    if (nnx_hit(s, a[0], b[0], b[1], -1) || nnx_hit(s, a[1], b[0], b[1], -1)) return false;
+    return true;
+}
+
+// ======================================================================= Compute_Constraint_Set
+struct Timers { double t[8] = {0}; };
+static inline double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// IPC.h:143-661 (3-D branch).  use_hash=false takes the reference's `#else` brute-force loops.
+static void compute_constraint_set(const Scene& s, bool elastic, double dHat2, double thickness, bool use_hash,
+    std::vector<I4>& constraintSet, std::vector<D2>& stencilInfo, Timers* tm, bool quiet)
+{
+    SpatialHash sh;
+    double t0 = now_s();
+    if (use_hash) sh.build_static(s, 1.0, quiet);
+    double t1 = now_s();
+    if (elastic) thickness = 0;
+    const double dHat = std::sqrt(dHat2) + thickness;
+    dHat2 = dHat * dHat;
+
+    // ---- point-triangle pass (IPC.h:145-355)
+    std::vector<std::vector<I4>> csPT(s.nBN);
+    std::vector<std::vector<D2>> infoPT(s.nBN);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int svI = 0; svI < s.nBN; ++svI) {
+        const int vI = s.BN[svI];
+        const V3 p = s.x(vI);
+        std::unordered_set<int> triInds;
+        auto visit_tri = [&](int sfI) {
+            const int* t = s.BT + 3 * sfI;
+            if (!pt_pair_ok(s, vI, t)) return;
+            const V3 t0 = s.x(t[0]), t1 = s.x(t[1]), t2 = s.x(t[2]);
+            if (!pt_cd_broadphase(p, t0, t1, t2, dHat)) return;
+            double d = 1e300;
+            switch (pt_type(p, t0, t1, t2)) {
+            case 0: d = pp_dist2(p, t0); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[0], -1, -1}); break;
+            case 1: d = pp_dist2(p, t1); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[1], -1, -1}); break;
+            case 2: d = pp_dist2(p, t2); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[2], -1, -1}); break;
+            case 3: d = pe_dist2(p, t0, t1); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[0], t[1], -1}); break;
+            case 4: d = pe_dist2(p, t1, t2); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[1], t[2], -1}); break;
+            case 5: d = pe_dist2(p, t2, t0); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[2], t[0], -1}); break;
+            case 6: d = pt_dist2(p, t0, t1, t2); if (d < dHat2) csPT[svI].push_back({-vI - 1, t[0], t[1], t[2]}); break;
+            default: break;
+            }
+            if (d < dHat2) {
+                double w = elastic ? s.BNArea[svI] * s.BTArea[sfI] : 1.0; // BNArea is misaligned for codim nodes; not read when !elastic
+                if (elastic && svI < s.codim0) w /= 2;
+                infoPT[svI].push_back({w, dHat2});
+            }
+        };
+        if (use_hash) {
+            sh.query_point_for_triangles(p, dHat, triInds);
+            for (int sfI : triInds) visit_tri(sfI);
+        }
+        else for (int sfI = 0; sfI < s.nBT; ++sfI) visit_tri(sfI);
+
+        if (svI >= s.codim0) { // rod or particle points vs rod edges (IPC.h:271-326)
+            auto visit_edge = [&](int eI) {
+                if (eI < s.nBE - s.nRod) return;
+                const int* e = s.BE + 2 * eI;
+                if (vI == e[0] || vI == e[1] || (s.DBC[vI] && s.DBC[e[0]] && s.DBC[e[1]])) return;
+                const V3 e0 = s.x(e[0]), e1 = s.x(e[1]);
+                if (!pe_cd_broadphase(p, e0, e1, dHat)) return;
+                double d = 1e300, ratio;
+                switch (pe_type(p, e0, e1, ratio)) {
+                case 0: d = pp_dist2(p, e0); if (d < dHat2) csPT[svI].push_back({-vI - 1, e[0], -1, -1}); break;
+                case 1: d = pp_dist2(p, e1); if (d < dHat2) csPT[svI].push_back({-vI - 1, e[1], -1, -1}); break;
+                case 2: d = pe_dist2(p, e0, e1); if (d < dHat2) csPT[svI].push_back({-vI - 1, e[0], e[1], -1}); break;
+                }
+                if (d < dHat2) infoPT[svI].push_back({1.0, dHat2});
+            };
+            if (use_hash) {
+                std::unordered_set<int> edgeInds;
+                sh.query_point_for_edges(p, dHat, edgeInds);
+                for (int eI : edgeInds) visit_edge(eI);
+            }
+            else for (int eI = 0; eI < s.nBE; ++eI) visit_edge(eI);
+
+            if (svI >= s.codim1) { // particle vs later points (IPC.h:328-352)
+                auto visit_point = [&](int svJ) {
+                    const int vJ = s.BN[svJ];
+                    if (svJ > svI && !(s.DBC[vI] && s.DBC[vJ])) {
+                        const double d = pp_dist2(p, s.x(vJ));
+                        if (d < dHat2) {
+                            csPT[svI].push_back({-vI - 1, vJ, -1, -1});
+                            infoPT[svI].push_back({1.0, dHat2});
+                        }
+                    }
+                };
+                if (use_hash) {
+                    std::unordered_set<int> pointInds;
+                    sh.query_point_for_points(p, dHat, pointInds);
+                    for (int svJ : pointInds) visit_point(svJ);
+                }
+                else for (int svJ = 0; svJ < s.nBN; ++svJ) visit_point(svJ);
+            }
+        }
+    }
+    double t2 = now_s();
+
+    // ---- edge-edge pass (IPC.h:358-568)
+    std::vector<std::vector<I4>> csEE(s.nBE);
+    std::vector<std::vector<D2>> infoEE(s.nBE);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int eI = 0; eI < s.nBE; ++eI) {
+        const int* a = s.BE + 2 * eI;
+        const V3 ea0 = s.x(a[0]), ea1 = s.x(a[1]);
+        auto visit = [&](int eJ) {
+            const int* b = s.BE + 2 * eJ;
+            if (!ee_pair_ok(s, eI, eJ, a, b)) return;
+            const V3 eb0 = s.x(b[0]), eb1 = s.x(b[1]);
+            if (!ee_cd_broadphase(ea0, ea1, eb0, eb1, dHat)) return;
+            const double cn2 = ee_cross_norm2(ea0, ea1, eb0, eb1);
+            const double eps_x = ee_mollifier_threshold(s.x0(a[0]), s.x0(a[1]), s.x0(b[0]), s.x0(b[1]));
+            const bool mol = (cn2 < eps_x);
+            double d = 1e300;
+            auto& out = csEE[eI];
+            switch (ee_type(ea0, ea1, eb0, eb1)) {
+            case 0: d = pp_dist2(ea0, eb0); if (d < dHat2) out.push_back(mol ? I4{a[0], b[0], -a[1] - 1, -b[1] - 1} : I4{-a[0] - 1, b[0], -1, -1}); break;
+            case 1: d = pp_dist2(ea0, eb1); if (d < dHat2) out.push_back(mol ? I4{a[0], b[1], -a[1] - 1, -b[0] - 1} : I4{-a[0] - 1, b[1], -1, -1}); break;
+            case 2: d = pe_dist2(ea0, eb0, eb1); if (d < dHat2) out.push_back(mol ? I4{a[0], b[0], b[1], -a[1] - 1} : I4{-a[0] - 1, b[0], b[1], -1}); break;
+            case 3: d = pp_dist2(ea1, eb0); if (d < dHat2) out.push_back(mol ? I4{a[1], b[0], -a[0] - 1, -b[1] - 1} : I4{-a[1] - 1, b[0], -1, -1}); break;
+            case 4: d = pp_dist2(ea1, eb1); if (d < dHat2) out.push_back(mol ? I4{a[1], b[1], -a[0] - 1, -b[0] - 1} : I4{-a[1] - 1, b[1], -1, -1}); break;
+            case 5: d = pe_dist2(ea1, eb0, eb1); if (d < dHat2) out.push_back(mol ? I4{a[1], b[0], b[1], -a[0] - 1} : I4{-a[1] - 1, b[0], b[1], -1}); break;
+            case 6: d = pe_dist2(eb0, ea0, ea1); if (d < dHat2) out.push_back(mol ? I4{b[0], a[0], a[1], -b[1] - 1} : I4{-b[0] - 1, a[0], a[1], -1}); break;
+            case 7: d = pe_dist2(eb1, ea0, ea1); if (d < dHat2) out.push_back(mol ? I4{b[1], a[0], a[1], -b[0] - 1} : I4{-b[1] - 1, a[0], a[1], -1}); break;
+            case 8: d = ee_dist2(ea0, ea1, eb0, eb1); if (d < dHat2) out.push_back(mol ? I4{a[0], a[1], -b[0] - 1, b[1]} : I4{a[0], a[1], b[0], b[1]}); break;
+            default: break;
+            }
+            if (d < dHat2) {
+                double w = elastic ? s.BEArea[eI] * s.BEArea[eJ] : 1.0;
+                if (elastic && (eI >= s.nBE - s.nRod) && (eJ >= s.nBE - s.nRod)) w *= 2;
+                infoEE[eI].push_back({w, dHat2});
+            }
+        };
+        if (use_hash) {
+            std::vector<int> edgeInds;
+            sh.query_edge_for_edges(ea0, ea1, dHat, edgeInds, eI);
+            for (int eJ : edgeInds) visit(eJ);
+        }
+        else for (int eJ = eI + 1; eJ < s.nBE; ++eJ) visit(eJ);
+    }
+    double t3 = now_s();
+
+    // ---- merge (IPC.h:571-661): PT/EE/mollified pass through; PP/PE de-duplicated by raw key
+    constraintSet.resize(0);
+    stencilInfo.resize(0);
+    std::map<I4, int> counter;
+    std::map<I4, D2> areaCounter;
+    for (int i = 0; i < s.nBN; ++i)
+        for (size_t k = 0; k < csPT[i].size(); ++k) {
+            const I4& c = csPT[i][k];
+            if (c[3] < 0) {
+                ++counter[c];
+                auto f = areaCounter.find(c);
+                if (f == areaCounter.end()) areaCounter[c] = infoPT[i][k];
+                else f->second[0] += infoPT[i][k][0];
+            }
+            else { constraintSet.push_back(c); stencilInfo.push_back(infoPT[i][k]); }
+        }
+    for (int i = 0; i < s.nBE; ++i)
+        for (size_t k = 0; k < csEE[i].size(); ++k) {
+            const I4& c = csEE[i][k];
+            if (c[0] < 0) {
+                ++counter[c];
+                auto f = areaCounter.find(c);
+                if (f == areaCounter.end()) areaCounter[c] = infoEE[i][k];
+                else f->second[0] += infoEE[i][k][0];
+            }
+            else { constraintSet.push_back(c); stencilInfo.push_back(infoEE[i][k]); }
+        }
+    for (const auto& cc : counter) {
+        constraintSet.push_back({cc.first[0], cc.first[1], cc.first[2], -cc.second});
+        const D2& a = areaCounter[cc.first];
+        stencilInfo.push_back({a[0] / cc.second, a[1]});
+    }
+    if (!elastic) for (auto& i : stencilInfo) i[0] = 1;
+    double t4 = now_s();
+    if (tm) { tm->t[0] = t1 - t0; tm->t[1] = t2 - t1; tm->t[2] = t3 - t2; tm->t[3] = t4 - t3; }
+}
+
+// ======================================================================= stencil decoding
+// Appendix-A dispatch shared by energy/gradient/Hessian/min-dist (IPC.h:801-938 etc.)
+enum Kind { K_PT, K_PE, K_PP, K_EE, K_EE_M, K_PE_M, K_PP_M };
+struct Stencil {
+    Kind kind;
+    int v[4];    // vertex ids in block order
+    int mult;    // multiplicity m (1 unless de-duplicated PP/PE)
+};
+static inline Stencil decode(const I4& c)
+{
+    Stencil st;
+    st.mult = 1;
+    if (c[0] >= 0) {
+        if (c[3] >= 0 && c[2] >= 0) { st.kind = K_EE; st.v[0] = c[0]; st.v[1] = c[1]; st.v[2] = c[2]; st.v[3] = c[3]; }
+        else if (c[3] >= 0) { st.kind = K_EE_M; st.v[0] = c[0]; st.v[1] = c[1]; st.v[2] = -c[2] - 1; st.v[3] = c[3]; }
+        else if (c[2] >= 0) { st.kind = K_PE_M; st.v[0] = c[0]; st.v[1] = -c[3] - 1; st.v[2] = c[1]; st.v[3] = c[2]; }
+        else { st.kind = K_PP_M; st.v[0] = c[0]; st.v[1] = -c[2] - 1; st.v[2] = c[1]; st.v[3] = -c[3] - 1; }
+    }
+    else {
+        st.v[0] = -c[0] - 1; st.v[1] = c[1]; st.v[2] = c[2]; st.v[3] = c[3];
+        if (c[3] >= 0) st.kind = K_PT;
+        else if (c[2] >= 0) { st.kind = K_PE; st.mult = -c[3]; }
+        else { st.kind = K_PP; st.mult = -c[3]; }
+    }
+    return st;
+}
+static inline double stencil_dist2(const Scene& s, const Stencil& st)
+{
+    switch (st.kind) {
+    case K_PT: return pt_dist2(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]));
+    case K_PE: return pe_dist2(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]));
+    case K_PP: return pp_dist2(s.x(st.v[0]), s.x(st.v[1]));
+    case K_EE: case K_EE_M: return ee_dist2(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]));
+    case K_PE_M: return pe_dist2(s.x(st.v[0]), s.x(st.v[2]), s.x(st.v[3]));
+    default: return pp_dist2(s.x(st.v[0]), s.x(st.v[2]));
+    }
+}
+static inline bool mollified(Kind k) { return k == K_EE_M || k == K_PE_M || k == K_PP_M; }
+
+// ======================================================================= Compute_Barrier (IPC.h:742-941)
+// returns 0, or 1 if a non-positive distance was met (reference: printf + exit(-1))
+static int compute_barrier(const Scene& s, bool elastic, const std::vector<I4>& cs, const std::vector<D2>& info,
+    double dHat2, const double* kappa, double thickness, double& E)
+{
+    if (elastic) thickness = 0;
+    const double thickness2 = thickness * thickness;
+    dHat2 += 2 * std::sqrt(dHat2) * thickness;
+    std::vector<double> barrierV(cs.size());
+    for (size_t cI = 0; cI < cs.size(); ++cI) {
+        const Stencil st = decode(cs[cI]);
+        double dist2 = stencil_dist2(s, st);
+        dist2 -= thickness2;
+        if (dist2 <= 0) return 1;
+        double b = barrier(elastic, dist2, dHat2, kappa);
+        if (mollified(st.kind)) {
+            const double eps_x = ee_mollifier_threshold(s.x0(st.v[0]), s.x0(st.v[1]), s.x0(st.v[2]), s.x0(st.v[3]));
+            b *= ee_mollifier(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), eps_x);
+        }
+        else if (cs[cI][0] < 0 && cs[cI][3] < -1) b *= -cs[cI][3];
+        b *= info[cI][0];
+        barrierV[cI] = b;
+    }
+    E += std::accumulate(barrierV.begin(), barrierV.end(), 0.0);
+    return 0;
+}
+
+// ======================================================================= Compute_Barrier_Gradient (IPC.h:943-1256)
+// g: 3*nV, accumulated in place (nodeAttr.g +=)
+static void compute_barrier_gradient(const Scene& s, bool elastic, const std::vector<I4>& cs, const std::vector<D2>& info,
+    double dHat2, const double* kappa, double thickness, double* g)
+{
+    if (elastic) thickness = 0;
+    const double thickness2 = thickness * thickness;
+    dHat2 += 2 * std::sqrt(dHat2) * thickness;
+    for (size_t cI = 0; cI < cs.size(); ++cI) {
+        const Stencil st = decode(cs[cI]);
+        const double w = info[cI][0];
+        const double dist2 = stencil_dist2(s, st) - thickness2;
+        const double bG = barrier_gradient(elastic, dist2, dHat2, kappa);
+        double dg[12];
+        auto add = [&](int slot, const double* v3, double sc) {
+            double* o = g + 3 * st.v[slot];
+            o[0] += sc * v3[0]; o[1] += sc * v3[1]; o[2] += sc * v3[2];
+        };
+        if (!mollified(st.kind)) {
+            int nb = 0;
+            switch (st.kind) {
+            case K_PT: pt_grad(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), dg); nb = 4; break;
+            case K_EE: ee_grad(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), dg); nb = 4; break;
+            case K_PE: pe_grad(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), dg); nb = 3; break;
+            default: pp_grad(s.x(st.v[0]), s.x(st.v[1]), dg); nb = 2; break;
+            }
+            const double sc = st.mult * w * bG; // IPC.h:1202,1227,1249
+            for (int k = 0; k < nb; ++k) add(k, dg + 3 * k, sc);
+        }
+        else {
+            const V3 a0 = s.x(st.v[0]), a1 = s.x(st.v[1]), b0 = s.x(st.v[2]), b1 = s.x(st.v[3]);
+            const double b = barrier(elastic, dist2, dHat2, kappa);
+            const double eps_x = ee_mollifier_threshold(s.x0(st.v[0]), s.x0(st.v[1]), s.x0(st.v[2]), s.x0(st.v[3]));
+            const double e = ee_mollifier(a0, a1, b0, b1, eps_x);
+            double eg[12];
+            ee_mollifier_grad(a0, a1, b0, b1, eps_x, eg);
+            for (int k = 0; k < 4; ++k) add(k, eg + 3 * k, w * b);
+            if (st.kind == K_EE_M) { // IPC.h:1081
+                ee_grad(a0, a1, b0, b1, dg);
+                for (int k = 0; k < 4; ++k) add(k, dg + 3 * k, w * e * bG);
+            }
+            else if (st.kind == K_PE_M) { // IPC.h:1122-1130: rows {0,2,3}
+                pe_grad(a0, b0, b1, dg);
+                add(0, dg, e * w * bG); add(2, dg + 3, e * w * bG); add(3, dg + 6, e * w * bG);
+            }
+            else { // IPC.h:1167-1174: rows {0,2}
+                pp_grad(a0, b0, dg);
+                add(0, dg, e * w * bG); add(2, dg + 3, e * w * bG);
+            }
+        }
+    }
+}
+
+// ======================================================================= Compute_Barrier_Hessian (IPC.h:1258-1731)
+struct Triplet { int row, col; double val; };
+
+static inline int block_dim(const I4& c) { return (c[0] >= 0 || c[3] >= 0) ? 12 : (c[2] >= 0 ? 9 : 6); }
+
+static void stencil_hessian(const Scene& s, bool elastic, const I4& c, double w, double dHat2, const double* kappa,
+    double thickness2, bool projectSPD, double* H /*n*n*/, int* vids, int& nb)
+{
+    const Stencil st = decode(c);
+    const double dist2 = stencil_dist2(s, st) - thickness2;
+    const double bG = barrier_gradient(elastic, dist2, dHat2, kappa);
+    const double bH = barrier_hessian(elastic, dist2, dHat2, kappa);
+    double dg[12], dH[144];
+    if (!mollified(st.kind)) {
+        switch (st.kind) {
+        case K_PT: nb = 4; pt_grad(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), dg);
+            pt_hess(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), dH); break;
+        case K_EE: nb = 4; ee_grad(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), dg);
+            ee_hess(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), s.x(st.v[3]), dH); break;
+        case K_PE: nb = 3; pe_grad(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), dg);
+            pe_hess(s.x(st.v[0]), s.x(st.v[1]), s.x(st.v[2]), dH); break;
+        default: nb = 2; pp_grad(s.x(st.v[0]), s.x(st.v[1]), dg); pp_hess(s.x(st.v[0]), s.x(st.v[1]), dH); break;
+        }
+        const int n = 3 * nb;
+        const double m = st.mult; // IPC.h:1640-1642: ((m bH) g) g^T + (m bG) H
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) H[i * n + j] = (((m * bH) * dg[i]) * dg[j] + (m * bG) * dH[i * n + j]) * w;
+        for (int k = 0; k < nb; ++k) vids[k] = st.v[k];
+        if (projectSPD) make_pd(n, H);
+        return;
+    }
+    nb = 4;
+    for (int k = 0; k < 4; ++k) vids[k] = st.v[k];
+    const V3 a0 = s.x(st.v[0]), a1 = s.x(st.v[1]), b0 = s.x(st.v[2]), b1 = s.x(st.v[3]);
+    const double b = barrier(elastic, dist2, dHat2, kappa);
+    const double eps_x = ee_mollifier_threshold(s.x0(st.v[0]), s.x0(st.v[1]), s.x0(st.v[2]), s.x0(st.v[3]));
+    const double e = ee_mollifier(a0, a1, b0, b1, eps_x);
+    double eg[12], eH[144];
+    ee_mollifier_grad(a0, a1, b0, b1, eps_x, eg);
+    ee_mollifier_hess(a0, a1, b0, b1, eps_x, eH);
+    // embed the distance gradient / Hessian into the 12-dof (ea0,ea1,eb0,eb1) frame
+    double G[12] = {0}, K[144] = {0};
+    int rows[4], nrow;
+    if (st.kind == K_EE_M) {
+        ee_grad(a0, a1, b0, b1, dg); ee_hess(a0, a1, b0, b1, dH);
+        nrow = 4; rows[0] = 0; rows[1] = 1; rows[2] = 2; rows[3] = 3;
+    }
+    else if (st.kind == K_PE_M) { // IPC.h:1526-1537
+        pe_grad(a0, b0, b1, dg); pe_hess(a0, b0, b1, dH);
+        nrow = 3; rows[0] = 0; rows[1] = 2; rows[2] = 3;
+    }
+    else { // IPC.h:1588-1599
+        pp_grad(a0, b0, dg); pp_hess(a0, b0, dH);
+        nrow = 2; rows[0] = 0; rows[1] = 2;
+    }
+    const int nn = 3 * nrow;
+    for (int I = 0; I < nrow; ++I)
+        for (int r = 0; r < 3; ++r) {
+            G[3 * rows[I] + r] = dg[3 * I + r];
+            for (int J = 0; J < nrow; ++J)
+                for (int cc = 0; cc < 3; ++cc) K[(3 * rows[I] + r) * 12 + 3 * rows[J] + cc] = dH[(3 * I + r) * nn + 3 * J + cc];
+        }
+    // IPC.h:1472-1475: bG (G eg^T + eg G^T) + b eH + e bH G G^T + e bG K, times w
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j)
+            H[i * 12 + j] = (bG * (G[i] * eg[j] + eg[i] * G[j]) + b * eH[i * 12 + j] + (e * bH * G[i]) * G[j] + e * bG * K[i * 12 + j]) * w;
+    if (projectSPD) make_pd(12, H);
+}
+
+static void compute_barrier_hessian(const Scene& s, bool elastic, const std::vector<I4>& cs, const std::vector<D2>& info,
+    double dHat2, const double* kappa, double thickness, bool projectSPD, std::vector<Triplet>& triplets)
+{
+    if (elastic) thickness = 0;
+    const double thickness2 = thickness * thickness;
+    dHat2 += 2 * std::sqrt(dHat2) * thickness;
+    std::vector<size_t> start(cs.size());
+    size_t cur = triplets.size();
+    for (size_t cI = 0; cI < cs.size(); ++cI) { // IPC.h:1370-1388
+        start[cI] = cur;
+        const int n = block_dim(cs[cI]);
+        cur += (size_t)n * n;
+    }
+    triplets.resize(cur);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long cI = 0; cI < (long)cs.size(); ++cI) {
+        double H[144];
+        int vids[4], nb;
+        stencil_hessian(s, elastic, cs[cI], info[cI][0], dHat2, kappa, thickness2, projectSPD, H, vids, nb);
+        const int n = 3 * nb;
+        Triplet* out = triplets.data() + start[cI];
+        for (int i = 0; i < nb; ++i)
+            for (int j = 0; j < nb; ++j)
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        out[(i * 3 + a) * n + j * 3 + b] = Triplet{vids[i] * 3 + a, vids[j] * 3 + b, H[(i * 3 + a) * n + j * 3 + b]};
+    }
+}
+
+// ======================================================================= ACCD (Math/Distance/CCD.h:279-483)
+// CCD.h:279-328
+static bool pt_accd(V3 p, V3 t0, V3 t1, V3 t2, V3 dp, V3 dt0, V3 dt1, V3 dt2, double eta, double thickness, double& toc)
+{
+    const V3 mov = (((dt0 + dt1) + dt2) + dp) / 4;
+    dt0 = dt0 - mov; dt1 = dt1 - mov; dt2 = dt2 - mov; dp = dp - mov;
+    const double maxDispMag = std::sqrt(norm2(dp)) + std::sqrt(std::max(std::max(norm2(dt0), norm2(dt1)), norm2(dt2)));
+    if (maxDispMag == 0) return false;
+    double dist2_cur = pt_dist2_unclassified(p, t0, t1, t2);
+    double dist_cur = std::sqrt(dist2_cur);
+    const double gap = eta * (dist2_cur - thickness * thickness) / (dist_cur + thickness);
+    const double toc_prev = toc;
+    toc = 0;
+    while (true) {
+        const double tocLowerBound = (1 - eta) * (dist2_cur - thickness * thickness) / ((dist_cur + thickness) * maxDispMag);
+        p = p + tocLowerBound * dp; t0 = t0 + tocLowerBound * dt0; t1 = t1 + tocLowerBound * dt1; t2 = t2 + tocLowerBound * dt2;
+        dist2_cur = pt_dist2_unclassified(p, t0, t1, t2);
+        dist_cur = std::sqrt(dist2_cur);
+        if (toc && ((dist2_cur - thickness * thickness) / (dist_cur + thickness) < gap)) break;
+        toc += tocLowerBound;
+        if (toc > toc_prev) return false;
+    }
+    return true;
+}
+// CCD.h:330-395
+static bool ee_accd(V3 ea0, V3 ea1, V3 eb0, V3 eb1, V3 dea0, V3 dea1, V3 deb0, V3 deb1, double eta, double thickness, double& toc)
+{
+    const V3 mov = (((dea0 + dea1) + deb0) + deb1) / 4;
+    dea0 = dea0 - mov; dea1 = dea1 - mov; deb0 = deb0 - mov; deb1 = deb1 - mov;
+    const double maxDispMag = std::sqrt(std::max(norm2(dea0), norm2(dea1))) + std::sqrt(std::max(norm2(deb0), norm2(deb1)));
+    if (maxDispMag == 0) return false;
+    auto min_endpoint = [&]() {
+        return std::min(std::min(norm2(ea0 - eb0), norm2(ea0 - eb1)), std::min(norm2(ea1 - eb0), norm2(ea1 - eb1)));
+    };
+    double dist2_cur = ee_dist2_unclassified(ea0, ea1, eb0, eb1);
+    double dFunc = dist2_cur - thickness * thickness;
+    if (dFunc <= 0) { dist2_cur = min_endpoint(); dFunc = dist2_cur - thickness * thickness; }
+    double dist_cur = std::sqrt(dist2_cur);
+    const double gap = eta * dFunc / (dist_cur + thickness);
+    const double toc_prev = toc;
+    toc = 0;
+    while (true) {
+        const double tocLowerBound = (1 - eta) * dFunc / ((dist_cur + thickness) * maxDispMag);
+        ea0 = ea0 + tocLowerBound * dea0; ea1 = ea1 + tocLowerBound * dea1; eb0 = eb0 + tocLowerBound * deb0; eb1 = eb1 + tocLowerBound * deb1;
+        dist2_cur = ee_dist2_unclassified(ea0, ea1, eb0, eb1);
+        dFunc = dist2_cur - thickness * thickness;
+        if (dFunc <= 0) { dist2_cur = min_endpoint(); dFunc = dist2_cur - thickness * thickness; }
+        dist_cur = std::sqrt(dist2_cur);
+        if (toc && (dFunc / (dist_cur + thickness) < gap)) break;
+        toc += tocLowerBound;
+        if (toc > toc_prev) return false;
+    }
+    return true;
+}
+// CCD.h:397-441
+static bool pe_accd(V3 p, V3 e0, V3 e1, V3 dp, V3 de0, V3 de1, double eta, double thickness, double& toc)
+{
+    const V3 mov = ((dp + de0) + de1) / 3;
+    de0 = de0 - mov; de1 = de1 - mov; dp = dp - mov;
+    const double maxDispMag = std::sqrt(norm2(dp)) + std::sqrt(std::max(norm2(de0), norm2(de1)));
+    if (maxDispMag == 0) return false;
+    double dist2_cur = pe_dist2_unclassified(p, e0, e1);
+    double dist_cur = std::sqrt(dist2_cur);
+    const double gap = eta * (dist2_cur - thickness * thickness) / (dist_cur + thickness);
+    const double toc_prev = toc;
+    toc = 0;
+    while (true) {
+        const double tocLowerBound = (1 - eta) * (dist2_cur - thickness * thickness) / ((dist_cur + thickness) * maxDispMag);
+        p = p + tocLowerBound * dp; e0 = e0 + tocLowerBound * de0; e1 = e1 + tocLowerBound * de1;
+        dist2_cur = pe_dist2_unclassified(p, e0, e1);
+        dist_cur = std::sqrt(dist2_cur);
+        if (toc && (dist2_cur - thickness * thickness) / (dist_cur + thickness) < gap) break;
+        toc += tocLowerBound;
+        if (toc > toc_prev) return false;
+    }
+    return true;
+}
+// CCD.h:443-483
+static bool pp_accd(V3 p0, V3 p1, V3 dp0, V3 dp1, double eta, double thickness, double& toc)
+{
+    const V3 mov = (dp0 + dp1) / 2;
+    dp1 = dp1 - mov; dp0 = dp0 - mov;
+    const double maxDispMag = std::sqrt(norm2(dp0)) + std::sqrt(norm2(dp1));
+    if (maxDispMag == 0) return false;
+    double dist2_cur = pp_dist2(p0, p1);
+    double dist_cur = std::sqrt(dist2_cur);
+    const double gap = eta * (dist2_cur - thickness * thickness) / (dist_cur + thickness);
+    const double toc_prev = toc;
+    toc = 0;
+    while (true) {
+        const double tocLowerBound = (1 - eta) * (dist2_cur - thickness * thickness) / ((dist_cur + thickness) * maxDispMag);
+        p0 = p0 + tocLowerBound * dp0; p1 = p1 + tocLowerBound * dp1;
+        dist2_cur = pp_dist2(p0, p1);
+        dist_cur = std::sqrt(dist2_cur);
+        if (toc && (dist2_cur - thickness * thickness) / (dist_cur + thickness) < gap) break;
+        toc += tocLowerBound;
+        if (toc > toc_prev) return false;
+    }
+    return true;
+}
+
+// ======================================================================= Compute_Intersection_Free_StepSize (IPC.h:1879-2244)
+// returns 0 ok, 2 if a PT pair produced largestAlpha == 0 (reference dumps coordinates and exit(-1))
+static int compute_step_size(const Scene& s, bool elastic, const double* searchDir, double thickness, bool use_hash,
+    double& stepSize, Timers* tm, bool quiet, long* nPairs)
+{
+    if (elastic) thickness = 0;
+    SpatialHash sh;
+    double t0 = now_s();
+    if (use_hash) sh.build_swept(s, searchDir, stepSize, 1.0, thickness, quiet);
+    double t1 = now_s();
+    int err = 0;
+    long pairs = 0;
+    auto dir = [&](int v) { return V3(searchDir + 3 * v); };
+
+    std::vector<double> alphaPT(s.nBN);
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : pairs)
+    for (int svI = 0; svI < s.nBN; ++svI) {
+        const int vI = s.BN[svI];
+        const V3 p = s.x(vI), dp = dir(vI);
+        alphaPT[svI] = stepSize;
+        std::unordered_set<int> sP, sE, sT;
+        if (use_hash) sh.query_point_for_primitives(svI, sP, sE, sT);
+        auto visit_tri = [&](int sfI) {
+            const int* t = s.BT + 3 * sfI;
+            if (!pt_pair_ok(s, vI, t)) return;
+            const V3 t0 = s.x(t[0]), t1 = s.x(t[1]), t2 = s.x(t[2]);
+            const V3 dt0 = dir(t[0]), dt1 = dir(t[1]), dt2 = dir(t[2]);
+            if (!pt_ccd_broadphase(p, t0, t1, t2, dp, dt0, dt1, dt2, thickness)) return;
+            ++pairs;
+            double largestAlpha = alphaPT[svI];
+            if (pt_accd(p, t0, t1, t2, dp, dt0, dt1, dt2, 0.1, thickness, largestAlpha))
+                if (alphaPT[svI] > largestAlpha) alphaPT[svI] = largestAlpha;
+            if (largestAlpha == 0) {
+#pragma omp atomic write
+                err = 2;
+            }
+        };
+        if (use_hash) for (int sfI : sT) visit_tri(sfI);
+        else for (int sfI = 0; sfI < s.nBT; ++sfI) visit_tri(sfI);
+
+        if (svI >= s.codim1) { // particle vs rod edges and later points (IPC.h:2098-2163)
+            auto visit_edge = [&](int eI) {
+                if (eI < s.nBE - s.nRod) return;
+                const int* e = s.BE + 2 * eI;
+                if (vI == e[0] || vI == e[1] || (s.DBC[vI] && s.DBC[e[0]] && s.DBC[e[1]])) return;
+                const V3 e0 = s.x(e[0]), e1 = s.x(e[1]), de0 = dir(e[0]), de1 = dir(e[1]);
+                if (!pe_ccd_broadphase(p, e0, e1, dp, de0, de1, thickness)) return;
+                ++pairs;
+                double largestAlpha = alphaPT[svI];
+                if (pe_accd(p, e0, e1, dp, de0, de1, 0.1, thickness, largestAlpha))
+                    if (alphaPT[svI] > largestAlpha) alphaPT[svI] = largestAlpha;
+            };
+            if (use_hash) for (int eI : sE) visit_edge(eI);
+            else for (int eI = 0; eI < s.nBE; ++eI) visit_edge(eI);
+            auto visit_point = [&](int svJ) {
+                if (svJ <= svI) return;
+                const int vJ = s.BN[svJ];
+                if (s.DBC[vI] && s.DBC[vJ]) return;
+                const V3 pJ = s.x(vJ), dpJ = dir(vJ);
+                if (!pp_ccd_broadphase(p, pJ, dp, dpJ, thickness)) return;
+                ++pairs;
+                double largestAlpha = alphaPT[svI];
+                if (pp_accd(p, pJ, dp, dpJ, 0.1, thickness, largestAlpha))
+                    if (alphaPT[svI] > largestAlpha) alphaPT[svI] = largestAlpha;
+            };
+            if (use_hash) for (int svJ : sP) visit_point(svJ);
+            else for (int svJ = 0; svJ < s.nBN; ++svJ) visit_point(svJ);
+        }
+    }
+    if (s.nBN) stepSize = std::min(stepSize, *std::min_element(alphaPT.begin(), alphaPT.end()));
+    double t2 = now_s();
+
+    std::vector<double> alphaEE(s.nBE);
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : pairs)
+    for (int eI = 0; eI < s.nBE; ++eI) {
+        const int* a = s.BE + 2 * eI;
+        const V3 ea0 = s.x(a[0]), ea1 = s.x(a[1]), dea0 = dir(a[0]), dea1 = dir(a[1]);
+        alphaEE[eI] = stepSize;
+        auto visit = [&](int eJ) {
+            const int* b = s.BE + 2 * eJ;
+            if (!ee_pair_ok(s, eI, eJ, a, b)) return;
+            const V3 eb0 = s.x(b[0]), eb1 = s.x(b[1]), deb0 = dir(b[0]), deb1 = dir(b[1]);
+            if (!ee_ccd_broadphase(ea0, ea1, eb0, eb1, dea0, dea1, deb0, deb1, thickness)) return;
+            ++pairs;
+            double largestAlpha = alphaEE[eI];
+            if (ee_accd(ea0, ea1, eb0, eb1, dea0, dea1, deb0, deb1, 0.1, thickness, largestAlpha))
+                if (alphaEE[eI] > largestAlpha) alphaEE[eI] = largestAlpha;
+        };
+        if (use_hash) {
+            std::unordered_set<int> sE;
+            sh.query_edge_for_edges(eI, sE);
+            for (int eJ : sE) visit(eJ);
+        }
+        else for (int eJ = eI + 1; eJ < s.nBE; ++eJ) visit(eJ);
+    }
+    if (s.nBE) stepSize = std::min(stepSize, *std::min_element(alphaEE.begin(), alphaEE.end()));
+    double t3 = now_s();
+    if (tm) { tm->t[0] = t1 - t0; tm->t[1] = t2 - t1; tm->t[2] = t3 - t2; }
+    if (nPairs) *nPairs = pairs;
+    return err;
+}
+
+// ======================================================================= Compute_Min_Dist2 (IPC.h:2246-2388)
+static void compute_min_dist2(const Scene& s, const std::vector<I4>& cs, double thickness, std::vector<double>& dist2, double& minDist2)
+{
+    dist2.resize(cs.size());
+    for (size_t cI = 0; cI < cs.size(); ++cI) dist2[cI] = stencil_dist2(s, decode(cs[cI]));
+    minDist2 = *std::min_element(dist2.begin(), dist2.end());
+    minDist2 -= thickness * thickness;
+}
+
+} // namespace cipc_oracle
+
+// ======================================================================= C API (ctypes)
+using namespace cipc_oracle;
+
+namespace {
+struct SceneHolder { Scene s; };
+std::vector<I4> g_cs;
+std::vector<D2> g_info;
+std::vector<Triplet> g_trip;
+Timers g_tm;
+
+void set_cs(const int* cs, const double* info, int n, std::vector<I4>& c, std::vector<D2>& w)
+{
+    c.resize(n); w.resize(n);
+    for (int i = 0; i < n; ++i) {
+        c[i] = {cs[4 * i], cs[4 * i + 1], cs[4 * i + 2], cs[4 * i + 3]};
+        w[i] = {info[2 * i], info[2 * i + 1]};
+    }
+}
+} // namespace
+
+extern "C" {
+
+void* oracle_scene_create(int nV, const double* X, const double* X0, int nBN, const int* BN, int nBE, const int* BE,
+    int nBT, const int* BT, int nRod, int codim0, int codim1, const uint8_t* DBC, int nnxPairs, const int* nnxPairList,
+    const double* BNArea, const double* BEArea, const double* BTArea)
+{
+    SceneHolder* h = new SceneHolder();
+    Scene& s = h->s;
+    s.nV = nV; s.X = X; s.X0 = X0; s.nBN = nBN; s.BN = BN; s.nBE = nBE; s.BE = BE; s.nBT = nBT; s.BT = BT;
+    s.nRod = nRod; s.codim0 = codim0; s.codim1 = codim1; s.DBC = DBC;
+    for (int i = 0; i < nnxPairs; ++i) s.NNX[nnxPairList[2 * i]].insert(nnxPairList[2 * i + 1]);
+    s.BNArea = BNArea; s.BEArea = BEArea; s.BTArea = BTArea;
+    return h;
+}
+void oracle_scene_set_X(void* h, const double* X) { ((SceneHolder*)h)->s.X = X; }
+void oracle_scene_destroy(void* h) { delete (SceneHolder*)h; }
+int oracle_num_threads()
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+// returns number of constraints; fetch with oracle_fetch_constraints
+int oracle_constraint_set(void* h, int elastic, double dHat2, double thickness, int use_hash, double* timers4)
+{
+    compute_constraint_set(((SceneHolder*)h)->s, elastic != 0, dHat2, thickness, use_hash != 0, g_cs, g_info, &g_tm, true);
+    if (timers4) for (int i = 0; i < 4; ++i) timers4[i] = g_tm.t[i];
+    return (int)g_cs.size();
+}
+void oracle_fetch_constraints(int* cs, double* info)
+{
+    for (size_t i = 0; i < g_cs.size(); ++i) {
+        for (int k = 0; k < 4; ++k) cs[4 * i + k] = g_cs[i][k];
+        info[2 * i] = g_info[i][0]; info[2 * i + 1] = g_info[i][1];
+    }
+}
+int oracle_barrier(void* h, int elastic, const int* cs, const double* info, int n, double dHat2, const double* kappa,
+    double thickness, double* E)
+{
+    std::vector<I4> c; std::vector<D2> w;
+    set_cs(cs, info, n, c, w);
+    return compute_barrier(((SceneHolder*)h)->s, elastic != 0, c, w, dHat2, kappa, thickness, *E);
+}
+void oracle_barrier_gradient(void* h, int elastic, const int* cs, const double* info, int n, double dHat2,
+    const double* kappa, double thickness, double* g)
+{
+    std::vector<I4> c; std::vector<D2> w;
+    set_cs(cs, info, n, c, w);
+    compute_barrier_gradient(((SceneHolder*)h)->s, elastic != 0, c, w, dHat2, kappa, thickness, g);
+}
+// returns number of triplets appended; fetch with oracle_fetch_triplets
+long oracle_barrier_hessian(void* h, int elastic, const int* cs, const double* info, int n, double dHat2,
+    const double* kappa, double thickness, int projectSPD)
+{
+    std::vector<I4> c; std::vector<D2> w;
+    set_cs(cs, info, n, c, w);
+    g_trip.clear();
+    compute_barrier_hessian(((SceneHolder*)h)->s, elastic != 0, c, w, dHat2, kappa, thickness, projectSPD != 0, g_trip);
+    return (long)g_trip.size();
+}
+void oracle_fetch_triplets(int* rows, int* cols, double* vals)
+{
+    for (size_t i = 0; i < g_trip.size(); ++i) { rows[i] = g_trip[i].row; cols[i] = g_trip[i].col; vals[i] = g_trip[i].val; }
+}
+int oracle_step_size(void* h, int elastic, const double* searchDir, double thickness, int use_hash, double* stepSize,
+    double* timers3, long* nPairs)
+{
+    int err = compute_step_size(((SceneHolder*)h)->s, elastic != 0, searchDir, thickness, use_hash != 0, *stepSize, &g_tm, true, nPairs);
+    if (timers3) for (int i = 0; i < 3; ++i) timers3[i] = g_tm.t[i];
+    return err;
+}
+void oracle_min_dist2(void* h, const int* cs, int n, double thickness, double* dist2, double* minDist2)
+{
+    std::vector<I4> c(n);
+    for (int i = 0; i < n; ++i) c[i] = {cs[4 * i], cs[4 * i + 1], cs[4 * i + 2], cs[4 * i + 3]};
+    std::vector<double> d;
+    compute_min_dist2(((SceneHolder*)h)->s, c, thickness, d, *minDist2);
+    std::memcpy(dist2, d.data(), sizeof(double) * n);
+}
+
+// ---- per-stencil probes used by the unit tests (kind: 0 PP, 1 PE, 2 PT, 3 EE, 4 EE cross-norm^2)
+void oracle_dist_derivs(int kind, const double* x, double* d, double* g, double* H)
+{
+    const V3 a(x), b(x + 3), c(x + 6), e(x + 9);
+    switch (kind) {
+    case 0: *d = pp_dist2(a, b); pp_grad(a, b, g); pp_hess(a, b, H); break;
+    case 1: *d = pe_dist2(a, b, c); pe_grad(a, b, c, g); pe_hess(a, b, c, H); break;
+    case 2: *d = pt_dist2(a, b, c, e); pt_grad(a, b, c, e, g); pt_hess(a, b, c, e, H); break;
+    case 3: *d = ee_dist2(a, b, c, e); ee_grad(a, b, c, e, g); ee_hess(a, b, c, e, H); break;
+    default: *d = ee_cross_norm2(a, b, c, e); eecn2_grad(a, b, c, e, g); eecn2_hess(a, b, c, e, H); break;
+    }
+}
+void oracle_mollifier(const double* x, double eps_x, double* e, double* g, double* H)
+{
+    const V3 a(x), b(x + 3), c(x + 6), d(x + 9);
+    *e = ee_mollifier(a, b, c, d, eps_x);
+    ee_mollifier_grad(a, b, c, d, eps_x, g);
+    ee_mollifier_hess(a, b, c, d, eps_x, H);
+}
+int oracle_pt_type(const double* x) { return pt_type(V3(x), V3(x + 3), V3(x + 6), V3(x + 9)); }
+int oracle_ee_type(const double* x) { return ee_type(V3(x), V3(x + 3), V3(x + 6), V3(x + 9)); }
+int oracle_pe_type(const double* x) { double r; return pe_type(V3(x), V3(x + 3), V3(x + 6), r); }
+double oracle_dist2_unclassified(int kind, const double* x)
+{
+    if (kind == 1) return pe_dist2_unclassified(V3(x), V3(x + 3), V3(x + 6));
+    if (kind == 2) return pt_dist2_unclassified(V3(x), V3(x + 3), V3(x + 6), V3(x + 9));
+    return ee_dist2_unclassified(V3(x), V3(x + 3), V3(x + 6), V3(x + 9));
+}
+// kind: 0 PP, 1 PE, 2 PT, 3 EE.  x = positions (4 x 3), dx = directions (4 x 3)
+int oracle_accd(int kind, const double* x, const double* dx, double eta, double thickness, double* toc)
+{
+    const V3 a(x), b(x + 3), c(x + 6), d(x + 9), da(dx), db(dx + 3), dc(dx + 6), dd(dx + 9);
+    switch (kind) {
+    case 0: return pp_accd(a, b, da, db, eta, thickness, *toc);
+    case 1: return pe_accd(a, b, c, da, db, dc, eta, thickness, *toc);
+    case 2: return pt_accd(a, b, c, d, da, db, dc, dd, eta, thickness, *toc);
+    default: return ee_accd(a, b, c, d, da, db, dc, dd, eta, thickness, *toc);
+    }
+}
+void oracle_barrier_fn(int elastic, double d, double dHat, const double* kappa, double* out3)
+{
+    out3[0] = barrier(elastic != 0, d, dHat, kappa);
+    out3[1] = barrier_gradient(elastic != 0, d, dHat, kappa);
+    out3[2] = barrier_hessian(elastic != 0, d, dHat, kappa);
+}
+void oracle_make_pd(int n, double* H) { make_pd(n, H); }
+void oracle_sym_eig(int n, const double* A, double* V, double* d) { sym_eig(n, A, V, d); }
+
+} // extern "C"

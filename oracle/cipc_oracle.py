@@ -1,0 +1,242 @@
+"""TEST INFRASTRUCTURE -- ctypes front-end of the CPU oracle (oracle/cipc_oracle.cpp) and of
+oracle/_ref (the reference's own distance headers compiled against a stub Eigen).
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
+The product path (codim-ipc_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def build(force=False):
+    """Compile the oracle (always possible: g++ only) and, if /root/reference exists, oracle/_ref."""
+    so = os.path.join(_HERE, "libcipc_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("cipc_oracle.cpp", "geom.h", "derivs.h", "eig.h")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "libcipc_oracle.so"], stdout=subprocess.DEVNULL)
+    ref_so = os.path.join(_HERE, "_ref", "libcipc_refdist.so")
+    if os.path.isdir("/root/reference/Library/Math/Distance") and (force or not os.path.exists(ref_so)):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "libcipc_oracle.so"))
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_barrier_hessian.restype = C.c_long
+        L.oracle_dist2_unclassified.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def ref():
+    """The reference-compiled probes, or None when oracle/_ref was never built."""
+    global _REF
+    if _REF is None:
+        p = os.path.join(_HERE, "_ref", "libcipc_refdist.so")
+        if not os.path.exists(p):
+            build()
+        if not os.path.exists(p):
+            return None
+        R = C.CDLL(p)
+        R.ref_dist2_unclassified.restype = C.c_double
+        R.ref_mollifier_threshold.restype = C.c_double
+        _REF = R
+    return _REF
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+class OracleScene:
+    """Holds contiguous copies of a scene dict (see codim-ipc_b200 scenes) for the oracle."""
+
+    def __init__(self, sc):
+        L = lib()
+        self.X = np.ascontiguousarray(sc["X"], dtype=np.float64)
+        self.X0 = np.ascontiguousarray(sc["X0"], dtype=np.float64)
+        self.BN = np.ascontiguousarray(sc["BN"], dtype=np.int32)
+        self.BE = np.ascontiguousarray(sc["BE"], dtype=np.int32).reshape(-1, 2)
+        self.BT = np.ascontiguousarray(sc["BT"], dtype=np.int32).reshape(-1, 3)
+        self.DBC = np.ascontiguousarray(sc["DBC"], dtype=np.uint8)
+        self.nnx = np.ascontiguousarray(sc.get("NNX", np.zeros((0, 2), np.int32)), dtype=np.int32).reshape(-1, 2)
+        self.nV = self.X.shape[0]
+        self.areas = [np.ascontiguousarray(sc[k], dtype=np.float64) if sc.get(k) is not None else None
+                      for k in ("BNArea", "BEArea", "BTArea")]
+        ap = [(_dp(a) if a is not None else None) for a in self.areas]
+        cd = sc.get("codim", (len(self.BN), len(self.BN)))
+        self.h = C.c_void_p(L.oracle_scene_create(
+            self.nV, _dp(self.X), _dp(self.X0), len(self.BN), _ip(self.BN), len(self.BE), _ip(self.BE),
+            len(self.BT), _ip(self.BT), int(sc.get("nRod", 0)), int(cd[0]), int(cd[1]),
+            self.DBC.ctypes.data_as(C.POINTER(C.c_uint8)), len(self.nnx), _ip(self.nnx), ap[0], ap[1], ap[2]))
+
+    def set_X(self, X):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        lib().oracle_scene_set_X(self.h, _dp(self.X))
+
+    def __del__(self):
+        try:
+            lib().oracle_scene_destroy(self.h)
+        except Exception:
+            pass
+
+    # ---- Compute_Constraint_Set
+    def constraint_set(self, dHat2, thickness, elastic=False, use_hash=True, timers=None):
+        L = lib()
+        tm = np.zeros(4)
+        n = L.oracle_constraint_set(self.h, int(elastic), C.c_double(dHat2), C.c_double(thickness), int(use_hash), _dp(tm))
+        cs = np.zeros((n, 4), np.int32)
+        info = np.zeros((n, 2), np.float64)
+        if n:
+            L.oracle_fetch_constraints(_ip(cs), _dp(info))
+        if timers is not None:
+            timers[:] = tm
+        return cs, info
+
+    # ---- Compute_Barrier (returns E added to E0)
+    def barrier(self, cs, info, dHat2, kappa, thickness, elastic=False, E0=0.0):
+        cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
+        kappa = np.ascontiguousarray(kappa, np.float64)
+        E = C.c_double(E0)
+        err = lib().oracle_barrier(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+                                   C.c_double(thickness), C.byref(E))
+        if err:
+            raise FloatingPointError("non-positive distance during barrier evaluation")
+        return E.value
+
+    def barrier_gradient(self, cs, info, dHat2, kappa, thickness, elastic=False, g=None):
+        cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
+        kappa = np.ascontiguousarray(kappa, np.float64)
+        if g is None:
+            g = np.zeros((self.nV, 3))
+        lib().oracle_barrier_gradient(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+                                      C.c_double(thickness), _dp(g))
+        return g
+
+    def barrier_hessian(self, cs, info, dHat2, kappa, thickness, projectSPD=True, elastic=False):
+        cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
+        kappa = np.ascontiguousarray(kappa, np.float64)
+        L = lib()
+        n = L.oracle_barrier_hessian(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+                                     C.c_double(thickness), int(projectSPD))
+        rows = np.zeros(n, np.int32); cols = np.zeros(n, np.int32); vals = np.zeros(n)
+        if n:
+            L.oracle_fetch_triplets(_ip(rows), _ip(cols), _dp(vals))
+        return rows, cols, vals
+
+    def step_size(self, searchDir, thickness, stepSize=1.0, elastic=False, use_hash=True, timers=None):
+        p = np.ascontiguousarray(searchDir, np.float64)
+        a = C.c_double(stepSize)
+        tm = np.zeros(3)
+        npairs = C.c_long(0)
+        err = lib().oracle_step_size(self.h, int(elastic), _dp(p), C.c_double(thickness), int(use_hash), C.byref(a), _dp(tm),
+                                     C.byref(npairs))
+        if err:
+            raise FloatingPointError("ACCD returned a zero step (reference would exit(-1))")
+        if timers is not None:
+            timers[:] = tm
+        self.last_pairs = npairs.value
+        return a.value
+
+    def min_dist2(self, cs, thickness):
+        cs = np.ascontiguousarray(cs, np.int32)
+        d = np.zeros(len(cs))
+        m = C.c_double(0)
+        lib().oracle_min_dist2(self.h, _ip(cs), len(cs), C.c_double(thickness), _dp(d), C.byref(m))
+        return d, m.value
+
+
+# ---- per-stencil probes (kind: 0 PP, 1 PE, 2 PT, 3 EE, 4 EE cross-norm^2)
+_NDOF = {0: 6, 1: 9, 2: 12, 3: 12, 4: 12}
+
+
+def _x12(x):
+    v = np.zeros(12)
+    x = np.asarray(x, np.float64).ravel()
+    v[:len(x)] = x
+    return v
+
+
+def dist_derivs(kind, x, which="oracle"):
+    n = _NDOF[kind]
+    x = _x12(x)
+    d = C.c_double(0); g = np.zeros(12); H = np.zeros(144)
+    fn = lib().oracle_dist_derivs if which == "oracle" else ref().ref_dist_derivs
+    fn(kind, _dp(x), C.byref(d), _dp(g), _dp(H))
+    return d.value, g[:n].copy(), H[:n * n].reshape(n, n).copy()
+
+
+def mollifier(x, eps_x, which="oracle"):
+    x = _x12(x)
+    e = C.c_double(0); g = np.zeros(12); H = np.zeros(144)
+    fn = lib().oracle_mollifier if which == "oracle" else ref().ref_mollifier
+    fn(_dp(x), C.c_double(eps_x), C.byref(e), _dp(g), _dp(H))
+    return e.value, g, H.reshape(12, 12)
+
+
+def dist_type(kind, x, which="oracle"):
+    x = _x12(x)
+    name = {1: "pe_type", 2: "pt_type", 3: "ee_type"}[kind]
+    fn = getattr(lib(), "oracle_" + name) if which == "oracle" else getattr(ref(), "ref_" + name)
+    return fn(_dp(x))
+
+
+def dist2_unclassified(kind, x, which="oracle"):
+    x = _x12(x)
+    fn = lib().oracle_dist2_unclassified if which == "oracle" else ref().ref_dist2_unclassified
+    return fn(kind, _dp(x))
+
+
+def accd(kind, x, dx, eta, thickness, toc, which="oracle"):
+    x = _x12(x); dx = _x12(dx)
+    t = C.c_double(toc)
+    fn = lib().oracle_accd if which == "oracle" else ref().ref_accd
+    ok = fn(kind, _dp(x), _dp(dx), C.c_double(eta), C.c_double(thickness), C.byref(t))
+    return bool(ok), t.value
+
+
+def barrier_fn(d, dHat, kappa, elastic=False, which="oracle"):
+    k = np.ascontiguousarray(kappa, np.float64)
+    out = np.zeros(3)
+    fn = lib().oracle_barrier_fn if which == "oracle" else ref().ref_barrier_fn
+    fn(int(elastic), C.c_double(d), C.c_double(dHat), _dp(k), _dp(out))
+    return out
+
+
+def make_pd(H):
+    H = np.ascontiguousarray(H, np.float64).copy()
+    lib().oracle_make_pd(H.shape[0], _dp(H))
+    return H
+
+
+def sym_eig(A):
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    V = np.zeros((n, n)); d = np.zeros(n)
+    lib().oracle_sym_eig(n, _dp(A), _dp(V), _dp(d))
+    return d, V
