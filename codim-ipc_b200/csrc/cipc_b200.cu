@@ -1,0 +1,1657 @@
+// cipc_b200.cu -- B200-native (sm_100a, fp64) C-IPC contact hot path behind the C ABI of
+// include/cipc_b200.h.  See DESIGN.md for the data layout and the per-kernel rooflines.
+//
+// Pipeline (one CUDA stream, everything resident in HBM):
+//   positions X / rest X0 / search dir P : double4 per node (32 B = one DRAM sector per gather)
+//   broad phase   : per-primitive integer voxel boxes -> (cell,kind | prim) entries -> LSD radix sort
+//                   -> per-cell kind ranges -> pair enumeration with the "min-corner" rule (each
+//                   overlapping pair is visited in exactly one cell) + topology filters + exact AABB test
+//   constraint set: closest-feature classification + d < dHat^2 per candidate, PP/PE de-duplication
+//                   through an index hash table, output in the reference's stencil encoding
+//   barrier       : E (tree reduction), g (fp64 atomics), H (12x12 / 9x9 / 6x6 blocks, PSD projection)
+//   step size     : swept voxel boxes mirroring SPATIAL_HASH.h:432-622, ACCD per pair, atomic min
+#include "../../include/cipc_b200.h"
+#include "geom.cuh"
+#include "eig.cuh"
+#include "prims.cuh"
+
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+namespace cg = cooperative_groups;
+
+namespace cipc {
+
+long g_launches = 0;
+
+// ===================================================================== device-side views
+struct Topo {
+    int nV, nBN, nBE, nBT, nRod, codim0, codim1;
+    const int* BN;
+    const int2* BE;
+    const int4* BT;
+    const uint8_t* flags; // bit0: DBC, bit1: node has NNExclusion entries
+    const int* v2sv;      // vertex -> (last) boundary-node slot, as SPATIAL_HASH.h:100 / :489
+    const u64* nnx;       // sorted (key<<32 | member)
+    int nNnx;
+};
+struct GridDesc {
+    double ox, oy, oz, inv; // cell = floor((x - o) * inv)
+    int gx, gy, gz;         // cells per axis (linear index = ix + gx*(iy + gy*iz))
+};
+
+__device__ __forceinline__ xv3 ldx(const double4* __restrict__ A, int v)
+{
+    const double4 q = A[v];
+    return xv3(xd(q.x), xd(q.y), xd(q.z));
+}
+__device__ __forceinline__ dv3 ldd(const double4* __restrict__ A, int v)
+{
+    const double4 q = A[v];
+    return dv3(q.x, q.y, q.z);
+}
+__device__ __forceinline__ bool nnx_has(const Topo& T, int v, int a)
+{
+    const u64 key = ((u64)(u32)v << 32) | (u32)a;
+    int lo = 0, hi = T.nNnx;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const u64 m = T.nnx[mid];
+        if (m < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo < T.nNnx && T.nnx[lo] == key;
+}
+// IPC.h:171-181 / :1984-1996
+__device__ __forceinline__ bool pt_pair_ok(const Topo& T, int vI, const int4& t)
+{
+    if (vI == t.x || vI == t.y || vI == t.z) return false;
+    const uint8_t fv = T.flags[vI];
+    if ((fv & 1) && (T.flags[t.x] & 1) && (T.flags[t.y] & 1) && (T.flags[t.z] & 1)) return false;
+    if ((fv & 2) && (nnx_has(T, vI, t.x) || nnx_has(T, vI, t.y) || nnx_has(T, vI, t.z))) return false;
+    return true;
+}
+// IPC.h:384-397 / :2202-2216
+__device__ __forceinline__ bool ee_pair_ok(const Topo& T, const int2& a, const int2& b)
+{
+    if (a.x == b.x || a.x == b.y || a.y == b.x || a.y == b.y) return false;
+    const uint8_t f0 = T.flags[a.x], f1 = T.flags[a.y];
+    if ((f0 & 1) && (f1 & 1) && (T.flags[b.x] & 1) && (T.flags[b.y] & 1)) return false;
+    if ((f0 & 2) && (nnx_has(T, a.x, b.x) || nnx_has(T, a.x, b.y))) return false;
+    if ((f1 & 2) && (nnx_has(T, a.y, b.x) || nnx_has(T, a.y, b.y))) return false;
+    return true;
+}
+
+// packed voxel coordinates: 21 bits per axis
+__device__ __forceinline__ u64 pack3(int x, int y, int z) { return (u64)(u32)x | ((u64)(u32)y << 21) | ((u64)(u32)z << 42); }
+__device__ __forceinline__ int ux(u64 p) { return (int)(p & 0x1fffffu); }
+__device__ __forceinline__ int uy(u64 p) { return (int)((p >> 21) & 0x1fffffu); }
+__device__ __forceinline__ int uz(u64 p) { return (int)((p >> 42) & 0x1fffffu); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ===================================================================== reductions for the grids
+__global__ void k_edge_len_partial(const double4* __restrict__ X, const int2* __restrict__ BE, int nBE, double* partial)
+{
+    double s = 0;
+    for (int e = blockIdx.x * RED_BT + threadIdx.x; e < nBE; e += RED_GRID * RED_BT) {
+        const int2 ed = BE[e];
+        s += sqrt((double)norm2(ldx(X, ed.x) - ldx(X, ed.y)));
+    }
+    s = block_sum<RED_BT>(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// sum over boundary-node slots of |p_x|+|p_y|+|p_z| (SPATIAL_HASH.h:466-474)
+__global__ void k_psize_partial(const double4* __restrict__ P, const int* __restrict__ BN, int nBN, double* partial)
+{
+    double s = 0;
+    for (int i = blockIdx.x * RED_BT + threadIdx.x; i < nBN; i += RED_GRID * RED_BT) {
+        const double4 p = P[BN[i]];
+        s += (fabs(p.x) + fabs(p.y)) + fabs(p.z);
+    }
+    s = block_sum<RED_BT>(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// bbox over boundary nodes of x (and x + alpha p when P != nullptr); out[0..2]=min, out[3..5]=max (ordered ints)
+__global__ void k_bbox(const double4* __restrict__ X, const double4* __restrict__ P, double alpha, const int* __restrict__ BN,
+    int nBN, long long* out)
+{
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nBN; i += gridDim.x * blockDim.x) {
+        const int v = BN[i];
+        const double4 x = X[v];
+        double c[3] = {x.x, x.y, x.z};
+        for (int d = 0; d < 3; ++d) { mn[d] = fmin(mn[d], c[d]); mx[d] = fmax(mx[d], c[d]); }
+        if (P) {
+            const double4 p = P[v];
+            const double e[3] = {__dadd_rn(x.x, __dmul_rn(alpha, p.x)), __dadd_rn(x.y, __dmul_rn(alpha, p.y)),
+                __dadd_rn(x.z, __dmul_rn(alpha, p.z))};
+            for (int d = 0; d < 3; ++d) { mn[d] = fmin(mn[d], e[d]); mx[d] = fmax(mx[d], e[d]); }
+        }
+    }
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fmin(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmax(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&out[d], dbl_ordered(mn[d]));
+            atomicMax(&out[3 + d], dbl_ordered(mx[d]));
+        }
+    }
+}
+
+// ===================================================================== voxel boxes
+// Constraint-set grid (our own; any superset of the AABB-gap test is valid):
+// every primitive's AABB inflated by r (~dHat/2).  prim ids: nodes [0,nBN), edges, triangles.
+__global__ void k_boxes_ccs(Topo T, const double4* __restrict__ X, GridDesc G, double r, u64* boxLo, u64* boxHi, u32* cnt)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nP = T.nBN + T.nBE + T.nBT;
+    if (g >= nP) return;
+    double lo[3], hi[3];
+    auto acc = [&](int v, bool first) {
+        const double4 q = X[v];
+        const double c[3] = {q.x, q.y, q.z};
+        for (int d = 0; d < 3; ++d) {
+            lo[d] = first ? c[d] : fmin(lo[d], c[d]);
+            hi[d] = first ? c[d] : fmax(hi[d], c[d]);
+        }
+    };
+    if (g < T.nBN) acc(T.BN[g], true);
+    else if (g < T.nBN + T.nBE) { const int2 e = T.BE[g - T.nBN]; acc(e.x, true); acc(e.y, false); }
+    else { const int4 t = T.BT[g - T.nBN - T.nBE]; acc(t.x, true); acc(t.y, false); acc(t.z, false); }
+    const double o[3] = {G.ox, G.oy, G.oz};
+    const int gd[3] = {G.gx, G.gy, G.gz};
+    int l[3], h[3];
+    for (int d = 0; d < 3; ++d) {
+        l[d] = clampi((int)floor((lo[d] - r - o[d]) * G.inv), 0, gd[d] - 1);
+        h[d] = clampi((int)floor((hi[d] + r - o[d]) * G.inv), 0, gd[d] - 1);
+    }
+    boxLo[g] = pack3(l[0], l[1], l[2]);
+    boxHi[g] = pack3(h[0], h[1], h[2]);
+    cnt[g] = (u32)(h[0] - l[0] + 1) * (u32)(h[1] - l[1] + 1) * (u32)(h[2] - l[2] + 1);
+}
+// Swept grid of the step-size search: per boundary-node slot, the voxel range of
+// [min(x, x+a p) - xi/2, max(x, x+a p) + xi/2]  (SPATIAL_HASH.h:522-529), arithmetic order kept.
+__global__ void k_node_boxes_ccd(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double alpha, double halfXi,
+    GridDesc G, u64* nodeLo, u64* nodeHi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T.nBN) return;
+    const int v = T.BN[i];
+    const double4 x = X[v], p = P[v];
+    const double c[3] = {x.x, x.y, x.z};
+    const double e[3] = {__dadd_rn(x.x, __dmul_rn(alpha, p.x)), __dadd_rn(x.y, __dmul_rn(alpha, p.y)), __dadd_rn(x.z, __dmul_rn(alpha, p.z))};
+    const double o[3] = {G.ox, G.oy, G.oz};
+    const int gd[3] = {G.gx, G.gy, G.gz};
+    int l[3], h[3];
+    for (int d = 0; d < 3; ++d) {
+        const double mn = __dsub_rn(fmin(c[d], e[d]), halfXi), mx = __dadd_rn(fmax(c[d], e[d]), halfXi);
+        l[d] = clampi((int)floor(__dmul_rn(__dsub_rn(mn, o[d]), G.inv)), 0, gd[d] - 1);
+        h[d] = clampi((int)floor(__dmul_rn(__dsub_rn(mx, o[d]), G.inv)), 0, gd[d] - 1);
+    }
+    nodeLo[i] = pack3(l[0], l[1], l[2]);
+    nodeHi[i] = pack3(h[0], h[1], h[2]);
+}
+// edges / triangles: union of their vertices' node boxes (SPATIAL_HASH.h:555-592)
+__global__ void k_prim_boxes_ccd(Topo T, const u64* __restrict__ nodeLo, const u64* __restrict__ nodeHi, u64* boxLo, u64* boxHi, u32* cnt)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nP = T.nBN + T.nBE + T.nBT;
+    if (g >= nP) return;
+    int l[3], h[3];
+    auto acc = [&](int sv, bool first) {
+        const u64 a = nodeLo[sv], b = nodeHi[sv];
+        const int al[3] = {ux(a), uy(a), uz(a)}, bh[3] = {ux(b), uy(b), uz(b)};
+        for (int d = 0; d < 3; ++d) {
+            l[d] = first ? al[d] : min(l[d], al[d]);
+            h[d] = first ? bh[d] : max(h[d], bh[d]);
+        }
+    };
+    if (g < T.nBN) acc(g, true);
+    else if (g < T.nBN + T.nBE) { const int2 e = T.BE[g - T.nBN]; acc(T.v2sv[e.x], true); acc(T.v2sv[e.y], false); }
+    else { const int4 t = T.BT[g - T.nBN - T.nBE]; acc(T.v2sv[t.x], true); acc(T.v2sv[t.y], false); acc(T.v2sv[t.z], false); }
+    boxLo[g] = pack3(l[0], l[1], l[2]);
+    boxHi[g] = pack3(h[0], h[1], h[2]);
+    cnt[g] = (u32)(h[0] - l[0] + 1) * (u32)(h[1] - l[1] + 1) * (u32)(h[2] - l[2] + 1);
+}
+// one (cell<<2|kind, local id) entry per covered voxel
+__global__ void k_emit_entries(Topo T, GridDesc G, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi,
+    const u32* __restrict__ off, u32* keys, u32* vals)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nP = T.nBN + T.nBE + T.nBT;
+    if (g >= nP) return;
+    u32 kind, id;
+    if (g < T.nBN) { kind = 0; id = g; }
+    else if (g < T.nBN + T.nBE) { kind = 1; id = g - T.nBN; }
+    else { kind = 2; id = g - T.nBN - T.nBE; }
+    const u64 a = boxLo[g], b = boxHi[g];
+    u32 o = off[g];
+    for (int iz = uz(a); iz <= uz(b); ++iz)
+        for (int iy = uy(a); iy <= uy(b); ++iy)
+            for (int ix = ux(a); ix <= ux(b); ++ix) {
+                const u32 cell = (u32)ix + (u32)G.gx * ((u32)iy + (u32)G.gy * (u32)iz);
+                keys[o] = (cell << 2) | kind;
+                vals[o] = id;
+                ++o;
+            }
+}
+__global__ void k_cell_heads(const u32* __restrict__ keys, u32 n, u32* heads)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    heads[i] = (i == 0 || (keys[i] >> 2) != (keys[i - 1] >> 2)) ? 1u : 0u;
+}
+// ks[c*4 + k] = first entry of cell c whose kind is >= k (k = 3: end of the cell run)
+__global__ void k_kind_starts(const u32* __restrict__ keys, const u32* __restrict__ headScan, const u32* __restrict__ heads, u32 n, u32* ks)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const bool end = (i == n);
+    const u32 ki = end ? 0 : (keys[i] & 3u);
+    const u32 ci = end ? 0 : (headScan[i] + heads[i] - 1u);
+    if (i == 0) {
+        for (u32 k = 0; k <= ki; ++k) ks[ci * 4 + k] = 0;
+        return;
+    }
+    const u32 kp = keys[i - 1] & 3u;
+    const u32 cp = headScan[i - 1] + heads[i - 1] - 1u;
+    if (end || heads[i]) {
+        for (u32 k = kp + 1; k <= 3; ++k) ks[cp * 4 + k] = i;
+        if (!end) for (u32 k = 0; k <= ki; ++k) ks[ci * 4 + k] = i;
+    }
+    else if (ki != kp) {
+        for (u32 k = kp + 1; k <= ki; ++k) ks[ci * 4 + k] = i;
+    }
+}
+
+// ===================================================================== candidate pairs
+struct CandOut {
+    int2* buf[4]; // 0 PT (slot, tri)  1 EE (eI, eJ)  2 PE (slot, edge)  3 PP (slotI, slotJ)
+    u32* count;   // 4 counters
+    u32 cap[4];
+};
+__device__ __forceinline__ void cand_push(const CandOut& o, int which, int a, int b)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    u32 base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&o.count[which], g.size());
+    base = g.shfl(base, 0);
+    const u32 idx = base + g.thread_rank();
+    if (idx < o.cap[which]) o.buf[which][idx] = make_int2(a, b);
+}
+// a pair of boxes that share cell `cell` is handled only in the cell that is the minimum corner
+// of the boxes' intersection
+__device__ __forceinline__ bool min_corner(u32 cell, u64 loA, u64 loB, const GridDesc& G)
+{
+    const u32 mx = (u32)max(ux(loA), ux(loB)), my = (u32)max(uy(loA), uy(loB)), mz = (u32)max(uz(loA), uz(loB));
+    return cell == mx + (u32)G.gx * (my + (u32)G.gy * mz);
+}
+
+// One thread per sorted hash entry in [e0, e1).  CCD=false: constraint-set pass (gap test with
+// dist = dHat).  CCD=true: step-size pass (swept AABB test with dist = thickness, full search dir).
+template <bool CCD>
+__global__ void __launch_bounds__(256) k_pairs(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double dist_,
+    const u32* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ headScan, const u32* __restrict__ heads,
+    const u32* __restrict__ ks, u32 e0, u32 e1, const u64* __restrict__ boxLo, GridDesc G, CandOut out)
+{
+    const u32 i = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e1) return;
+    const u32 key = keys[i], kind = key & 3u;
+    if (kind == 2) return;
+    const u32 cell = key >> 2, c = headScan[i] + heads[i] - 1u;
+    const int id = (int)vals[i];
+    const xd dist(dist_);
+    const int tOff = T.nBN + T.nBE;
+    if (kind == 0) {
+        const int svI = id, vI = T.BN[svI];
+        const u64 loA = boxLo[svI];
+        const xv3 p = ldx(X, vI);
+        xv3 dp;
+        if (CCD) dp = ldx(P, vI);
+        for (u32 j = ks[c * 4 + 2]; j < ks[c * 4 + 3]; ++j) {
+            const int t = (int)vals[j];
+            if (!min_corner(cell, loA, boxLo[tOff + t], G)) continue;
+            const int4 tri = T.BT[t];
+            if (!pt_pair_ok(T, vI, tri)) continue;
+            const xv3 t0 = ldx(X, tri.x), t1 = ldx(X, tri.y), t2 = ldx(X, tri.z);
+            bool ok;
+            if (CCD) ok = pt_ccd_broadphase(p, t0, t1, t2, dp, ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
+            else ok = pt_cd_broadphase(p, t0, t1, t2, dist);
+            if (ok) cand_push(out, 0, svI, t);
+        }
+        // rod / particle points against rod edges (IPC.h:271-326; step size: particles only, :2098-2135)
+        if (T.nRod > 0 && svI >= (CCD ? T.codim1 : T.codim0)) {
+            for (u32 j = ks[c * 4 + 1]; j < ks[c * 4 + 2]; ++j) {
+                const int e = (int)vals[j];
+                if (e < T.nBE - T.nRod) continue;
+                if (!min_corner(cell, loA, boxLo[T.nBN + e], G)) continue;
+                const int2 ed = T.BE[e];
+                if (vI == ed.x || vI == ed.y) continue;
+                if ((T.flags[vI] & 1) && (T.flags[ed.x] & 1) && (T.flags[ed.y] & 1)) continue;
+                const xv3 q0 = ldx(X, ed.x), q1 = ldx(X, ed.y);
+                bool ok;
+                if (CCD) ok = pe_ccd_broadphase(p, q0, q1, dp, ldx(P, ed.x), ldx(P, ed.y), dist);
+                else ok = pe_cd_broadphase(p, q0, q1, dist);
+                if (ok) cand_push(out, 2, svI, e);
+            }
+        }
+        // particle against later boundary-node slots (IPC.h:328-352, :2137-2163)
+        if (svI >= T.codim1) {
+            for (u32 j = ks[c * 4 + 0]; j < ks[c * 4 + 1]; ++j) {
+                const int svJ = (int)vals[j];
+                if (svJ <= svI) continue;
+                if (!min_corner(cell, loA, boxLo[svJ], G)) continue;
+                const int vJ = T.BN[svJ];
+                if ((T.flags[vI] & 1) && (T.flags[vJ] & 1)) continue;
+                bool ok = true;
+                if (CCD) ok = pp_ccd_broadphase(p, ldx(X, vJ), dp, ldx(P, vJ), dist);
+                if (ok) cand_push(out, 3, svI, svJ);
+            }
+        }
+    }
+    else {
+        const int eI = id;
+        const int2 a = T.BE[eI];
+        const u64 loA = boxLo[T.nBN + eI];
+        const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y);
+        xv3 da0, da1;
+        if (CCD) { da0 = ldx(P, a.x); da1 = ldx(P, a.y); }
+        for (u32 j = ks[c * 4 + 1]; j < ks[c * 4 + 2]; ++j) {
+            const int eJ = (int)vals[j];
+            if (eJ <= eI) continue;
+            if (!min_corner(cell, loA, boxLo[T.nBN + eJ], G)) continue;
+            const int2 b = T.BE[eJ];
+            if (!ee_pair_ok(T, a, b)) continue;
+            const xv3 b0 = ldx(X, b.x), b1 = ldx(X, b.y);
+            bool ok;
+            if (CCD) ok = ee_ccd_broadphase(a0, a1, b0, b1, da0, da1, ldx(P, b.x), ldx(P, b.y), dist);
+            else ok = ee_cd_broadphase(a0, a1, b0, b1, dist);
+            if (ok) cand_push(out, 1, eI, eJ);
+        }
+    }
+}
+
+// ===================================================================== constraint-set narrow phase
+struct NarrowOut {
+    int4* pass;   // PT / EE / mollified stencils (never duplicated)
+    int4* raw;    // PP / PE stencils before de-duplication (c3 = -1)
+    u32* count;   // [0] pass, [1] raw
+};
+__device__ __forceinline__ void push4(int4* buf, u32* ctr, int4 v)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    u32 base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(ctr, g.size());
+    base = g.shfl(base, 0);
+    buf[base + g.thread_rank()] = v;
+}
+// IPC.h:189-257
+__global__ void k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int vI = T.BN[c.x];
+    const int4 t = T.BT[c.y];
+    const xv3 p = ldx(X, vI), t0 = ldx(X, t.x), t1 = ldx(X, t.y), t2 = ldx(X, t.z);
+    const xd dHat2(dHat2_);
+    int4 r;
+    xd d;
+    bool isPass = false;
+    switch (pt_type(p, t0, t1, t2)) {
+    case 0: d = pp_dist2(p, t0); r = make_int4(-vI - 1, t.x, -1, -1); break;
+    case 1: d = pp_dist2(p, t1); r = make_int4(-vI - 1, t.y, -1, -1); break;
+    case 2: d = pp_dist2(p, t2); r = make_int4(-vI - 1, t.z, -1, -1); break;
+    case 3: d = pe_dist2(p, t0, t1); r = make_int4(-vI - 1, t.x, t.y, -1); break;
+    case 4: d = pe_dist2(p, t1, t2); r = make_int4(-vI - 1, t.y, t.z, -1); break;
+    case 5: d = pe_dist2(p, t2, t0); r = make_int4(-vI - 1, t.z, t.x, -1); break;
+    default: d = pt_dist2(p, t0, t1, t2); r = make_int4(-vI - 1, t.x, t.y, t.z); isPass = true; break;
+    }
+    if (d < dHat2) {
+        if (isPass) push4(out.pass, &out.count[0], r);
+        else push4(out.raw, &out.count[1], r);
+    }
+}
+// IPC.h:414-564
+__global__ void k_narrow_ee(Topo T, const double4* __restrict__ X, const double4* __restrict__ X0, const int2* __restrict__ cand, u32 n,
+    double dHat2_, NarrowOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int2 a = T.BE[c.x], b = T.BE[c.y];
+    const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y), b0 = ldx(X, b.x), b1 = ldx(X, b.y);
+    const xd dHat2(dHat2_);
+    const xd cn2 = ee_cross_norm2(a0, a1, b0, b1);
+    const xd eps_x = ee_mollifier_threshold(ldx(X0, a.x), ldx(X0, a.y), ldx(X0, b.x), ldx(X0, b.y));
+    const bool mol = cn2 < eps_x;
+    int4 r;
+    xd d;
+    switch (ee_type(a0, a1, b0, b1)) {
+    case 0: d = pp_dist2(a0, b0); r = mol ? make_int4(a.x, b.x, -a.y - 1, -b.y - 1) : make_int4(-a.x - 1, b.x, -1, -1); break;
+    case 1: d = pp_dist2(a0, b1); r = mol ? make_int4(a.x, b.y, -a.y - 1, -b.x - 1) : make_int4(-a.x - 1, b.y, -1, -1); break;
+    case 2: d = pe_dist2(a0, b0, b1); r = mol ? make_int4(a.x, b.x, b.y, -a.y - 1) : make_int4(-a.x - 1, b.x, b.y, -1); break;
+    case 3: d = pp_dist2(a1, b0); r = mol ? make_int4(a.y, b.x, -a.x - 1, -b.y - 1) : make_int4(-a.y - 1, b.x, -1, -1); break;
+    case 4: d = pp_dist2(a1, b1); r = mol ? make_int4(a.y, b.y, -a.x - 1, -b.x - 1) : make_int4(-a.y - 1, b.y, -1, -1); break;
+    case 5: d = pe_dist2(a1, b0, b1); r = mol ? make_int4(a.y, b.x, b.y, -a.x - 1) : make_int4(-a.y - 1, b.x, b.y, -1); break;
+    case 6: d = pe_dist2(b0, a0, a1); r = mol ? make_int4(b.x, a.x, a.y, -b.y - 1) : make_int4(-b.x - 1, a.x, a.y, -1); break;
+    case 7: d = pe_dist2(b1, a0, a1); r = mol ? make_int4(b.y, a.x, a.y, -b.x - 1) : make_int4(-b.y - 1, a.x, a.y, -1); break;
+    default: d = ee_dist2(a0, a1, b0, b1); r = mol ? make_int4(a.x, a.y, -b.x - 1, b.y) : make_int4(a.x, a.y, b.x, b.y); break;
+    }
+    if (d < dHat2) {
+        if (r.x >= 0) push4(out.pass, &out.count[0], r);
+        else push4(out.raw, &out.count[1], r);
+    }
+}
+// IPC.h:281-322
+__global__ void k_narrow_pe(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int vI = T.BN[c.x];
+    const int2 e = T.BE[c.y];
+    const xv3 p = ldx(X, vI), e0 = ldx(X, e.x), e1 = ldx(X, e.y);
+    const xd dHat2(dHat2_);
+    int4 r;
+    xd d;
+    switch (pe_type(p, e0, e1)) {
+    case 0: d = pp_dist2(p, e0); r = make_int4(-vI - 1, e.x, -1, -1); break;
+    case 1: d = pp_dist2(p, e1); r = make_int4(-vI - 1, e.y, -1, -1); break;
+    default: d = pe_dist2(p, e0, e1); r = make_int4(-vI - 1, e.x, e.y, -1); break;
+    }
+    if (d < dHat2) push4(out.raw, &out.count[1], r);
+}
+// IPC.h:336-349
+__global__ void k_narrow_pp(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int vI = T.BN[c.x], vJ = T.BN[c.y];
+    const xd d = pp_dist2(ldx(X, vI), ldx(X, vJ));
+    if (d < xd(dHat2_)) push4(out.raw, &out.count[1], make_int4(-vI - 1, vJ, -1, -1));
+}
+
+// PP/PE de-duplication (IPC.h:599-654): same raw 4-tuple => one stencil with multiplicity.
+// Index hash table: a slot holds the index of the first record that claimed it.
+__device__ __forceinline__ u32 hash3(int a, int b, int c)
+{
+    u32 h = (u32)a * 0x9E3779B1u;
+    h ^= (u32)b * 0x85EBCA77u + (h << 6) + (h >> 2);
+    h ^= (u32)c * 0xC2B2AE3Du + (h << 6) + (h >> 2);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+__global__ void k_dedup_insert(const int4* __restrict__ raw, u32 n, u32* slots, u32* slotCnt, u32 mask)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 k = raw[i];
+    u32 h = hash3(k.x, k.y, k.z) & mask;
+    while (true) {
+        const u32 prev = atomicCAS(&slots[h], 0xffffffffu, i);
+        if (prev == 0xffffffffu) { atomicAdd(&slotCnt[h], 1u); return; }
+        const int4 o = raw[prev];
+        if (o.x == k.x && o.y == k.y && o.z == k.z) { atomicAdd(&slotCnt[h], 1u); return; }
+        h = (h + 1) & mask;
+    }
+}
+__global__ void k_dedup_emit(const int4* __restrict__ raw, const u32* __restrict__ slots, const u32* __restrict__ slotCnt, u32 nSlots,
+    int4* out, u32* outCount)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSlots) return;
+    const u32 r = slots[s];
+    if (r == 0xffffffffu) return;
+    const int4 k = raw[r];
+    push4(out, outCount, make_int4(k.x, k.y, k.z, -(int)slotCnt[s]));
+}
+__global__ void k_fill_info(double2* info, u32 n, double w, double dHat2)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) info[i] = make_double2(w, dHat2);
+}
+
+// ===================================================================== stencil decoding
+enum Kind { K_PT = 0, K_PE = 1, K_PP = 2, K_EE = 3, K_EE_M = 4, K_PE_M = 5, K_PP_M = 6 };
+struct Stencil {
+    int kind, mult;
+    int v[4];
+};
+__device__ __forceinline__ Stencil decode(const int4 c)
+{
+    Stencil s;
+    s.mult = 1;
+    if (c.x >= 0) {
+        if (c.w >= 0 && c.z >= 0) { s.kind = K_EE; s.v[0] = c.x; s.v[1] = c.y; s.v[2] = c.z; s.v[3] = c.w; }
+        else if (c.w >= 0) { s.kind = K_EE_M; s.v[0] = c.x; s.v[1] = c.y; s.v[2] = -c.z - 1; s.v[3] = c.w; }
+        else if (c.z >= 0) { s.kind = K_PE_M; s.v[0] = c.x; s.v[1] = -c.w - 1; s.v[2] = c.y; s.v[3] = c.z; }
+        else { s.kind = K_PP_M; s.v[0] = c.x; s.v[1] = -c.z - 1; s.v[2] = c.y; s.v[3] = -c.w - 1; }
+    }
+    else {
+        s.v[0] = -c.x - 1; s.v[1] = c.y; s.v[2] = c.z; s.v[3] = c.w;
+        if (c.w >= 0) s.kind = K_PT;
+        else if (c.z >= 0) { s.kind = K_PE; s.mult = -c.w; }
+        else { s.kind = K_PP; s.mult = -c.w; }
+    }
+    return s;
+}
+__device__ __forceinline__ double stencil_dist2(const double4* __restrict__ X, const Stencil& s)
+{
+    switch (s.kind) {
+    case K_PT: return pt_dist2(ldx(X, s.v[0]), ldx(X, s.v[1]), ldx(X, s.v[2]), ldx(X, s.v[3]));
+    case K_PE: return pe_dist2(ldx(X, s.v[0]), ldx(X, s.v[1]), ldx(X, s.v[2]));
+    case K_PP: return pp_dist2(ldx(X, s.v[0]), ldx(X, s.v[1]));
+    case K_EE: case K_EE_M: return ee_dist2(ldx(X, s.v[0]), ldx(X, s.v[1]), ldx(X, s.v[2]), ldx(X, s.v[3]));
+    case K_PE_M: return pe_dist2(ldx(X, s.v[0]), ldx(X, s.v[2]), ldx(X, s.v[3]));
+    default: return pp_dist2(ldx(X, s.v[0]), ldx(X, s.v[2]));
+    }
+}
+__device__ __forceinline__ int block_dim_of(const int4 c) { return (c.x >= 0 || c.w >= 0) ? 12 : (c.z >= 0 ? 9 : 6); }
+
+struct BarrierParams {
+    double dHat2;      // already offset: dHat2 + 2 sqrt(dHat2) xi   (IPC.h:756-757)
+    double thickness2; // xi^2
+    double k0;
+    int elastic;
+};
+// mollifier value e and threshold for a mollified stencil (rest positions X0)
+__device__ __forceinline__ void mollifier_terms(const double4* __restrict__ X, const double4* __restrict__ X0, const Stencil& s,
+    double& eps_x, double& cn2)
+{
+    eps_x = ee_mollifier_threshold(ldx(X0, s.v[0]), ldx(X0, s.v[1]), ldx(X0, s.v[2]), ldx(X0, s.v[3]));
+    cn2 = ee_cross_norm2(ldx(X, s.v[0]), ldx(X, s.v[1]), ldx(X, s.v[2]), ldx(X, s.v[3]));
+}
+
+// ===================================================================== Compute_Barrier (IPC.h:742-941)
+__global__ void __launch_bounds__(RED_BT) k_barrier_energy(const double4* __restrict__ X, const double4* __restrict__ X0,
+    const int4* __restrict__ cs, const double2* __restrict__ info, u32 n, BarrierParams bp, double* partial, int* errFlag)
+{
+    double acc = 0;
+    for (u32 i = blockIdx.x * RED_BT + threadIdx.x; i < n; i += RED_GRID * RED_BT) {
+        const int4 c = cs[i];
+        const Stencil s = decode(c);
+        const double d = stencil_dist2(X, s) - bp.thickness2;
+        if (d <= 0) { *errFlag = CIPC_ERR_NONPOSITIVE_DIST; continue; }
+        double b = barrier_b(bp.elastic, d, bp.dHat2, bp.k0);
+        if (s.kind >= K_EE_M) {
+            double eps_x, cn2;
+            mollifier_terms(X, X0, s, eps_x, cn2);
+            if (cn2 < eps_x) b *= eem(cn2, eps_x);
+        }
+        else if (c.x < 0 && c.w < -1) b *= (double)(-c.w);
+        acc += b * info[i].x;
+    }
+    acc = block_sum<RED_BT>(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// ===================================================================== Compute_Barrier_Gradient (IPC.h:943-1256)
+__device__ __forceinline__ void gadd(double* g, int v, const double* d3, double sc)
+{
+    atomicAdd(&g[3 * v], sc * d3[0]);
+    atomicAdd(&g[3 * v + 1], sc * d3[1]);
+    atomicAdd(&g[3 * v + 2], sc * d3[2]);
+}
+__global__ void __launch_bounds__(128) k_barrier_gradient(const double4* __restrict__ X, const double4* __restrict__ X0,
+    const int4* __restrict__ cs, const double2* __restrict__ info, u32 n, BarrierParams bp, double* g)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Stencil s = decode(cs[i]);
+    const double w = info[i].x;
+    const double d = stencil_dist2(X, s) - bp.thickness2;
+    const double bG = barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
+    double dg[12];
+    const int rows3[3] = {0, 1, 2};
+    if (s.kind < K_EE_M) {
+        int nb;
+        if (s.kind == K_PT || s.kind == K_EE) {
+            const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+            d4_derivs(s.kind == K_EE, x, dg, nullptr, 0.0);
+            nb = 4;
+        }
+        else if (s.kind == K_PE) { pe_derivs(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), dg, nullptr, 9, rows3, 0.0); nb = 3; }
+        else { pp_derivs(ldd(X, s.v[0]), ldd(X, s.v[1]), dg, nullptr, 6, rows3, 0.0); nb = 2; }
+        const double sc = (double)s.mult * w * bG;
+        for (int k = 0; k < nb; ++k) gadd(g, s.v[k], dg + 3 * k, sc);
+        return;
+    }
+    const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+    const double b = barrier_b(bp.elastic, d, bp.dHat2, bp.k0);
+    double eps_x, cn2;
+    mollifier_terms(X, X0, s, eps_x, cn2);
+    double e = 1.0;
+    if (cn2 < eps_x) {
+        e = eem(cn2, eps_x);
+        double eg[12];
+        eecn2_derivs(x, eg, nullptr, 0.0);
+        const double q = eem_g(cn2, eps_x) * w * b;
+        for (int k = 0; k < 4; ++k) gadd(g, s.v[k], eg + 3 * k, q);
+    }
+    const double sc = e * w * bG;
+    if (s.kind == K_EE_M) {
+        d4_derivs(true, x, dg, nullptr, 0.0);
+        for (int k = 0; k < 4; ++k) gadd(g, s.v[k], dg + 3 * k, sc);
+    }
+    else if (s.kind == K_PE_M) {
+        pe_derivs(x[0], x[2], x[3], dg, nullptr, 9, rows3, 0.0);
+        gadd(g, s.v[0], dg, sc); gadd(g, s.v[2], dg + 3, sc); gadd(g, s.v[3], dg + 6, sc);
+    }
+    else {
+        pp_derivs(x[0], x[2], dg, nullptr, 6, rows3, 0.0);
+        gadd(g, s.v[0], dg, sc); gadd(g, s.v[2], dg + 3, sc);
+    }
+}
+
+// ===================================================================== Compute_Barrier_Hessian (IPC.h:1258-1731)
+__global__ void k_block_sizes(const int4* __restrict__ cs, u32 n, u32* sz)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = block_dim_of(cs[i]);
+    sz[i] = (u32)(d * d);
+}
+// Builds the n x n block of one stencil into H (row-major, n = 3*nb), returns nb and vertex ids.
+__device__ void stencil_hessian(const double4* __restrict__ X, const double4* __restrict__ X0, const int4 c, double w,
+    const BarrierParams& bp, bool projectSPD, double* H, int* vids, int& nb)
+{
+    const Stencil s = decode(c);
+    const double d = stencil_dist2(X, s) - bp.thickness2;
+    const double bG = barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
+    const double bH = barrier_H(bp.elastic, d, bp.dHat2, bp.k0);
+    double dg[12];
+    const int rows3[3] = {0, 1, 2};
+    if (s.kind < K_EE_M) {
+        const double m = (double)s.mult;
+        if (s.kind == K_PT || s.kind == K_EE) {
+            nb = 4;
+            for (int i = 0; i < 144; ++i) H[i] = 0.0;
+            const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+            d4_derivs(s.kind == K_EE, x, dg, H, w * m * bG);
+        }
+        else if (s.kind == K_PE) {
+            nb = 3;
+            for (int i = 0; i < 81; ++i) H[i] = 0.0;
+            pe_derivs(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), dg, H, 9, rows3, w * m * bG);
+        }
+        else {
+            nb = 2;
+            for (int i = 0; i < 36; ++i) H[i] = 0.0;
+            pp_derivs(ldd(X, s.v[0]), ldd(X, s.v[1]), dg, H, 6, rows3, w * m * bG);
+        }
+        const int n = 3 * nb;
+        const double q = w * m * bH;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) H[i * n + j] += q * dg[i] * dg[j];
+        for (int k = 0; k < nb; ++k) vids[k] = s.v[k];
+        if (projectSPD) {
+            if (nb == 4) psd_project_jacobi<12>(H);
+            else if (nb == 3) psd_project_jacobi<9>(H);
+            else psd_project_jacobi<6>(H);
+        }
+        return;
+    }
+    // mollified stencils: 12 x 12 in the (ea0, ea1, eb0, eb1) frame (IPC.h:1472-1475, 1526-1537, 1588-1599)
+    nb = 4;
+    for (int k = 0; k < 4; ++k) vids[k] = s.v[k];
+    for (int i = 0; i < 144; ++i) H[i] = 0.0;
+    const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+    const double b = barrier_b(bp.elastic, d, bp.dHat2, bp.k0);
+    double eps_x, cn2;
+    mollifier_terms(X, X0, s, eps_x, cn2);
+    double e = 1.0;
+    double eg[12];
+    for (int i = 0; i < 12; ++i) eg[i] = 0.0;
+    if (cn2 < eps_x) {
+        e = eem(cn2, eps_x);
+        const double qg = eem_g(cn2, eps_x), qH = eem_H(eps_x);
+        double cg_[12];
+        eecn2_derivs(x, cg_, H, w * b * qg); // b * eH, first part: q_g * d2(cn2)
+        for (int i = 0; i < 12; ++i)
+            for (int j = 0; j < 12; ++j) H[i * 12 + j] += w * b * qH * cg_[i] * cg_[j];
+        for (int i = 0; i < 12; ++i) eg[i] = qg * cg_[i];
+    }
+    double G[12];
+    for (int i = 0; i < 12; ++i) G[i] = 0.0;
+    if (s.kind == K_EE_M) {
+        d4_derivs(true, x, dg, H, w * e * bG);
+        for (int i = 0; i < 12; ++i) G[i] = dg[i];
+    }
+    else if (s.kind == K_PE_M) {
+        const int rows[3] = {0, 2, 3};
+        pe_derivs(x[0], x[2], x[3], dg, H, 12, rows, w * e * bG);
+        for (int k = 0; k < 3; ++k) for (int r = 0; r < 3; ++r) G[3 * rows[k] + r] = dg[3 * k + r];
+    }
+    else {
+        const int rows[2] = {0, 2};
+        pp_derivs(x[0], x[2], dg, H, 12, rows, w * e * bG);
+        for (int k = 0; k < 2; ++k) for (int r = 0; r < 3; ++r) G[3 * rows[k] + r] = dg[3 * k + r];
+    }
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j)
+            H[i * 12 + j] += w * (bG * (G[i] * eg[j] + eg[i] * G[j]) + (e * bH) * G[i] * G[j]);
+    if (projectSPD) psd_project_jacobi<12>(H);
+}
+__global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
+    const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, u32 n, BarrierParams bp,
+    int projectSPD, cipc_triplet* trip)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double H[144];
+    int vids[4], nb;
+    stencil_hessian(X, X0, cs[i], info[i].x, bp, projectSPD != 0, H, vids, nb);
+    const int nn = 3 * nb;
+    cipc_triplet* o = trip + off[i];
+    for (int I = 0; I < nb; ++I)
+        for (int a = 0; a < 3; ++a)
+            for (int J = 0; J < nb; ++J)
+                for (int b2 = 0; b2 < 3; ++b2) {
+                    cipc_triplet t;
+                    t.row = vids[I] * 3 + a; t.col = vids[J] * 3 + b2; t.val = H[(I * 3 + a) * nn + J * 3 + b2];
+                    o[(I * 3 + a) * nn + J * 3 + b2] = t;
+                }
+}
+template <int N>
+__global__ void k_test_make_pd(double* H, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double A[N * N];
+    for (int k = 0; k < N * N; ++k) A[k] = H[(size_t)i * N * N + k];
+    psd_project_jacobi<N>(A);
+    for (int k = 0; k < N * N; ++k) H[(size_t)i * N * N + k] = A[k];
+}
+
+// ===================================================================== Compute_Min_Dist2 (IPC.h:2246-2388)
+__global__ void k_min_dist(const double4* __restrict__ X, const int4* __restrict__ cs, u32 n, double* dist2, long long* minBits)
+{
+    double m = 1e300;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double d = stencil_dist2(X, decode(cs[i]));
+        if (dist2) dist2[i] = d;
+        m = fmin(m, d);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(minBits, dbl_ordered(m));
+}
+
+// ===================================================================== ACCD over candidate pairs
+// alphaBits holds the running minimum step as the bit pattern of a positive double (monotone).
+struct AccdOut {
+    u64* alphaBits;
+    int* errFlag;
+};
+__device__ __forceinline__ void accd_commit(const AccdOut& o, bool hit, xd toc, bool checkZero)
+{
+    if (hit) atomicMin(o.alphaBits, (u64)__double_as_longlong(toc.v));
+    if (checkZero && hit && toc.v == 0.0) *o.errFlag = CIPC_ERR_ZERO_STEP;
+}
+__global__ void __launch_bounds__(128) k_accd_pt(Topo T, const double4* __restrict__ X, const double4* __restrict__ P,
+    const int2* __restrict__ cand, u32 n, double thickness, double bound, AccdOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int vI = T.BN[c.x];
+    const int4 t = T.BT[c.y];
+    xd toc;
+    const bool hit = pt_accd(ldx(X, vI), ldx(X, t.x), ldx(X, t.y), ldx(X, t.z), ldx(P, vI), ldx(P, t.x), ldx(P, t.y), ldx(P, t.z),
+        xd(0.1), xd(thickness), xd(bound), toc, (const volatile double*)out.alphaBits);
+    accd_commit(out, hit, toc, true);
+}
+__global__ void __launch_bounds__(128) k_accd_ee(Topo T, const double4* __restrict__ X, const double4* __restrict__ P,
+    const int2* __restrict__ cand, u32 n, double thickness, double bound, AccdOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int2 a = T.BE[c.x], b = T.BE[c.y];
+    xd toc;
+    const bool hit = ee_accd(ldx(X, a.x), ldx(X, a.y), ldx(X, b.x), ldx(X, b.y), ldx(P, a.x), ldx(P, a.y), ldx(P, b.x), ldx(P, b.y),
+        xd(0.1), xd(thickness), xd(bound), toc, (const volatile double*)out.alphaBits);
+    accd_commit(out, hit, toc, false);
+}
+__global__ void __launch_bounds__(128) k_accd_pe(Topo T, const double4* __restrict__ X, const double4* __restrict__ P,
+    const int2* __restrict__ cand, u32 n, double thickness, double bound, AccdOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int vI = T.BN[c.x];
+    const int2 e = T.BE[c.y];
+    xd toc;
+    const bool hit = pe_accd(ldx(X, vI), ldx(X, e.x), ldx(X, e.y), ldx(P, vI), ldx(P, e.x), ldx(P, e.y), xd(0.1), xd(thickness),
+        xd(bound), toc, (const volatile double*)out.alphaBits);
+    accd_commit(out, hit, toc, false);
+}
+__global__ void __launch_bounds__(128) k_accd_pp(Topo T, const double4* __restrict__ X, const double4* __restrict__ P,
+    const int2* __restrict__ cand, u32 n, double thickness, double bound, AccdOut out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    const int vI = T.BN[c.x], vJ = T.BN[c.y];
+    xd toc;
+    const bool hit = pp_accd(ldx(X, vI), ldx(X, vJ), ldx(P, vI), ldx(P, vJ), xd(0.1), xd(thickness), xd(bound), toc,
+        (const volatile double*)out.alphaBits);
+    accd_commit(out, hit, toc, false);
+}
+
+// ===================================================================== marshalling helpers
+__global__ void k_expand3(const double* __restrict__ src, double4* dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_double4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.0);
+}
+__global__ void k_pack_edges(const int* __restrict__ src, int stride, int n, int2* dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_int2(src[(size_t)i * stride], src[(size_t)i * stride + 1]);
+}
+__global__ void k_pack_tris(const int* __restrict__ src, int stride, int n, int4* dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_int4(src[(size_t)i * stride], src[(size_t)i * stride + 1], src[(size_t)i * stride + 2], 0);
+}
+__global__ void k_fill_u32(u32* p, size_t n, u32 v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+} // namespace cipc
+
+// ========================================================================================= context
+using namespace cipc;
+
+struct StageEv {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+struct cipc_ctx {
+    int dev = 0, rank = 0, world = 1;
+    cudaStream_t st = nullptr;
+    std::string err;
+    // topology
+    Topo T{};
+    u64 topoHash = 0;
+    DevBuf<int> BN, v2sv, stageI;
+    DevBuf<int2> BE;
+    DevBuf<int4> BT;
+    DevBuf<uint8_t> flags;
+    DevBuf<u64> nnx;
+    DevBuf<double> BNArea, BEArea, BTArea;
+    // state
+    DevBuf<double4> X, X0, P;
+    bool haveX = false, haveX0 = false, haveP = false;
+    DevBuf<double> stageD;
+    // hash
+    DevBuf<u64> boxLo, boxHi, nodeLo, nodeHi;
+    DevBuf<u32> cnt, keys, vals, heads, headScan, ks;
+    SortWork sortwk;
+    ScanWork scanwk;
+    DevBuf<double> partial, scal;  // scal: [0] E partial, [1] alpha, [2] min dist2, [3..] scratch
+    DevBuf<long long> bbox;        // 6 ordered ints
+    DevBuf<u32> counters;          // 16 device counters
+    DevBuf<int> errFlag;
+    // candidates
+    DevBuf<int2> cand[4];
+    // constraints
+    DevBuf<int4> cs, raw;
+    DevBuf<double2> info;
+    u32 nC = 0;
+    DevBuf<u32> slots, slotCnt;
+    // outputs
+    DevBuf<double> g, dist2;
+    DevBuf<cipc_triplet> trip;
+    DevBuf<u32> tripOff;
+    int64_t nTrip = 0;
+    PinnedBuf pin;
+    // timing
+    std::vector<StageEv> stages;
+    std::vector<cudaEvent_t> evPool;
+    size_t evUsed = 0;
+    std::map<std::string, int64_t> ctr;
+
+    cudaEvent_t ev()
+    {
+        if (evUsed == evPool.size()) {
+            cudaEvent_t e;
+            CIPC_CUDA(cudaEventCreate(&e));
+            evPool.push_back(e);
+        }
+        return evPool[evUsed++];
+    }
+    void begin_call() { stages.clear(); evUsed = 0; }
+    struct Scope {
+        cipc_ctx* c;
+        size_t idx;
+        Scope(cipc_ctx* c_, const char* name) : c(c_)
+        {
+            StageEv s;
+            s.name = name; s.a = c->ev(); s.b = c->ev();
+            CIPC_CUDA(cudaEventRecord(s.a, c->st));
+            c->stages.push_back(s);
+            idx = c->stages.size() - 1;
+        }
+        ~Scope() { cudaEventRecord(c->stages[idx].b, c->st); }
+    };
+};
+
+namespace {
+
+const int TB = 256;
+
+template <class F>
+int guarded(cipc_ctx* ctx, F f)
+{
+    if (!ctx) return CIPC_ERR_ARG;
+    try {
+        CIPC_CUDA(cudaSetDevice(ctx->dev));
+        return f();
+    }
+    catch (const CudaError& e) {
+        ctx->err = e.what();
+        return CIPC_ERR_CUDA;
+    }
+    catch (const std::exception& e) {
+        ctx->err = e.what();
+        return CIPC_ERR_ARG;
+    }
+}
+
+u64 fnv(const void* p, size_t n, u64 h)
+{
+    const unsigned char* c = (const unsigned char*)p;
+    // 8 bytes at a time is enough for a change detector
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { u64 w; memcpy(&w, c + i, 8); h = (h ^ w) * 0x100000001b3ULL; h ^= h >> 29; }
+    for (; i < n; ++i) h = (h ^ c[i]) * 0x100000001b3ULL;
+    return h;
+}
+
+void upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int stride_bytes)
+{
+    const int n = c->T.nV;
+    dst.reserve(n, c->st);
+    if (stride_bytes == 32) {
+        CIPC_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)n * 32, cudaMemcpyHostToDevice, c->st));
+    }
+    else if (stride_bytes == 24) {
+        c->stageD.reserve((size_t)3 * n, c->st);
+        CIPC_CUDA(cudaMemcpyAsync(c->stageD.p, src, (size_t)n * 24, cudaMemcpyHostToDevice, c->st));
+        CIPC_LAUNCH(k_expand3, div_up(n, TB), TB, 0, c->st, c->stageD.p, dst.p, n);
+    }
+    else throw std::runtime_error("stride_bytes must be 24 or 32");
+}
+
+// ---- spatial hash (shared by the constraint-set and the step-size passes)
+struct HashInfo {
+    GridDesc G;
+    u32 nEntries = 0, nCells = 0;
+};
+
+// sum of partials helper: returns value on host
+double reduce_to_host(cipc_ctx* c, double scale)
+{
+    CIPC_LAUNCH(k_final_sum, 1, RED_BT, 0, c->st, c->partial.p, RED_GRID, c->scal.p + 3, scale);
+    double v;
+    CIPC_CUDA(cudaMemcpyAsync(&v, c->scal.p + 3, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    return v;
+}
+double mean_edge_len(cipc_ctx* c)
+{
+    CIPC_LAUNCH(k_edge_len_partial, RED_GRID, RED_BT, 0, c->st, c->X.p, c->BE.p, c->T.nBE, c->partial.p);
+    return reduce_to_host(c, 1.0 / (double)c->T.nBE);
+}
+void bbox_to_host(cipc_ctx* c, const double4* P, double alpha, double* mn, double* mx)
+{
+    long long init[6];
+    for (int d = 0; d < 3; ++d) { init[d] = dbl_ordered_h(1e300); init[3 + d] = dbl_ordered_h(-1e300); }
+    CIPC_CUDA(cudaMemcpyAsync(c->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, c->st));
+    CIPC_LAUNCH(k_bbox, RED_GRID, RED_BT, 0, c->st, c->X.p, P, alpha, c->BN.p, c->T.nBN, c->bbox.p);
+    long long out[6];
+    CIPC_CUDA(cudaMemcpyAsync(out, c->bbox.p, sizeof(out), cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    for (int d = 0; d < 3; ++d) {
+        long long a = out[d], b = out[3 + d];
+        a = a >= 0 ? a : (a ^ 0x7fffffffffffffffLL);
+        b = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+        memcpy(&mn[d], &a, 8);
+        memcpy(&mx[d], &b, 8);
+    }
+}
+// after boxes + counts are in place: scan, emit, sort, cell table
+void build_cell_lists(cipc_ctx* c, HashInfo& H)
+{
+    const Topo& T = c->T;
+    const int nP = T.nBN + T.nBE + T.nBT;
+    device_excl_scan(c->cnt.p, c->cnt.p, nP, c->scanwk, c->st);
+    u32 nE;
+    CIPC_CUDA(cudaMemcpyAsync(&nE, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    H.nEntries = nE;
+    c->keys.reserve(nE, c->st); c->vals.reserve(nE, c->st); c->heads.reserve(nE, c->st); c->headScan.reserve(nE, c->st);
+    if (nE == 0) { H.nCells = 0; return; }
+    CIPC_LAUNCH(k_emit_entries, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, c->cnt.p, c->keys.p, c->vals.p);
+    const double cells = (double)H.G.gx * H.G.gy * H.G.gz;
+    int bits = 2;
+    while ((double)(1ULL << (bits - 2)) < cells) ++bits;
+    device_radix_sort(c->keys.p, c->vals.p, nE, bits, c->sortwk, c->st);
+    CIPC_LAUNCH(k_cell_heads, div_up(nE, TB), TB, 0, c->st, c->keys.p, nE, c->heads.p);
+    device_excl_scan(c->heads.p, c->headScan.p, nE, c->scanwk, c->st);
+    u32 nCells;
+    CIPC_CUDA(cudaMemcpyAsync(&nCells, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    H.nCells = nCells;
+    c->ks.reserve((size_t)nCells * 4, c->st);
+    CIPC_LAUNCH(k_kind_starts, div_up((size_t)nE + 1, TB), TB, 0, c->st, c->keys.p, c->headScan.p, c->heads.p, nE, c->ks.p);
+    c->ctr["hash_entries"] = nE;
+    c->ctr["hash_cells"] = nCells;
+}
+// grid sizing shared by both passes (SPATIAL_HASH.h:71-86): voxelCount = ceil(range/voxel), total <= ~1e9
+bool size_grid(const double* mn, const double* mx, double voxelSize, GridDesc& G, bool plusOne)
+{
+    const double range[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+    double inv = 1.0 / voxelSize;
+    double amt = 1;
+    for (int d = 0; d < 3; ++d) amt *= std::max(1.0, std::ceil(range[d] * inv));
+    if (amt > 1e9) {
+        voxelSize *= std::pow(amt / 1.0e9, 1.0 / 3);
+        inv = 1.0 / voxelSize;
+    }
+    long g[3];
+    for (int d = 0; d < 3; ++d) {
+        g[d] = std::max(1L, (long)std::ceil(range[d] * inv)) + (plusOne ? 1 : 0);
+        if (g[d] > (1L << 21) - 1) return false;
+    }
+    if ((double)g[0] * g[1] * g[2] >= (double)(1L << 30)) return false;
+    G.ox = mn[0]; G.oy = mn[1]; G.oz = mn[2]; G.inv = inv;
+    G.gx = (int)g[0]; G.gy = (int)g[1]; G.gz = (int)g[2];
+    return true;
+}
+
+// enumerate candidate pairs for this rank's slice of the sorted entries; grows buffers on overflow
+template <bool CCD>
+void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
+{
+    const u32 nE = H.nEntries;
+    const u32 e0 = (u32)((u64)nE * c->rank / c->world), e1 = (u32)((u64)nE * (c->rank + 1) / c->world);
+    for (int k = 0; k < 4; ++k) counts[k] = 0;
+    if (e1 <= e0) return;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CandOut out;
+        for (int k = 0; k < 4; ++k) {
+            if (c->cand[k].cap == 0) c->cand[k].reserve(k < 2 ? (size_t)8 * (c->T.nBN + c->T.nBE) + 1024 : 1024, c->st);
+            out.buf[k] = c->cand[k].p;
+            out.cap[k] = (u32)std::min<size_t>(c->cand[k].cap, 0xfffffff0u);
+        }
+        out.count = c->counters.p;
+        CIPC_CUDA(cudaMemsetAsync(c->counters.p, 0, 16 * sizeof(u32), c->st));
+        CIPC_LAUNCH(k_pairs<CCD>, div_up(e1 - e0, 256), 256, 0, c->st, c->T, c->X.p, c->P.p, dist, c->keys.p, c->vals.p,
+            c->headScan.p, c->heads.p, c->ks.p, e0, e1, c->boxLo.p, H.G, out);
+        CIPC_CUDA(cudaMemcpyAsync(counts, c->counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        bool ok = true;
+        for (int k = 0; k < 4; ++k)
+            if (counts[k] > out.cap[k]) { ok = false; c->cand[k].reserve((size_t)counts[k] + counts[k] / 8, c->st); }
+        if (ok) return;
+    }
+    throw std::runtime_error("candidate buffer kept overflowing");
+}
+
+BarrierParams make_bp(int elastic, double dHat2, const double* kappa, double thickness)
+{
+    if (elastic) thickness = 0;
+    BarrierParams bp;
+    bp.thickness2 = thickness * thickness;
+    bp.dHat2 = dHat2 + 2 * std::sqrt(dHat2) * thickness;
+    bp.k0 = kappa[0];
+    bp.elastic = elastic;
+    return bp;
+}
+int fetch_err(cipc_ctx* c)
+{
+    int e = 0;
+    CIPC_CUDA(cudaMemcpyAsync(&e, c->errFlag.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    return e;
+}
+void need(bool cond, const char* what)
+{
+    if (!cond) throw std::runtime_error(what);
+}
+
+// ---- stage bodies (results left on the device)
+int do_barrier_energy(cipc_ctx* c, int elastic, double dHat2, const double* kappa, double thickness)
+{
+    need(c->haveX, "positions not set");
+    const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
+    CIPC_CUDA(cudaMemsetAsync(c->errFlag.p, 0, sizeof(int), c->st));
+    {
+        cipc_ctx::Scope sc(c, "barrier_E");
+        CIPC_LAUNCH(k_barrier_energy, RED_GRID, RED_BT, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->nC, bp, c->partial.p,
+            c->errFlag.p);
+        CIPC_LAUNCH(k_final_sum, 1, RED_BT, 0, c->st, c->partial.p, RED_GRID, c->scal.p + 0, 1.0);
+    }
+    return CIPC_OK;
+}
+int do_barrier_gradient(cipc_ctx* c, int elastic, double dHat2, const double* kappa, double thickness)
+{
+    need(c->haveX, "positions not set");
+    const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
+    c->g.reserve((size_t)3 * c->T.nV, c->st);
+    cipc_ctx::Scope sc(c, "barrier_g");
+    CIPC_CUDA(cudaMemsetAsync(c->g.p, 0, (size_t)3 * c->T.nV * sizeof(double), c->st));
+    if (c->nC) CIPC_LAUNCH(k_barrier_gradient, div_up(c->nC, 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->nC, bp, c->g.p);
+    return CIPC_OK;
+}
+int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
+{
+    need(c->haveX && c->haveP, "positions / search direction not set");
+    if (elastic) thickness = 0;
+    const Topo& T = c->T;
+    HashInfo H;
+    double alpha = stepIn;
+    {
+        cipc_ctx::Scope sc(c, "ccd_hash_build");
+        double voxelSize = 1.0;
+        if (T.nBE) voxelSize *= mean_edge_len(c);
+        // span rule (SPATIAL_HASH.h:466-482).  The sum is a fixed-tree reduction; when the rule
+        // fires the step is biased down by 4e-13 relative so that it never exceeds the sequential
+        // CPU sum's result.
+        CIPC_LAUNCH(k_psize_partial, RED_GRID, RED_BT, 0, c->st, c->P.p, c->BN.p, T.nBN, c->partial.p);
+        const double pSize = reduce_to_host(c, 1.0 / ((double)T.nBN * 3.0));
+        const double spanSize = alpha * pSize / voxelSize;
+        if (spanSize > 1) alpha = (alpha / spanSize) * (1.0 - 4e-13);
+        double mn[3], mx[3];
+        bbox_to_host(c, c->P.p, alpha, mn, mx);
+        for (int d = 0; d < 3; ++d) { mn[d] -= thickness / 2; mx[d] += thickness / 2; }
+        if (!size_grid(mn, mx, voxelSize, H.G, true)) return CIPC_ERR_GRID;
+        const int nP = T.nBN + T.nBE + T.nBT;
+        c->boxLo.reserve(nP, c->st); c->boxHi.reserve(nP, c->st); c->cnt.reserve(nP, c->st);
+        c->nodeLo.reserve(T.nBN, c->st); c->nodeHi.reserve(T.nBN, c->st);
+        CIPC_LAUNCH(k_node_boxes_ccd, div_up(T.nBN, TB), TB, 0, c->st, T, c->X.p, c->P.p, alpha, thickness / 2, H.G, c->nodeLo.p, c->nodeHi.p);
+        CIPC_LAUNCH(k_prim_boxes_ccd, div_up(nP, TB), TB, 0, c->st, T, c->nodeLo.p, c->nodeHi.p, c->boxLo.p, c->boxHi.p, c->cnt.p);
+        build_cell_lists(c, H);
+    }
+    u32 counts[4];
+    {
+        cipc_ctx::Scope sc(c, "ccd_pairs");
+        run_pairs<true>(c, H, thickness, counts);
+    }
+    c->ctr["ccd_pairs"] = (int64_t)counts[0] + counts[1] + counts[2] + counts[3];
+    {
+        cipc_ctx::Scope sc(c, "ccd_accd");
+        u64 bits;
+        memcpy(&bits, &alpha, 8);
+        CIPC_CUDA(cudaMemcpyAsync(c->scal.p + 1, &bits, 8, cudaMemcpyHostToDevice, c->st));
+        CIPC_CUDA(cudaMemsetAsync(c->errFlag.p, 0, sizeof(int), c->st));
+        AccdOut out{(u64*)(c->scal.p + 1), c->errFlag.p};
+        if (counts[0]) CIPC_LAUNCH(k_accd_pt, div_up(counts[0], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[0].p, counts[0], thickness, alpha, out);
+        if (counts[2]) CIPC_LAUNCH(k_accd_pe, div_up(counts[2], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[2].p, counts[2], thickness, alpha, out);
+        if (counts[3]) CIPC_LAUNCH(k_accd_pp, div_up(counts[3], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[3].p, counts[3], thickness, alpha, out);
+        if (counts[1]) CIPC_LAUNCH(k_accd_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[1].p, counts[1], thickness, alpha, out);
+    }
+    return CIPC_OK;
+}
+int do_min_dist(cipc_ctx* c, bool wantDist)
+{
+    need(c->haveX, "positions not set");
+    cipc_ctx::Scope sc(c, "min_dist");
+    const long long init = dbl_ordered_h(1e300);
+    CIPC_CUDA(cudaMemcpyAsync(c->scal.p + 2, &init, 8, cudaMemcpyHostToDevice, c->st));
+    if (wantDist) c->dist2.reserve(c->nC, c->st);
+    if (c->nC) CIPC_LAUNCH(k_min_dist, RED_GRID, RED_BT, 0, c->st, c->X.p, c->cs.p, c->nC, wantDist ? c->dist2.p : nullptr, (long long*)(c->scal.p + 2));
+    return CIPC_OK;
+}
+
+} // namespace
+
+// ========================================================================================= C ABI
+extern "C" {
+
+const char* cipc_version(void) { return "cipc_b200 0.1 (sm_100a)"; }
+int64_t cipc_kernel_launches(void) { return g_launches; }
+
+int cipc_create(int device, int rank, int world, cipc_ctx** out)
+{
+    if (!out || world < 1 || rank < 0 || rank >= world) return CIPC_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
+        fprintf(stderr, "cipc_b200: no usable CUDA device (requested %d of %d); this library has no CPU path\n", device, ndev);
+        return CIPC_ERR_CUDA;
+    }
+    std::unique_ptr<cipc_ctx> c(new cipc_ctx());
+    c->dev = device; c->rank = rank; c->world = world;
+    try {
+        CIPC_CUDA(cudaSetDevice(device));
+        CIPC_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        c->partial.reserve(RED_GRID, c->st);
+        c->scal.reserve(16, c->st);
+        c->bbox.reserve(6, c->st);
+        c->counters.reserve(16, c->st);
+        c->errFlag.reserve(1, c->st);
+        CIPC_CUDA(cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+    }
+    catch (const std::exception& e) {
+        fprintf(stderr, "cipc_b200: %s\n", e.what());
+        return CIPC_ERR_CUDA;
+    }
+    *out = c.release();
+    return CIPC_OK;
+}
+void cipc_destroy(cipc_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    cudaStreamSynchronize(ctx->st);
+    for (auto e : ctx->evPool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+const char* cipc_last_error(cipc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int cipc_sync(cipc_ctx* ctx)
+{
+    return guarded(ctx, [&]() { CIPC_CUDA(cudaStreamSynchronize(ctx->st)); return (int)CIPC_OK; });
+}
+
+int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE, const int32_t* BE, int be_stride, int nBT,
+    const int32_t* BT, int bt_stride, int nRod, const int32_t codim[2], const uint8_t* dbc, int nNnx, const int32_t* nnxPairs,
+    const double* BNArea, const double* BEArea, const double* BTArea)
+{
+    return guarded(ctx, [&]() {
+        if (nV <= 0 || nBN < 0 || nBE < 0 || nBT < 0 || (be_stride != 2 && be_stride != 4) || (bt_stride != 3 && bt_stride != 4) || !dbc)
+            return (int)CIPC_ERR_ARG;
+        cipc_ctx* c = ctx;
+        u64 h = 0xcbf29ce484222325ULL;
+        const int hdr[8] = {nV, nBN, nBE, nBT, nRod, codim[0], codim[1], nNnx};
+        h = fnv(hdr, sizeof(hdr), h);
+        h = fnv(BN, (size_t)nBN * 4, h);
+        h = fnv(BE, (size_t)nBE * be_stride * 4, h);
+        h = fnv(BT, (size_t)nBT * bt_stride * 4, h);
+        h = fnv(dbc, nV, h);
+        if (nNnx) h = fnv(nnxPairs, (size_t)nNnx * 8, h);
+        if (BNArea) h = fnv(BNArea, (size_t)nBN * 8, h ^ 1);
+        if (h == c->topoHash && c->T.nV == nV) return (int)CIPC_OK; // unchanged: keep the resident copy
+        Topo& T = c->T;
+        T.nV = nV; T.nBN = nBN; T.nBE = nBE; T.nBT = nBT; T.nRod = nRod; T.codim0 = codim[0]; T.codim1 = codim[1];
+        c->BN.reserve(std::max(nBN, 1), c->st); c->BE.reserve(std::max(nBE, 1), c->st); c->BT.reserve(std::max(nBT, 1), c->st);
+        c->flags.reserve(nV, c->st); c->v2sv.reserve(nV, c->st);
+        CIPC_CUDA(cudaMemcpyAsync(c->BN.p, BN, (size_t)nBN * 4, cudaMemcpyHostToDevice, c->st));
+        const size_t need_i = std::max((size_t)nBE * be_stride, (size_t)nBT * bt_stride);
+        c->stageI.reserve(std::max<size_t>(need_i, 1), c->st);
+        if (nBE) {
+            CIPC_CUDA(cudaMemcpyAsync(c->stageI.p, BE, (size_t)nBE * be_stride * 4, cudaMemcpyHostToDevice, c->st));
+            CIPC_LAUNCH(k_pack_edges, div_up(nBE, TB), TB, 0, c->st, c->stageI.p, be_stride, nBE, c->BE.p);
+        }
+        if (nBT) {
+            CIPC_CUDA(cudaMemcpyAsync(c->stageI.p, BT, (size_t)nBT * bt_stride * 4, cudaMemcpyHostToDevice, c->st));
+            CIPC_LAUNCH(k_pack_tris, div_up(nBT, TB), TB, 0, c->st, c->stageI.p, bt_stride, nBT, c->BT.p);
+        }
+        // flags and vertex -> boundary slot map are small host loops
+        std::vector<uint8_t> fl(dbc, dbc + nV);
+        for (int v = 0; v < nV; ++v) fl[v] = fl[v] ? 1 : 0;
+        std::vector<u64> nn(nNnx);
+        for (int i = 0; i < nNnx; ++i) {
+            const int k = nnxPairs[2 * i], m = nnxPairs[2 * i + 1];
+            if (k < 0 || k >= nV) return (int)CIPC_ERR_ARG;
+            fl[k] |= 2;
+            nn[i] = ((u64)(u32)k << 32) | (u32)m;
+        }
+        std::sort(nn.begin(), nn.end());
+        std::vector<int> v2(nV, 0);
+        for (int i = 0; i < nBN; ++i) {
+            if (BN[i] < 0 || BN[i] >= nV) return (int)CIPC_ERR_ARG;
+            v2[BN[i]] = i;
+        }
+        CIPC_CUDA(cudaMemcpyAsync(c->flags.p, fl.data(), nV, cudaMemcpyHostToDevice, c->st));
+        CIPC_CUDA(cudaMemcpyAsync(c->v2sv.p, v2.data(), (size_t)nV * 4, cudaMemcpyHostToDevice, c->st));
+        c->nnx.reserve(std::max(nNnx, 1), c->st);
+        if (nNnx) CIPC_CUDA(cudaMemcpyAsync(c->nnx.p, nn.data(), (size_t)nNnx * 8, cudaMemcpyHostToDevice, c->st));
+        if (BNArea && BEArea && BTArea) {
+            c->BNArea.reserve(std::max(nBN, 1), c->st); c->BEArea.reserve(std::max(nBE, 1), c->st); c->BTArea.reserve(std::max(nBT, 1), c->st);
+            CIPC_CUDA(cudaMemcpyAsync(c->BEArea.p, BEArea, (size_t)nBE * 8, cudaMemcpyHostToDevice, c->st));
+            CIPC_CUDA(cudaMemcpyAsync(c->BTArea.p, BTArea, (size_t)nBT * 8, cudaMemcpyHostToDevice, c->st));
+        }
+        CIPC_CUDA(cudaStreamSynchronize(c->st)); // host vectors above go out of scope
+        T.BN = c->BN.p; T.BE = c->BE.p; T.BT = c->BT.p; T.flags = c->flags.p; T.v2sv = c->v2sv.p; T.nnx = c->nnx.p; T.nNnx = nNnx;
+        c->topoHash = h;
+        c->haveX = c->haveX0 = c->haveP = false;
+        c->nC = 0;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes)
+{
+    return guarded(ctx, [&]() {
+        need(ctx->T.nV > 0, "topology not set");
+        upload_vec3(ctx, ctx->X, X, stride_bytes);
+        ctx->haveX = true;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes)
+{
+    return guarded(ctx, [&]() {
+        need(ctx->T.nV > 0, "topology not set");
+        upload_vec3(ctx, ctx->X0, X0, stride_bytes);
+        ctx->haveX0 = true;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_set_search_dir(cipc_ctx* ctx, const double* p)
+{
+    return guarded(ctx, [&]() {
+        need(ctx->T.nV > 0, "topology not set");
+        upload_vec3(ctx, ctx->P, p, 24);
+        ctx->haveP = true;
+        return (int)CIPC_OK;
+    });
+}
+
+int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickness, int* nC_out)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->haveX && c->haveX0, "positions / rest positions not set");
+        if (elastic) return (int)CIPC_ERR_UNSUPPORTED; // every FEMShell scene runs initialize_OIPC (elasticIPC=false)
+        c->begin_call();
+        const Topo& T = c->T;
+        const double dHat = std::sqrt(dHat2) + thickness; // IPC.h:53-54
+        const double dHat2o = dHat * dHat;
+        HashInfo H;
+        {
+            cipc_ctx::Scope sc(c, "ccs_hash_build");
+            double voxelSize = 1.0;
+            if (T.nBE) voxelSize *= mean_edge_len(c);
+            else voxelSize = 4.0 * dHat;
+            double mn[3], mx[3];
+            bbox_to_host(c, nullptr, 0.0, mn, mx);
+            double mag = 0;
+            for (int d = 0; d < 3; ++d) mag = std::max(mag, std::max(std::fabs(mn[d]), std::fabs(mx[d])));
+            // inflation radius: half the activation distance plus a rounding guard, so that any pair
+            // that passes the reference's AABB gap test (gap <= dHat) shares a voxel
+            const double r = 0.5 * dHat * (1.0 + 1e-9) + 8.0 * 2.220446049250313e-16 * mag;
+            for (int d = 0; d < 3; ++d) { mn[d] -= r; mx[d] += r; }
+            if (!size_grid(mn, mx, voxelSize, H.G, true)) return (int)CIPC_ERR_GRID;
+            const int nP = T.nBN + T.nBE + T.nBT;
+            c->boxLo.reserve(nP, c->st); c->boxHi.reserve(nP, c->st); c->cnt.reserve(nP, c->st);
+            CIPC_LAUNCH(k_boxes_ccs, div_up(nP, TB), TB, 0, c->st, T, c->X.p, H.G, r, c->boxLo.p, c->boxHi.p, c->cnt.p);
+            build_cell_lists(c, H);
+        }
+        u32 counts[4];
+        {
+            cipc_ctx::Scope sc(c, "ccs_pairs");
+            run_pairs<false>(c, H, dHat, counts);
+        }
+        c->ctr["candidates_pt"] = counts[0]; c->ctr["candidates_ee"] = counts[1];
+        c->ctr["candidates_pe"] = counts[2]; c->ctr["candidates_pp"] = counts[3];
+        const size_t total = (size_t)counts[0] + counts[1] + counts[2] + counts[3];
+        c->cs.reserve(total + 1, c->st);
+        c->raw.reserve(total + 1, c->st);
+        u32 hc[2];
+        {
+            cipc_ctx::Scope sc(c, "ccs_narrow");
+            CIPC_CUDA(cudaMemsetAsync(c->counters.p + 8, 0, 4 * sizeof(u32), c->st));
+            NarrowOut out{c->cs.p, c->raw.p, c->counters.p + 8};
+            if (counts[0]) CIPC_LAUNCH(k_narrow_pt, div_up(counts[0], 128), 128, 0, c->st, T, c->X.p, c->cand[0].p, counts[0], dHat2o, out);
+            if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->X0.p, c->cand[1].p, counts[1], dHat2o, out);
+            if (counts[2]) CIPC_LAUNCH(k_narrow_pe, div_up(counts[2], 128), 128, 0, c->st, T, c->X.p, c->cand[2].p, counts[2], dHat2o, out);
+            if (counts[3]) CIPC_LAUNCH(k_narrow_pp, div_up(counts[3], 128), 128, 0, c->st, T, c->X.p, c->cand[3].p, counts[3], dHat2o, out);
+            CIPC_CUDA(cudaMemcpyAsync(hc, c->counters.p + 8, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+        }
+        u32 nC = hc[0];
+        {
+            cipc_ctx::Scope sc(c, "ccs_merge");
+            const u32 nRaw = hc[1];
+            if (nRaw) {
+                u32 nSlots = 1024;
+                while (nSlots < 2 * nRaw) nSlots <<= 1;
+                c->slots.reserve(nSlots, c->st); c->slotCnt.reserve(nSlots, c->st);
+                CIPC_CUDA(cudaMemsetAsync(c->slots.p, 0xff, (size_t)nSlots * 4, c->st));
+                CIPC_CUDA(cudaMemsetAsync(c->slotCnt.p, 0, (size_t)nSlots * 4, c->st));
+                CIPC_LAUNCH(k_dedup_insert, div_up(nRaw, TB), TB, 0, c->st, c->raw.p, nRaw, c->slots.p, c->slotCnt.p, nSlots - 1);
+                // the unique PP/PE stencils are appended behind the pass-through ones (counter keeps running)
+                CIPC_LAUNCH(k_dedup_emit, div_up(nSlots, TB), TB, 0, c->st, c->raw.p, c->slots.p, c->slotCnt.p, nSlots, c->cs.p, c->counters.p + 8);
+                CIPC_CUDA(cudaMemcpyAsync(&nC, c->counters.p + 8, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+                CIPC_CUDA(cudaStreamSynchronize(c->st));
+            }
+            c->info.reserve((size_t)nC + 1, c->st);
+            if (nC) CIPC_LAUNCH(k_fill_info, div_up(nC, TB), TB, 0, c->st, c->info.p, nC, 1.0, dHat2o);
+        }
+        c->nC = nC;
+        c->ctr["constraints"] = nC;
+        if (nC_out) *nC_out = (int)nC;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        if (c->nC == 0) return (int)CIPC_OK;
+        if (cs) CIPC_CUDA(cudaMemcpyAsync(cs, c->cs.p, (size_t)c->nC * 16, cudaMemcpyDeviceToHost, c->st));
+        if (info) CIPC_CUDA(cudaMemcpyAsync(info, c->info.p, (size_t)c->nC * 16, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        return (int)CIPC_OK;
+    });
+}
+int cipc_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int nC)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        if (nC < 0) return (int)CIPC_ERR_ARG;
+        c->cs.reserve((size_t)nC + 1, c->st); c->info.reserve((size_t)nC + 1, c->st);
+        if (nC) {
+            CIPC_CUDA(cudaMemcpyAsync(c->cs.p, cs, (size_t)nC * 16, cudaMemcpyHostToDevice, c->st));
+            CIPC_CUDA(cudaMemcpyAsync(c->info.p, info, (size_t)nC * 16, cudaMemcpyHostToDevice, c->st));
+        }
+        c->nC = (u32)nC;
+        return (int)CIPC_OK;
+    });
+}
+
+int cipc_barrier_energy_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness)
+{
+    return guarded(ctx, [&]() { ctx->begin_call(); return do_barrier_energy(ctx, elastic, dHat2, kappa, thickness); });
+}
+int cipc_barrier_energy(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* E)
+{
+    return guarded(ctx, [&]() {
+        ctx->begin_call();
+        int r = do_barrier_energy(ctx, elastic, dHat2, kappa, thickness);
+        if (r) return r;
+        double v;
+        CIPC_CUDA(cudaMemcpyAsync(&v, ctx->scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        r = fetch_err(ctx);
+        if (r) return r;
+        *E += v;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness)
+{
+    return guarded(ctx, [&]() { ctx->begin_call(); return do_barrier_gradient(ctx, elastic, dHat2, kappa, thickness); });
+}
+int cipc_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* g, int stride)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        if (stride < 24 || stride % 8) return (int)CIPC_ERR_ARG;
+        c->begin_call();
+        int r = do_barrier_gradient(c, elastic, dHat2, kappa, thickness);
+        if (r) return r;
+        const size_t n = (size_t)c->T.nV;
+        double* h = (double*)c->pin.reserve(n * 24);
+        CIPC_CUDA(cudaMemcpyAsync(h, c->g.p, n * 24, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        const size_t sd = stride / 8;
+        for (size_t v = 0; v < n; ++v) { // nodeAttr.g += (IPC.h:1034-1042)
+            g[v * sd] += h[3 * v]; g[v * sd + 1] += h[3 * v + 1]; g[v * sd + 2] += h[3 * v + 2];
+        }
+        return (int)CIPC_OK;
+    });
+}
+int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
+    int64_t* nTrip)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->haveX, "positions not set");
+        c->begin_call();
+        const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
+        c->nTrip = 0;
+        if (c->nC) {
+            cipc_ctx::Scope sc(c, "barrier_H");
+            c->tripOff.reserve(c->nC, c->st);
+            CIPC_LAUNCH(k_block_sizes, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->tripOff.p);
+            device_excl_scan(c->tripOff.p, c->tripOff.p, c->nC, c->scanwk, c->st);
+            u32 tot;
+            CIPC_CUDA(cudaMemcpyAsync(&tot, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+            if ((u64)c->nC * 144 > 0xffffffffull) return (int)CIPC_ERR_UNSUPPORTED; // 32-bit triplet offsets
+            c->nTrip = tot;
+            c->trip.reserve(tot, c->st);
+            CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->nC, bp,
+                projectSPD, c->trip.p);
+        }
+        if (nTrip) *nTrip = c->nTrip;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
+{
+    return guarded(ctx, [&]() {
+        if (ctx->nTrip) {
+            CIPC_CUDA(cudaMemcpyAsync(out, ctx->trip.p, (size_t)ctx->nTrip * sizeof(cipc_triplet), cudaMemcpyDeviceToHost, ctx->st));
+            CIPC_CUDA(cudaStreamSynchronize(ctx->st));
+        }
+        return (int)CIPC_OK;
+    });
+}
+int cipc_step_size_dev(cipc_ctx* ctx, int elastic, double thickness, double stepIn)
+{
+    return guarded(ctx, [&]() { ctx->begin_call(); return do_step_size(ctx, elastic, thickness, stepIn); });
+}
+int cipc_step_size(cipc_ctx* ctx, int elastic, double thickness, double* step)
+{
+    return guarded(ctx, [&]() {
+        ctx->begin_call();
+        int r = do_step_size(ctx, elastic, thickness, *step);
+        if (r) return r;
+        double v;
+        CIPC_CUDA(cudaMemcpyAsync(&v, ctx->scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        r = fetch_err(ctx);
+        if (r) return r;
+        *step = v;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_min_dist2_dev(cipc_ctx* ctx, double thickness)
+{
+    (void)thickness;
+    return guarded(ctx, [&]() { ctx->begin_call(); return do_min_dist(ctx, false); });
+}
+int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        c->begin_call();
+        if (c->nC == 0) return (int)CIPC_ERR_ARG; // reference dereferences min_element of an empty vector
+        int r = do_min_dist(c, dist2 != nullptr);
+        if (r) return r;
+        long long bits;
+        CIPC_CUDA(cudaMemcpyAsync(&bits, c->scal.p + 2, 8, cudaMemcpyDeviceToHost, c->st));
+        if (dist2) CIPC_CUDA(cudaMemcpyAsync(dist2, c->dist2.p, (size_t)c->nC * 8, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        bits = bits >= 0 ? bits : (bits ^ 0x7fffffffffffffffLL);
+        double m;
+        memcpy(&m, &bits, 8);
+        *minDist2 = m - thickness * thickness;
+        return (int)CIPC_OK;
+    });
+}
+
+double* cipc_dev_positions(cipc_ctx* ctx) { return ctx ? (double*)ctx->X.p : nullptr; }
+double* cipc_dev_gradient(cipc_ctx* ctx) { return ctx ? ctx->g.p : nullptr; }
+double* cipc_dev_scalars(cipc_ctx* ctx) { return ctx ? ctx->scal.p : nullptr; }
+
+double cipc_stage_ms(cipc_ctx* ctx, const char* stage)
+{
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->dev);
+    cudaStreamSynchronize(ctx->st);
+    double tot = -1;
+    for (auto& s : ctx->stages)
+        if (s.name == stage) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) tot = (tot < 0 ? 0 : tot) + ms;
+        }
+    return tot;
+}
+int64_t cipc_counter(cipc_ctx* ctx, const char* name)
+{
+    if (!ctx) return -1;
+    auto it = ctx->ctr.find(name);
+    return it == ctx->ctr.end() ? -1 : it->second;
+}
+
+// ---- test hooks
+int cipc_test_scan(cipc_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint32_t* total)
+{
+    return guarded(ctx, [&]() {
+        DevBuf<u32> d;
+        d.reserve(n + 1, ctx->st);
+        CIPC_CUDA(cudaMemcpyAsync(d.p, in, n * 4, cudaMemcpyHostToDevice, ctx->st));
+        device_excl_scan(d.p, d.p, n, ctx->scanwk, ctx->st);
+        CIPC_CUDA(cudaMemcpyAsync(out, d.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CIPC_CUDA(cudaMemcpyAsync(total, ctx->scanwk.total.p, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CIPC_CUDA(cudaStreamSynchronize(ctx->st));
+        return (int)CIPC_OK;
+    });
+}
+int cipc_test_sort(cipc_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits)
+{
+    return guarded(ctx, [&]() {
+        DevBuf<u32> k, v;
+        k.reserve(n + 1, ctx->st); v.reserve(n + 1, ctx->st);
+        CIPC_CUDA(cudaMemcpyAsync(k.p, keys, n * 4, cudaMemcpyHostToDevice, ctx->st));
+        CIPC_CUDA(cudaMemcpyAsync(v.p, vals, n * 4, cudaMemcpyHostToDevice, ctx->st));
+        device_radix_sort(k.p, v.p, n, bits, ctx->sortwk, ctx->st);
+        CIPC_CUDA(cudaMemcpyAsync(keys, k.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CIPC_CUDA(cudaMemcpyAsync(vals, v.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CIPC_CUDA(cudaStreamSynchronize(ctx->st));
+        return (int)CIPC_OK;
+    });
+}
+int cipc_test_make_pd(cipc_ctx* ctx, double* H, int n, int count)
+{
+    return guarded(ctx, [&]() {
+        if (n != 6 && n != 9 && n != 12) return (int)CIPC_ERR_ARG;
+        DevBuf<double> d;
+        const size_t tot = (size_t)count * n * n;
+        d.reserve(tot + 1, ctx->st);
+        CIPC_CUDA(cudaMemcpyAsync(d.p, H, tot * 8, cudaMemcpyHostToDevice, ctx->st));
+        if (n == 12) CIPC_LAUNCH(k_test_make_pd<12>, div_up(count, 64), 64, 0, ctx->st, d.p, count);
+        else if (n == 9) CIPC_LAUNCH(k_test_make_pd<9>, div_up(count, 64), 64, 0, ctx->st, d.p, count);
+        else CIPC_LAUNCH(k_test_make_pd<6>, div_up(count, 64), 64, 0, ctx->st, d.p, count);
+        CIPC_CUDA(cudaMemcpyAsync(H, d.p, tot * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CIPC_CUDA(cudaStreamSynchronize(ctx->st));
+        return (int)CIPC_OK;
+    });
+}
+
+} // extern "C"

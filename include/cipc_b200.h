@@ -1,0 +1,127 @@
+/* cipc_b200.h -- C ABI of the B200-native C-IPC contact hot path (libcipc_b200.so).
+ *
+ * The reference (ipc-sim/Codim-IPC) has no FFI layer for this path: it is six header-only C++
+ * function templates in Library/FEM/IPC.h instantiated inside the pybind11 module.  Each entry
+ * point below is what a binding for one of those templates calls; `shim/FEM/IPC.h` in this repo
+ * re-declares the six templates with the reference's signatures on top of this ABI (see
+ * INTEGRATION.md).  All pointers are HOST pointers unless the name says `_dev`.  All functions
+ * return a cipc_status; nothing falls back to the CPU -- without a CUDA device cipc_create fails.
+ *
+ * Reference interface replaced (file:line under /root/reference/Library):
+ *   cipc_constraint_set   <- Compute_Constraint_Set              FEM/IPC.h:19-36   (3-D branch :143-661)
+ *   cipc_barrier_energy   <- Compute_Barrier                     FEM/IPC.h:742-748
+ *   cipc_barrier_gradient <- Compute_Barrier_Gradient            FEM/IPC.h:943-948
+ *   cipc_barrier_hessian  <- Compute_Barrier_Hessian             FEM/IPC.h:1258-1265
+ *   cipc_step_size        <- Compute_Intersection_Free_StepSize  FEM/IPC.h:1879-1890
+ *   cipc_min_dist2        <- Compute_Min_Dist2                   FEM/IPC.h:2246-2249
+ *   cipc_set_topology / cipc_set_positions / cipc_set_rest_positions / cipc_set_search_dir
+ *                         <- the Storage->device marshalling of MESH_NODE / MESH_NODE_ATTR
+ *                            (FEM/DATA_TYPE.h:7-31, Math/VECTOR.h:33-47: element i of a
+ *                            VECTOR<double,3> store is 4 contiguous doubles = 32 bytes).
+ */
+#ifndef CIPC_B200_H
+#define CIPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cipc_ctx cipc_ctx;
+
+typedef enum {
+    CIPC_OK = 0,
+    CIPC_ERR_CUDA = 1,             /* CUDA runtime failure or no device; message in cipc_last_error */
+    CIPC_ERR_NONPOSITIVE_DIST = 2, /* reference: printf("%le distance detected ...") + exit(-1)  IPC.h:773-776 */
+    CIPC_ERR_ZERO_STEP = 3,        /* reference: coordinate dump + exit(-1)                   IPC.h:2014-2032 */
+    CIPC_ERR_ARG = 4,
+    CIPC_ERR_GRID = 5,             /* voxel grid does not fit the 30-bit cell key */
+    CIPC_ERR_UNSUPPORTED = 6
+} cipc_status;
+
+/* 16-byte triplet, layout-identical to Eigen::Triplet<double,int> {int row; int col; double value;} */
+typedef struct { int32_t row, col; double val; } cipc_triplet;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  rank/world: this process' share of the candidate-pair work (multi-GPU:
+ * one process per GPU); rank=0, world=1 for a single GPU. */
+int cipc_create(int device, int rank, int world, cipc_ctx** out);
+void cipc_destroy(cipc_ctx* ctx);
+const char* cipc_last_error(cipc_ctx* ctx);
+
+/* ---- marshalling ---------------------------------------------------------------------- */
+/* Boundary primitive lists as the reference builds them every step (FEM/Shell/IMPLICIT_EULER.h:224-300).
+ * be_stride / bt_stride: ints between consecutive edges / triangles (2 or 4; 3 or 4 -- VECTOR<int,k>
+ * is 16 bytes, i.e. stride 4).  dbc: nV bytes (DBCb).  nnx: NNExclusion flattened to (key,member)
+ * pairs.  Areas may be NULL unless elasticIPC is used.  Re-uploads only when the content changed. */
+int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE, const int32_t* BE, int be_stride,
+                      int nBT, const int32_t* BT, int bt_stride, int nRod, const int32_t codimBNStartInd[2],
+                      const uint8_t* dbc, int nNnxPairs, const int32_t* nnxPairs,
+                      const double* BNArea, const double* BEArea, const double* BTArea);
+/* stride_bytes: 32 for the reference's VECTOR<double,3> storage, 24 for packed xyz */
+int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes);
+int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes);
+int cipc_set_search_dir(cipc_ctx* ctx, const double* p /* 3*nV packed, like std::vector<T> searchDir */);
+
+/* ---- Compute_Constraint_Set ------------------------------------------------------------ */
+/* Builds the constraint set for the resident positions; it stays resident on the device.
+ * nC_out: number of constraints held by THIS rank. */
+int cipc_constraint_set(cipc_ctx* ctx, int elasticIPC, double dHat2, double thickness, int* nC_out);
+/* copies the resident set out: cs = nC x 4 int32 (VECTOR<int,4> stride 4), info = nC x 2 double */
+int cipc_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info);
+/* makes a caller-owned set resident (used when the caller's vectors are not the last ones produced) */
+int cipc_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int nC);
+
+/* ---- barrier terms on the resident constraint set and positions --------------------------- */
+/* E_inout += sum_c w_c m_c b(d_c) e_c          (accumulates like the reference, IPC.h:940) */
+int cipc_barrier_energy(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness, double* E_inout);
+/* g[v] += ...  g_stride_bytes between consecutive nodes' 3 doubles (nodeAttr.g inside the AoSoA: see INTEGRATION.md) */
+int cipc_barrier_gradient(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
+                          double* g, int g_stride_bytes);
+/* computes all (PSD-projected) blocks on the device; nTriplets_out = 144/81/36 per constraint */
+int cipc_barrier_hessian(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
+                         int projectSPD, int64_t* nTriplets_out);
+/* copies the triplets of the last cipc_barrier_hessian to `out` (caller appends them, IPC.h:1371-1388) */
+int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out);
+
+/* ---- Compute_Intersection_Free_StepSize --------------------------------------------------- */
+/* stepSize_inout: in = current upper bound, out = min(bound [possibly shrunk by the span rule,
+ * Grid/SPATIAL_HASH.h:466-482], min over candidate pairs of the ACCD time of impact) of THIS rank's pairs */
+int cipc_step_size(cipc_ctx* ctx, int elasticIPC, double thickness, double* stepSize_inout);
+
+/* ---- Compute_Min_Dist2 ---------------------------------------------------------------------- */
+/* dist2 may be NULL; minDist2 = min_c dist2[c] - thickness^2 */
+int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2);
+
+/* ---- device-resident access (multi-GPU reductions, benchmarking) ----------------------------- */
+double* cipc_dev_positions(cipc_ctx* ctx);      /* nV x 4 doubles (x,y,z,pad) */
+double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient_dev */
+double* cipc_dev_scalars(cipc_ctx* ctx);        /* [0]=energy partial, [1]=step size, [2]=min dist2 of the last *_dev call */
+/* same stages with every result left on the device (no D2H): */
+int cipc_barrier_energy_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
+int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
+int cipc_step_size_dev(cipc_ctx* ctx, int elasticIPC, double thickness, double stepSize_in);
+int cipc_min_dist2_dev(cipc_ctx* ctx, double thickness);
+int cipc_sync(cipc_ctx* ctx);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* device milliseconds (CUDA events on the library's stream) of the named stage of the last call:
+ * "ccs_hash_build","ccs_pairs","ccs_narrow","ccs_merge","barrier_E","barrier_g","barrier_H",
+ * "ccd_hash_build","ccd_pairs","ccd_accd","min_dist" ; -1 if unknown */
+double cipc_stage_ms(cipc_ctx* ctx, const char* stage);
+/* counters of the last call: "candidates_pt","candidates_ee","candidates_pe","candidates_pp",
+ * "hash_entries","hash_cells","constraints","ccd_pairs" ; -1 if unknown */
+int64_t cipc_counter(cipc_ctx* ctx, const char* name);
+int64_t cipc_kernel_launches(void);  /* kernels launched by this library since load */
+const char* cipc_version(void);
+
+/* ---- test hooks (device primitives, exercised by tests/) ----------------------------------- */
+int cipc_test_scan(cipc_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint32_t* total);
+int cipc_test_sort(cipc_ctx* ctx, uint32_t* keys, uint32_t* vals, int64_t n, int bits);
+int cipc_test_make_pd(cipc_ctx* ctx, double* H /* count x n x n */, int n, int count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIPC_B200_H */

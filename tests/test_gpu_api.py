@@ -1,0 +1,76 @@
+"""The reference-named entry points (codim_ipc_b200.Compute_*) keep the reference's call semantics:
+outputs resized and filled, E accumulated, g accumulated in place, triplets appended, step in/out."""
+import numpy as np
+import pytest
+
+from helpers import sort_cs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_named_entry_points():
+    import codim_ipc_b200 as cipc
+    from codim_ipc_b200 import scenes
+    from oracle import cipc_oracle as O
+    sc = scenes.mixed_small()
+    S = O.OracleScene(sc)
+    rod = sc["BE"][len(sc["BE"]) - sc["nRod"]:]
+    particle = sc["BN"][sc["codim"][1]:]
+    X4 = np.zeros((len(sc["X"]), 4)); X4[:, :3] = sc["X"]  # VECTOR<double,3> storage: 32-byte elements
+    cs, ptee, info = cipc.Compute_Constraint_Set(X4, sc["X0"], sc["BN"], sc["BE"], sc["BT"], particle, rod, sc["NNX"], sc["BNArea"],
+                                                 sc["BEArea"], sc["BTArea"], sc["codim"], sc["DBC"], sc["dHat2"], sc["xi"], False)
+    cs_o, info_o = S.constraint_set(sc["dHat2"], sc["xi"])
+    assert np.array_equal(sort_cs(cs), sort_cs(cs_o)) and len(ptee) == 0
+    E = cipc.Compute_Barrier(X4, sc["X0"], cs, info, sc["dHat2"], sc["kappa"], sc["xi"], 1.5)
+    assert abs((E - 1.5) - S.barrier(cs, info, sc["dHat2"], sc["kappa"], sc["xi"])) <= 1e-9 * abs(E - 1.5)
+    g = np.ones((len(sc["X"]), 4))
+    cipc.Compute_Barrier_Gradient(X4, cs, info, sc["dHat2"], sc["kappa"], sc["xi"], sc["X0"], g)
+    g_o = S.barrier_gradient(cs, info, sc["dHat2"], sc["kappa"], sc["xi"])
+    assert np.abs(g[:, :3] - 1.0 - g_o).max() <= 1e-9 * np.abs(g_o).max() and np.all(g[:, 3] == 1.0)
+    pre = np.zeros(7, cipc.TRIPLET_DTYPE); pre["val"] = 3.0
+    trip = cipc.Compute_Barrier_Hessian(X4, sc["X0"], cs, info, sc["dHat2"], sc["kappa"], sc["xi"], True, pre)
+    r_o, c_o, v_o = S.barrier_hessian(cs, info, sc["dHat2"], sc["kappa"], sc["xi"])
+    assert len(trip) == 7 + len(v_o) and np.all(trip["val"][:7] == 3.0) and np.array_equal(trip["row"][7:], r_o)
+    a = cipc.Compute_Intersection_Free_StepSize(X4, sc["BN"], sc["BE"], sc["BT"], particle, rod, sc["NNX"], sc["codim"], sc["DBC"],
+                                                sc["p"].ravel(), sc["xi"], 1.0)
+    a_o = S.step_size(sc["p"], sc["xi"], 1.0)
+    assert a <= a_o and a_o - a <= 1e-12 * a_o
+    d, m = cipc.Compute_Min_Dist2(X4, cs, sc["xi"])
+    d_o, m_o = S.min_dist2(cs, sc["xi"])
+    assert np.array_equal(d, d_o) and m == m_o
+
+
+def test_topology_reupload_only_on_change(ctx):
+    from codim_ipc_b200 import scenes
+    sc = scenes.cloth_stack(10, 2)
+    ctx.set_scene(sc)
+    n1 = ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+    ctx.set_scene(sc)  # identical content: the hash matches, resident copy kept
+    n2 = ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+    sc2 = scenes.cloth_stack(10, 3)
+    ctx.set_scene(sc2)
+    n3 = ctx.constraint_set(sc2["dHat2"], sc2["xi"], fetch=False)
+    assert n1 == n2 and n3 > n1
+
+
+def test_rank_partition_covers_all_pairs():
+    """world=2 contexts on one device: the union of the two ranks' pass-through constraints and the
+    merged PP/PE multiplicities equals the single-rank result."""
+    import codim_ipc_b200 as cipc
+    from codim_ipc_b200 import scenes, multi
+    sc = scenes.cloth_stack(24, 4)
+    full = cipc.ContactContext(0)
+    full.set_scene(sc)
+    cs_full, _ = full.constraint_set(sc["dHat2"], sc["xi"])
+    parts = []
+    for r in range(2):
+        c = cipc.ContactContext(0, rank=r, world=2)
+        c.set_scene(sc)
+        parts.append(c.constraint_set(sc["dHat2"], sc["xi"])[0])
+        a_r = c.step_size(sc["xi"], 1.0)
+        parts.append(a_r)
+        c.close()
+    merged = multi.merge_constraint_sets([parts[0], parts[2]])
+    assert np.array_equal(sort_cs(merged), sort_cs(cs_full))
+    assert min(parts[1], parts[3]) == full.step_size(sc["xi"], 1.0)
+    full.close()
