@@ -216,25 +216,26 @@ def cloth_on_sphere(n=112, dHat=1e-3, xi=0.0, seed=1, draped=False):
 
 
 def noodles(nrod=25, nseg=200, dHat=5e-4, xi=1e-3, seed=3):
-    """cfg3: nrod x nrod discrete rods of nseg segments (length 0.4) packed at centre spacing
-    xi+0.5*dHat above a bowl-like DBC mesh (Projects/FEMShell/10_noodles.py:26-31,44)."""
+    """cfg3: nrod x nrod discrete rods of nseg segments (length 0.4) packed in crossing layers at centre
+    spacing xi+0.5*dHat above a DBC plate (Projects/FEMShell/10_noodles.py:26-31,44)."""
     rng = np.random.default_rng(seed)
     gap = xi + 0.5 * dHat
     rods = []
     t = np.linspace(0, 0.4, nseg + 1)
-    for i in range(nrod):
+    for i in range(nrod):  # layer i at height (i+1)*gap; even layers run along x, odd layers along z
         for j in range(nrod):
-            # neighbouring rods run in alternating directions (x / z) on stacked levels so that rods cross
-            if (i + j) % 2 == 0:
-                V = np.stack([t - 0.2, np.full_like(t, (i % 2) * gap * 2 + gap), np.full_like(t, (j - nrod / 2) * gap * 2)], 1)
+            off = (j - nrod / 2) * gap
+            if i % 2 == 0:
+                V = np.stack([t - 0.2, np.full_like(t, (i + 1) * gap), np.full_like(t, off)], 1)
             else:
-                V = np.stack([np.full_like(t, (i - nrod / 2) * gap * 2), np.full_like(t, (j % 2) * gap * 2 + 2 * gap), t - 0.2], 1)
+                V = np.stack([np.full_like(t, off), np.full_like(t, (i + 1) * gap), t - 0.2], 1)
             V = V + rng.normal(0, 0.05 * dHat, V.shape)
             rods.append((V, False))
-    Vb, Fb = uv_sphere(34, 34, 0.45)
-    keep = Vb[Fb].mean(1)[:, 1] < -0.05  # lower cap = bowl
-    Fb = Fb[keep]
-    Vb[:, 1] += 0.45 - 0.5 * gap
+    # obstacle under the pile (the reference uses bowl.obj, absent here): a flat ~2.3K-triangle DBC
+    # plate 1.04*gap below the lowest rod layer, i.e. inside the activation distance
+    Vb, Fb = grid_mesh(34, side=0.5)
+    Vb = rot_y(Vb, 9.0)
+    Vb[:, 1] = -0.04 * gap
     sc = assemble([(Vb, Fb, True)], rods=rods, dHat=dHat, xi=xi, seed=seed + 2)
     sc["name"] = "noodles_%dx%dx%d" % (nrod, nrod, nseg)
     return sc
