@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- contact-stage benchmark of the B200 C-IPC hot path (BASELINE.json metric).
+
+A "step" is one contact stage of a Newton iteration on one synthetic scene:
+    1x Compute_Constraint_Set + 1x Compute_Barrier + 1x Compute_Barrier_Gradient
+    + 1x Compute_Barrier_Hessian (PSD-projected) + 1x Compute_Intersection_Free_StepSize + 2x Compute_Min_Dist2
+Workload: cfg5, the 1M-triangle stacked-cloth scene the BASELINE target is quoted on
+(10 layers x 224 x 224 x 2 triangles, gap xi + dHat/2, dense self contact); `--workload` picks another.
+
+  value  : ms per step with every input resident in HBM (device-side CUDA events, max over ranks)
+  e2e    : ms per step through the reference-named host API (codim_ipc_b200.Compute_* call pattern of the
+           shim: host numpy/pinned buffers in, constraint set / gradient / Hessian triplets / dist2 out),
+           host<->device copies inside the timed region
+  N > 1  : the same scene, candidate pairs partitioned across ranks by cell ranges of the sorted hash
+           ("strong" scaling); NCCL all-reduces the step size (min), energy and gradient (sum), min-dist (min)
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded
+sample of the same workload, scaled to the full size (the reference itself cannot be built offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "IPC contact-stage ms/Newton iter (hash+barrier Hessian+ACCD)"
+WORKLOADS = {  # name -> (n, layers)
+    "cfg5_1m": (224, 10),
+    "cfg5_250k": (112, 10),
+    "cfg5_62k": (56, 10),
+}
+CPU_SAMPLE = {"cfg5_1m": ("cfg5_250k", 4.0), "cfg5_250k": ("cfg5_62k", 4.0), "cfg5_62k": ("cfg5_62k", 1.0)}
+
+
+def make_scene(name):
+    from codim_ipc_b200 import scenes
+    n, L = WORKLOADS[name]
+    return scenes.cloth_stack(n, L)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi every 200 ms while the timed region runs (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_contact_stage(sc, threads=None):
+    """one contact stage on the CPU oracle; returns (seconds, per-stage dict, nConstraints)"""
+    from oracle import cipc_oracle as O
+    if threads:
+        O.set_num_threads(threads)
+    S = O.OracleScene(sc)
+    st = {}
+    t0 = time.perf_counter()
+    cs, info = S.constraint_set(sc["dHat2"], sc["xi"]); t1 = time.perf_counter(); st["constraint_set"] = t1 - t0
+    S.barrier(cs, info, sc["dHat2"], sc["kappa"], sc["xi"]); t2 = time.perf_counter(); st["barrier_E"] = t2 - t1
+    S.barrier_gradient(cs, info, sc["dHat2"], sc["kappa"], sc["xi"]); t3 = time.perf_counter(); st["barrier_g"] = t3 - t2
+    S.barrier_hessian_notfetch(cs, info, sc["dHat2"], sc["kappa"], sc["xi"], True); t4 = time.perf_counter(); st["barrier_H"] = t4 - t3
+    S.step_size(sc["p"], sc["xi"], 1.0); t5 = time.perf_counter(); st["step_size"] = t5 - t4
+    S.min_dist2(cs, sc["xi"]); S.min_dist2(cs, sc["xi"]); t6 = time.perf_counter(); st["min_dist_x2"] = t6 - t5
+    return t6 - t0, st, len(cs)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cipc_oracle as O
+    sample, scale = CPU_SAMPLE[args.workload]
+    sc = make_scene(sample)
+    cores = O.num_threads()
+    times = []
+    for i in range(args.warmup + args.steps):
+        t, st, nC = cpu_contact_stage(sc)
+        if i >= args.warmup:
+            times.append(t)
+    ms = 1e3 * float(np.mean(times)) * scale
+    desc = "oracle port (-O3 -mavx2 -mfma -fopenmp, reference's parallel structure) on %s (%d triangles, %d constraints), x%.0f to %s" % (
+        sample, len(sc["BT"]), nC, scale, args.workload)
+    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "triangles": WORKLOADS[args.workload][0] ** 2 * 2 * WORKLOADS[args.workload][1]},
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg5_1m", choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--stage-report", action="store_true", help="print the per-stage device times to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import codim_ipc_b200 as cipc
+    from codim_ipc_b200 import multi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dc = multi.DistContact() if world > 1 else None
+
+    sc = make_scene(args.workload)
+    nV, nT = len(sc["X"]), len(sc["BT"])
+    ctx = cipc.ContactContext(local, rank, world)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)  # the library's kernels, torch events and NCCL share one stream
+    ctx.set_scene(sc)
+    dHat2, xi, kappa = sc["dHat2"], sc["xi"], sc["kappa"]
+    scal = multi.wrap_device_f64(ctx.dev_ptrs()["scalars"], 16, local)
+
+    def allreduce(t, op):
+        if dc is not None:
+            dc.dist.all_reduce(t, op=op)
+
+    def device_step():
+        """inputs resident; results stay on the device"""
+        nC = ctx.constraint_set(dHat2, xi, fetch=False)
+        ctx.barrier_energy_dev(dHat2, kappa, xi)
+        if dc is not None:
+            allreduce(scal[0:1], dc.dist.ReduceOp.SUM)
+        ctx.barrier_gradient_dev(dHat2, kappa, xi)
+        if dc is not None:
+            allreduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, local), dc.dist.ReduceOp.SUM)
+        nTrip = ctx.barrier_hessian(dHat2, kappa, xi, True, fetch=False)
+        ctx.step_size_dev(xi, 1.0)
+        if dc is not None:
+            allreduce(scal[1:2], dc.dist.ReduceOp.MIN)
+        for _ in range(2):
+            ctx.min_dist2_dev(xi)
+            if dc is not None:
+                allreduce(scal[2:3], dc.dist.ReduceOp.MIN)
+        return nC, nTrip
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        nC, nTrip = device_step()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    stage_names = ["ccs_hash_build", "ccs_pairs", "ccs_narrow", "ccs_merge", "barrier_E", "barrier_g", "barrier_H", "k_barrier_hessian",
+                   "ccd_hash_build", "ccd_pairs", "ccd_accd", "min_dist"]
+    launches0 = cipc.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kH_ms = []
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
+        ev[i][0].record(stream)
+        nC, nTrip = device_step()
+        ev[i][1].record(stream)
+    sync_all()
+    launches = cipc.kernel_launches() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    # the dominant kernel, timed live with CUDA events on its own stream (stage timers of the last step)
+    ctx.barrier_hessian(dHat2, kappa, xi, True, fetch=False)
+    kH = ctx.stage_ms("k_barrier_hessian")
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+
+    # per-stage report (one extra untimed step)
+    stages = {}
+    ctx.constraint_set(dHat2, xi, fetch=False)
+    for s in stage_names[:4]:
+        stages[s] = ctx.stage_ms(s)
+    counters = {k: ctx.counter(k) for k in ("hash_entries", "hash_cells", "candidates_pt", "candidates_ee", "candidates_pe", "candidates_pp", "constraints")}
+    ctx.barrier_energy_dev(dHat2, kappa, xi); stages["barrier_E"] = ctx.stage_ms("barrier_E")
+    ctx.barrier_gradient_dev(dHat2, kappa, xi); stages["barrier_g"] = ctx.stage_ms("barrier_g")
+    ctx.barrier_hessian(dHat2, kappa, xi, True, fetch=False); stages["barrier_H"] = ctx.stage_ms("barrier_H")
+    ctx.step_size_dev(xi, 1.0)
+    for s in ("ccd_hash_build", "ccd_pairs", "ccd_accd"):
+        stages[s] = ctx.stage_ms(s)
+    counters["ccd_pairs"] = ctx.counter("ccd_pairs")
+    ctx.min_dist2_dev(xi); stages["min_dist"] = ctx.stage_ms("min_dist")
+
+    # ---- end-to-end through the host API (pinned host buffers; copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+        X4 = pin((nV, 4), torch.float64); X4[:, :3] = sc["X"]; X4[:, 3] = 0
+        X04 = pin((nV, 4), torch.float64); X04[:, :3] = sc["X0"]; X04[:, 3] = 0
+        p_h = pin((nV * 3,), torch.float64); p_h[:] = sc["p"].ravel()
+        g_h = pin((nV, 4), torch.float64)
+        nC_cap, nT_cap = int(nC * 1.05) + 1024, int(nTrip * 1.05) + 1024
+        cs_h = pin((nC_cap, 4), torch.int32); info_h = pin((nC_cap, 2), torch.float64); d_h = pin((nC_cap,), torch.float64)
+        trip_raw = torch.empty((nT_cap, 2), dtype=torch.float64).pin_memory().numpy()
+        trip_h = trip_raw.view(cipc.TRIPLET_DTYPE).reshape(-1)
+        import ctypes as C
+
+        def e2e_step():
+            h2d = d2h = 0
+            # Compute_Constraint_Set: X, x0 in; constraintSet, stencilInfo out
+            ctx.set_positions(X4); ctx.set_rest_positions(X04); h2d += 2 * X4.nbytes
+            n = ctx.constraint_set(dHat2, xi, fetch=False)
+            ctx._ck(ctx.L.cipc_get_constraints(ctx.h, cs_h.ctypes.data_as(C.POINTER(C.c_int32)), info_h.ctypes.data_as(C.POINTER(C.c_double))))
+            d2h += n * 32
+            # Compute_Barrier / _Gradient / _Hessian: X in (the shim keeps the constraint set it just produced resident)
+            ctx.set_positions(X4); h2d += X4.nbytes
+            E = ctx.barrier_energy(dHat2, kappa, xi, 0.0); d2h += 8
+            ctx.set_positions(X4); h2d += X4.nbytes
+            g_h[:] = 0
+            ctx.barrier_gradient(dHat2, kappa, xi, g_h); d2h += nV * 24
+            ctx.set_positions(X4); h2d += X4.nbytes
+            tr = ctx.barrier_hessian(dHat2, kappa, xi, True, out=trip_h); d2h += len(tr) * 16
+            # Compute_Intersection_Free_StepSize: X, searchDir in; step out
+            ctx.set_positions(X4); ctx.set_search_dir(p_h); h2d += X4.nbytes + p_h.nbytes
+            a = ctx.step_size(xi, 1.0); d2h += 8
+            # Compute_Min_Dist2 x2: X in; dist2, min out
+            for _ in range(2):
+                ctx.set_positions(X4); h2d += X4.nbytes
+                m = C.c_double(0)
+                ctx._ck(ctx.L.cipc_min_dist2(ctx.h, C.c_double(xi), d_h.ctypes.data_as(C.POINTER(C.c_double)), C.byref(m))); d2h += n * 8 + 8
+            return h2d, d2h, (E, a, m.value)
+
+        for _ in range(max(1, args.warmup - 1)):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            h2d, d2h, res = e2e_step()
+        sync_all()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(t.item()), "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (barrier Hessian): algorithmic bytes per constraint
+    #   read 16 B stencil + 16 B info + 4 vertices x 32 B, write 144 (or 81/36) triplets x 16 B
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = nC * (16 + 16 + 4 * 32) + nTrip * 16
+    achieved = alg_bytes / (kH * 1e-3) / 1e9 if kH and kH > 0 else None
+    roof = {"bound": "hbm", "kernel": "k_barrier_hessian", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel_ms": kH, "algorithmic_bytes": int(alg_bytes),
+            "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
+    tr_path = os.path.join(ROOT, "profiles", "traffic_k_barrier_hessian.json")
+    if os.path.exists(tr_path):
+        try:
+            tj = json.load(open(tr_path))
+            if tj.get("workload") == args.workload:
+                roof["traffic"] = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cipc_oracle as O
+        sample, scale = CPU_SAMPLE[args.workload]
+        scs = make_scene(sample)
+        tcpu, st, nCs = cpu_contact_stage(scs)
+        cpu = {"value": 1e3 * tcpu * scale, "unit": "ms", "cores": O.num_threads(), "kind": "port",
+               "sample": "one contact stage of the oracle on %s (%d triangles, %d constraints, %.1f s), scaled x%.0f by triangle count" % (
+                   sample, len(scs["BT"]), nCs, tcpu, scale),
+               "stages_s": {k: round(v, 4) for k, v in st.items()}}
+
+    line = {"metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "triangles": nT, "nodes": nV, "boundary_edges": len(sc["BE"]), "constraints_rank0": int(nC),
+                       "triplets_rank0": int(nTrip), "dHat": float(np.sqrt(dHat2)), "xi": float(xi), "l2": "flushed between timed steps (256 MiB write); working set >> L2",
+                       "parallelism": "pairs partitioned by hash-cell ranges x%d" % world},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters}
+    if args.stage_report:
+        print(json.dumps(line["stages_ms"], indent=1), file=sys.stderr)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

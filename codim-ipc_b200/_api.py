@@ -53,6 +53,7 @@ def load_library():
     L.cipc_last_error.restype = C.c_char_p
     L.cipc_version.restype = C.c_char_p
     L.cipc_stage_ms.restype = C.c_double
+    L.cipc_event_elapsed_ms.restype = C.c_double
     L.cipc_counter.restype = C.c_int64
     L.cipc_kernel_launches.restype = C.c_int64
     for f in ("cipc_dev_positions", "cipc_dev_gradient", "cipc_dev_scalars"):
@@ -235,6 +236,16 @@ class ContactContext:
 
     def sync(self):
         self._ck(self.L.cipc_sync(self.h))
+
+    def set_stream(self, cuda_stream_handle):
+        """run on the caller's CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream"""
+        self._ck(self.L.cipc_set_stream(self.h, C.c_void_p(cuda_stream_handle or None)))
+
+    def event_record(self, slot):
+        self._ck(self.L.cipc_event_record(self.h, int(slot)))
+
+    def event_elapsed_ms(self, a, b):
+        return self.L.cipc_event_elapsed_ms(self.h, int(a), int(b))
 
     def dev_ptrs(self):
         return dict(X=self.L.cipc_dev_positions(self.h), g=self.L.cipc_dev_gradient(self.h), scalars=self.L.cipc_dev_scalars(self.h))

@@ -878,7 +878,8 @@ struct StageEv {
 
 struct cipc_ctx {
     int dev = 0, rank = 0, world = 1;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, ownSt = nullptr;
+    cudaEvent_t userEv[64] = {};
     std::string err;
     // topology
     Topo T{};
@@ -1236,7 +1237,8 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
     c->dev = device; c->rank = rank; c->world = world;
     try {
         CIPC_CUDA(cudaSetDevice(device));
-        CIPC_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        CIPC_CUDA(cudaStreamCreateWithFlags(&c->ownSt, cudaStreamNonBlocking));
+        c->st = c->ownSt;
         c->partial.reserve(RED_GRID, c->st);
         c->scal.reserve(16, c->st);
         c->bbox.reserve(6, c->st);
@@ -1258,13 +1260,41 @@ void cipc_destroy(cipc_ctx* ctx)
     cudaSetDevice(ctx->dev);
     cudaStreamSynchronize(ctx->st);
     for (auto e : ctx->evPool) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->st);
+    for (auto e : ctx->userEv) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->ownSt);
     delete ctx;
 }
 const char* cipc_last_error(cipc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int cipc_sync(cipc_ctx* ctx)
 {
     return guarded(ctx, [&]() { CIPC_CUDA(cudaStreamSynchronize(ctx->st)); return (int)CIPC_OK; });
+}
+
+int cipc_set_stream(cipc_ctx* ctx, void* stream)
+{
+    return guarded(ctx, [&]() {
+        CIPC_CUDA(cudaStreamSynchronize(ctx->st));
+        ctx->st = stream ? (cudaStream_t)stream : ctx->ownSt;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_event_record(cipc_ctx* ctx, int slot)
+{
+    return guarded(ctx, [&]() {
+        if (slot < 0 || slot >= 64) return (int)CIPC_ERR_ARG;
+        if (!ctx->userEv[slot]) CIPC_CUDA(cudaEventCreate(&ctx->userEv[slot]));
+        CIPC_CUDA(cudaEventRecord(ctx->userEv[slot], ctx->st));
+        return (int)CIPC_OK;
+    });
+}
+double cipc_event_elapsed_ms(cipc_ctx* ctx, int a, int b)
+{
+    if (!ctx || a < 0 || b < 0 || a >= 64 || b >= 64 || !ctx->userEv[a] || !ctx->userEv[b]) return -1;
+    cudaSetDevice(ctx->dev);
+    if (cudaEventSynchronize(ctx->userEv[b]) != cudaSuccess) return -1;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->userEv[a], ctx->userEv[b]) != cudaSuccess) return -1;
+    return ms;
 }
 
 int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE, const int32_t* BE, int be_stride, int nBT,
@@ -1525,8 +1555,11 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
             if ((u64)c->nC * 144 > 0xffffffffull) return (int)CIPC_ERR_UNSUPPORTED; // 32-bit triplet offsets
             c->nTrip = tot;
             c->trip.reserve(tot, c->st);
-            CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->nC, bp,
-                projectSPD, c->trip.p);
+            {
+                cipc_ctx::Scope sk(c, "k_barrier_hessian");
+                CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->nC, bp,
+                    projectSPD, c->trip.p);
+            }
         }
         if (nTrip) *nTrip = c->nTrip;
         return (int)CIPC_OK;

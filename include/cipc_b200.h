@@ -104,6 +104,13 @@ int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const
 int cipc_step_size_dev(cipc_ctx* ctx, int elasticIPC, double thickness, double stepSize_in);
 int cipc_min_dist2_dev(cipc_ctx* ctx, double thickness);
 int cipc_sync(cipc_ctx* ctx);
+/* run all subsequent work on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) so that
+ * the caller's events / NCCL collectives order against it without host synchronisation; NULL restores the
+ * library's own stream */
+int cipc_set_stream(cipc_ctx* ctx, void* cuda_stream);
+/* CUDA events on the library's stream: record into slot [0,64) / elapsed milliseconds between two slots */
+int cipc_event_record(cipc_ctx* ctx, int slot);
+double cipc_event_elapsed_ms(cipc_ctx* ctx, int slot_a, int slot_b);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 /* device milliseconds (CUDA events on the library's stream) of the named stage of the last call:

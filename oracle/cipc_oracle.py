@@ -149,6 +149,13 @@ class OracleScene:
             L.oracle_fetch_triplets(_ip(rows), _ip(cols), _dp(vals))
         return rows, cols, vals
 
+    def barrier_hessian_notfetch(self, cs, info, dHat2, kappa, thickness, projectSPD=True, elastic=False):
+        """computes the triplets inside the oracle without copying them out (CPU-baseline timing); returns their number"""
+        cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
+        kappa = np.ascontiguousarray(kappa, np.float64)
+        return lib().oracle_barrier_hessian(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+                                            C.c_double(thickness), int(projectSPD))
+
     def step_size(self, searchDir, thickness, stepSize=1.0, elastic=False, use_hash=True, timers=None):
         p = np.ascontiguousarray(searchDir, np.float64)
         a = C.c_double(stepSize)
