@@ -13,6 +13,7 @@
 #include "../../include/cipc_b200.h"
 #include "geom.cuh"
 #include "eig.cuh"
+#include "hess.cuh"
 #include "prims.cuh"
 
 #include <cooperative_groups.h>
@@ -738,12 +739,76 @@ __device__ void stencil_hessian(const double4* __restrict__ X, const double4* __
             H[i * 12 + j] += w * (bG * (G[i] * eg[j] + eg[i] * G[j]) + (e * bH) * G[i] * G[j]);
     if (projectSPD) psd_project_jacobi<12>(H);
 }
-__global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
-    const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, u32 n, BarrierParams bp,
-    int projectSPD, cipc_triplet* trip)
+// class of a stencil for the Hessian pass: 0 = PT / EE, 1 = PE, 2 = PP (low-rank fast paths), 3 = mollified (dense path)
+__global__ void k_classify(const int4* __restrict__ cs, u32 n, u32* idx0, u32* idx1, u32* idx2, u32* idx3, u32* counts)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int4 c = cs[i];
+    int cls;
+    if (c.x >= 0) cls = (c.w >= 0 && c.z >= 0) ? 0 : 3;
+    else cls = (c.w >= 0) ? 0 : (c.z >= 0 ? 1 : 2);
+    u32* lists[4] = {idx0, idx1, idx2, idx3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (cls == k) {
+            cg::coalesced_group g = cg::coalesced_threads();
+            u32 base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(&counts[k], g.size());
+            base = g.shfl(base, 0);
+            lists[k][base + g.thread_rank()] = i;
+        }
+}
+__device__ __forceinline__ void put_triplet(cipc_triplet* o, int row, int col, double val)
+{
+    // one 16-byte store per triplet
+    int4 q;
+    q.x = row; q.y = col;
+    const long long b = __double_as_longlong(val);
+    q.z = (int)(b & 0xffffffffLL); q.w = (int)(b >> 32);
+    *reinterpret_cast<int4*>(o) = q;
+}
+// CLS 0: PT / EE (rank-5 path), 1: PE (rank-4 path), 2: PP (closed form).  One thread per stencil.
+template <int CLS>
+__global__ void __launch_bounds__(128) k_hessian_lowrank(const double4* __restrict__ X, const int4* __restrict__ cs,
+    const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
+    int projectSPD, cipc_triplet* trip)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const u32 i = idx[k];
+    const int4 c = cs[i];
+    const Stencil s = decode(c);
+    const double wm = info[i].x * (double)s.mult;
+    const double d = stencil_dist2(X, s) - bp.thickness2;
+    const double alpha = wm * barrier_H(bp.elastic, d, bp.dHat2, bp.k0);
+    const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
+    cipc_triplet* o = trip + off[i];
+    constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2);
+    constexpr int NN = 3 * NB;
+    int vid[4] = {s.v[0], s.v[1], s.v[2], s.v[3]};
+    auto emit = [&](int I, int J, const double* B) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b2 = 0; b2 < 3; ++b2)
+                put_triplet(o + (3 * I + a) * NN + 3 * J + b2, vid[I] * 3 + a, vid[J] * 3 + b2, B[3 * a + b2]);
+    };
+    if (CLS == 0) {
+        const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+        hess4_lowrank(s.kind == K_EE, x, alpha, beta, projectSPD != 0, emit);
+    }
+    else if (CLS == 1) hess_pe_lowrank(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), alpha, beta, projectSPD != 0, emit);
+    else hess_pp_closed(ldd(X, s.v[0]), ldd(X, s.v[1]), alpha, beta, projectSPD != 0, emit);
+}
+// dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
+__global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
+    const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
+    BarrierParams bp, int projectSPD, cipc_triplet* trip)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const u32 i = idx ? idx[k] : k;
     double H[144];
     int vids[4], nb;
     stencil_hessian(X, X0, cs[i], info[i].x, bp, projectSPD != 0, H, vids, nb);
@@ -752,11 +817,8 @@ __global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restric
     for (int I = 0; I < nb; ++I)
         for (int a = 0; a < 3; ++a)
             for (int J = 0; J < nb; ++J)
-                for (int b2 = 0; b2 < 3; ++b2) {
-                    cipc_triplet t;
-                    t.row = vids[I] * 3 + a; t.col = vids[J] * 3 + b2; t.val = H[(I * 3 + a) * nn + J * 3 + b2];
-                    o[(I * 3 + a) * nn + J * 3 + b2] = t;
-                }
+                for (int b2 = 0; b2 < 3; ++b2)
+                    put_triplet(o + (I * 3 + a) * nn + J * 3 + b2, vids[I] * 3 + a, vids[J] * 3 + b2, H[(I * 3 + a) * nn + J * 3 + b2]);
 }
 template <int N>
 __global__ void k_test_make_pd(double* H, int count)
@@ -913,7 +975,7 @@ struct cipc_ctx {
     // outputs
     DevBuf<double> g, dist2;
     DevBuf<cipc_triplet> trip;
-    DevBuf<u32> tripOff;
+    DevBuf<u32> tripOff, clsIdx[4];
     int64_t nTrip = 0;
     PinnedBuf pin;
     // timing
@@ -1555,10 +1617,32 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
             if ((u64)c->nC * 144 > 0xffffffffull) return (int)CIPC_ERR_UNSUPPORTED; // 32-bit triplet offsets
             c->nTrip = tot;
             c->trip.reserve(tot, c->st);
-            {
+            const char* dense = getenv("CIPC_HESSIAN_DENSE"); // cross-check switch: force the dense eigen path for every stencil
+            if (dense && dense[0] == '1') {
                 cipc_ctx::Scope sk(c, "k_barrier_hessian");
-                CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->nC, bp,
-                    projectSPD, c->trip.p);
+                CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                    (const u32*)nullptr, c->nC, bp, projectSPD, c->trip.p);
+            }
+            else {
+                for (int k = 0; k < 4; ++k) c->clsIdx[k].reserve(c->nC, c->st);
+                CIPC_CUDA(cudaMemsetAsync(c->counters.p + 12, 0, 4 * sizeof(u32), c->st));
+                CIPC_LAUNCH(k_classify, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->clsIdx[0].p, c->clsIdx[1].p, c->clsIdx[2].p,
+                    c->clsIdx[3].p, c->counters.p + 12);
+                u32 nk[4];
+                CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+                CIPC_CUDA(cudaStreamSynchronize(c->st));
+                {
+                    cipc_ctx::Scope sk(c, "k_barrier_hessian");
+                    if (nk[0]) CIPC_LAUNCH(k_hessian_lowrank<0>, div_up(nk[0], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                        c->clsIdx[0].p, nk[0], bp, projectSPD, c->trip.p);
+                }
+                if (nk[1]) CIPC_LAUNCH(k_hessian_lowrank<1>, div_up(nk[1], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                    c->clsIdx[1].p, nk[1], bp, projectSPD, c->trip.p);
+                if (nk[2]) CIPC_LAUNCH(k_hessian_lowrank<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                    c->clsIdx[2].p, nk[2], bp, projectSPD, c->trip.p);
+                if (nk[3]) CIPC_LAUNCH(k_barrier_hessian, div_up(nk[3], 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                    c->clsIdx[3].p, nk[3], bp, projectSPD, c->trip.p);
+                c->ctr["hessian_4pt"] = nk[0]; c->ctr["hessian_pe"] = nk[1]; c->ctr["hessian_pp"] = nk[2]; c->ctr["hessian_mollified"] = nk[3];
             }
         }
         if (nTrip) *nTrip = c->nTrip;

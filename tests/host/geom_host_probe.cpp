@@ -2,6 +2,8 @@
 // lets the CPU test-suite compare the product's geometry code with the oracle without a GPU.
 #define CIPC_HOST_TEST 1
 #include "../../codim-ipc_b200/csrc/geom.cuh"
+#include "../../codim-ipc_b200/csrc/hess.cuh"
+#include "../../codim-ipc_b200/csrc/eig.cuh"
 using namespace cipc;
 static xv3 X(const double* p) { return xv3(xd(p[0]), xd(p[1]), xd(p[2])); }
 static dv3 Dv(const double* p) { return dv3(p[0], p[1], p[2]); }
@@ -58,6 +60,24 @@ int probe_broadphase(int kind, const double* x, const double* dx, double dist)
     case 5: return pe_ccd_broadphase(X(x), X(x + 3), X(x + 6), X(dx), X(dx + 3), X(dx + 6), dist);
     default: return pp_ccd_broadphase(X(x), X(x + 3), X(dx), X(dx + 3), dist);
     }
+}
+// low-rank Hessian paths of hess.cuh: kind 0 PP, 1 PE, 2 PT, 3 EE;  H = alpha g g^T + beta K (projected if project)
+void probe_hess_lowrank(int kind, const double* x, double alpha, double beta, int project, double* H)
+{
+    const dv3 v[4] = {Dv(x), Dv(x + 3), Dv(x + 6), Dv(x + 9)};
+    const int n = (kind == 0) ? 6 : (kind == 1 ? 9 : 12);
+    auto emit = [&](int I, int J, const double* B) {
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[(3 * I + a) * n + 3 * J + b] = B[3 * a + b];
+    };
+    if (kind == 0) hess_pp_closed(v[0], v[1], alpha, beta, project != 0, emit);
+    else if (kind == 1) hess_pe_lowrank(v[0], v[1], v[2], alpha, beta, project != 0, emit);
+    else hess4_lowrank(kind == 3, v, alpha, beta, project != 0, emit);
+}
+void probe_psd_jacobi(int n, double* H)
+{
+    if (n == 6) psd_project_jacobi<6>(H);
+    else if (n == 9) psd_project_jacobi<9>(H);
+    else psd_project_jacobi<12>(H);
 }
 void probe_barrier(int elastic, double d, double dHat, double k0, double* out3)
 {
