@@ -801,24 +801,90 @@ __global__ void __launch_bounds__(128) k_hessian_lowrank(const double4* __restri
     else if (CLS == 1) hess_pe_lowrank(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), alpha, beta, projectSPD != 0, emit);
     else hess_pp_closed(ldd(X, s.v[0]), ldd(X, s.v[1]), alpha, beta, projectSPD != 0, emit);
 }
+// ---- two-phase projected Hessian: (A) per stencil, factor the PSD block as sum_k y_k y_k^T (k <= 3 / 2 / 1),
+//      (B) one thread per triplet expands y y^T into the (row, col, value) stream with fully coalesced 16-byte stores.
+struct __align__(32) YHdr {
+    u32 off;      // first triplet of the stencil's block, 0xffffffff = handled by the dense path
+    int v[4];     // vertex ids in block order
+    int pad[3];
+};
+template <int CLS> struct YShape { static constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2); static constexpr int NY = (CLS == 0) ? 3 : (CLS == 1 ? 2 : 1); };
+
+template <int CLS>
+__global__ void __launch_bounds__(128, 3) k_hessian_factor(const double4* __restrict__ X, const int4* __restrict__ cs,
+    const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
+    double* __restrict__ Yout, YHdr* __restrict__ hdr, u32* denseList, u32* denseCount)
+{
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const u32 i = idx[q];
+    const Stencil s = decode(cs[i]);
+    const double wm = info[i].x * (double)s.mult;
+    const double d = stencil_dist2(X, s) - bp.thickness2;
+    const double alpha = wm * barrier_H(bp.elastic, d, bp.dHat2, bp.k0);
+    const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
+    constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY;
+    YHdr h;
+    h.off = off[i];
+    h.v[0] = s.v[0]; h.v[1] = s.v[1]; h.v[2] = s.v[2]; h.v[3] = s.v[3];
+    h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    if (!(beta < 0.0) || !(alpha > 0.0)) {
+        // outside the barrier's support (stale constraint set) the inertia argument does not hold: dense path
+        h.off = 0xffffffffu;
+        hdr[q] = h;
+        denseList[atomicAdd(denseCount, 1u)] = i;
+        return;
+    }
+    double Y[NY * NN];
+    if (CLS == 0) {
+        const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+        hess4_factor(s.kind == K_EE, x, alpha, beta, Y);
+    }
+    else if (CLS == 1) hess_pe_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), alpha, beta, Y);
+    else hess_pp_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), alpha, beta, Y);
+    double2* o = reinterpret_cast<double2*>(Yout + (size_t)q * (NY * NN));
+#pragma unroll
+    for (int k = 0; k < NY * NN / 2; ++k) o[k] = make_double2(Y[2 * k], Y[2 * k + 1]);
+    hdr[q] = h;
+}
+template <int CLS>
+__global__ void __launch_bounds__(256) k_hessian_expand(const double* __restrict__ Yin, const YHdr* __restrict__ hdr, u64 total,
+    cipc_triplet* __restrict__ trip)
+{
+    constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, PER = NN * NN;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const u32 q = (u32)(t / PER);
+    const int e = (int)(t - (u64)q * PER);
+    const int r = e / NN, c = e - r * NN;
+    const YHdr h = hdr[q];
+    if (h.off == 0xffffffffu) return;
+    const double* y = Yin + (size_t)q * (NY * NN);
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
+    const int ri = r / 3, ci = c / 3;
+    put_triplet(trip + (size_t)h.off + e, h.v[ri] * 3 + (r - 3 * ri), h.v[ci] * 3 + (c - 3 * ci), v);
+}
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 __global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
     const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
-    BarrierParams bp, int projectSPD, cipc_triplet* trip)
+    const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip)
 {
-    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const u32 i = idx ? idx[k] : k;
-    double H[144];
-    int vids[4], nb;
-    stencil_hessian(X, X0, cs[i], info[i].x, bp, projectSPD != 0, H, vids, nb);
-    const int nn = 3 * nb;
-    cipc_triplet* o = trip + off[i];
-    for (int I = 0; I < nb; ++I)
-        for (int a = 0; a < 3; ++a)
-            for (int J = 0; J < nb; ++J)
-                for (int b2 = 0; b2 < 3; ++b2)
-                    put_triplet(o + (I * 3 + a) * nn + J * 3 + b2, vids[I] * 3 + a, vids[J] * 3 + b2, H[(I * 3 + a) * nn + J * 3 + b2]);
+    if (nDev) n = *nDev; // list length produced on the device (fallbacks of the factor kernels)
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const u32 i = idx ? idx[k] : k;
+        double H[144];
+        int vids[4], nb;
+        stencil_hessian(X, X0, cs[i], info[i].x, bp, projectSPD != 0, H, vids, nb);
+        const int nn = 3 * nb;
+        cipc_triplet* o = trip + off[i];
+        for (int I = 0; I < nb; ++I)
+            for (int a = 0; a < 3; ++a)
+                for (int J = 0; J < nb; ++J)
+                    for (int b2 = 0; b2 < 3; ++b2)
+                        put_triplet(o + (I * 3 + a) * nn + J * 3 + b2, vids[I] * 3 + a, vids[J] * 3 + b2, H[(I * 3 + a) * nn + J * 3 + b2]);
+    }
 }
 template <int N>
 __global__ void k_test_make_pd(double* H, int count)
@@ -976,6 +1042,8 @@ struct cipc_ctx {
     DevBuf<double> g, dist2;
     DevBuf<cipc_triplet> trip;
     DevBuf<u32> tripOff, clsIdx[4];
+    DevBuf<double> Y;
+    DevBuf<double4> yhdr; // YHdr records (32 B each)
     int64_t nTrip = 0;
     PinnedBuf pin;
     // timing
@@ -1621,7 +1689,7 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
             if (dense && dense[0] == '1') {
                 cipc_ctx::Scope sk(c, "k_barrier_hessian");
                 CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
-                    (const u32*)nullptr, c->nC, bp, projectSPD, c->trip.p);
+                    (const u32*)nullptr, c->nC, (const u32*)nullptr, bp, projectSPD, c->trip.p);
             }
             else {
                 for (int k = 0; k < 4; ++k) c->clsIdx[k].reserve(c->nC, c->st);
@@ -1631,17 +1699,44 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
                 u32 nk[4];
                 CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
                 CIPC_CUDA(cudaStreamSynchronize(c->st));
-                {
+                if (projectSPD) {
+                    // (A) factor, (B) expand; stencils the factor kernels reject are appended to the dense list
+                    const size_t ydoubles = (size_t)nk[0] * 36 + (size_t)nk[1] * 18 + (size_t)nk[2] * 6;
+                    c->Y.reserve(ydoubles + 4, c->st);
+                    c->yhdr.reserve((size_t)nk[0] + nk[1] + nk[2] + 1, c->st);
+                    double* Y0 = c->Y.p; double* Y1 = Y0 + (size_t)nk[0] * 36; double* Y2 = Y1 + (size_t)nk[1] * 18;
+                    YHdr* h0 = (YHdr*)c->yhdr.p; YHdr* h1 = h0 + nk[0]; YHdr* h2 = h1 + nk[1];
+                    u32* dl = c->clsIdx[3].p; u32* dn = c->counters.p + 15; // counters[15] = length of the dense list (starts at nk[3])
+                    {
+                        cipc_ctx::Scope sk(c, "k_hessian_factor");
+                        if (nk[0]) CIPC_LAUNCH(k_hessian_factor<0>, div_up(nk[0], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                            c->clsIdx[0].p, nk[0], bp, Y0, h0, dl, dn);
+                        if (nk[1]) CIPC_LAUNCH(k_hessian_factor<1>, div_up(nk[1], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                            c->clsIdx[1].p, nk[1], bp, Y1, h1, dl, dn);
+                        if (nk[2]) CIPC_LAUNCH(k_hessian_factor<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                            c->clsIdx[2].p, nk[2], bp, Y2, h2, dl, dn);
+                    }
+                    {
+                        cipc_ctx::Scope sk(c, "k_barrier_hessian"); // the dominant kernel: triplet expansion
+                        if (nk[0]) CIPC_LAUNCH(k_hessian_expand<0>, div_up((u64)nk[0] * 144, 256), 256, 0, c->st, Y0, h0, (u64)nk[0] * 144, c->trip.p);
+                    }
+                    if (nk[1]) CIPC_LAUNCH(k_hessian_expand<1>, div_up((u64)nk[1] * 81, 256), 256, 0, c->st, Y1, h1, (u64)nk[1] * 81, c->trip.p);
+                    if (nk[2]) CIPC_LAUNCH(k_hessian_expand<2>, div_up((u64)nk[2] * 36, 256), 256, 0, c->st, Y2, h2, (u64)nk[2] * 36, c->trip.p);
+                    // mollified stencils + rejected ones: dense eigen path, list length read on the device
+                    CIPC_LAUNCH(k_barrier_hessian, 592, 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
+                        (const u32*)dn, bp, projectSPD, c->trip.p);
+                }
+                else {
                     cipc_ctx::Scope sk(c, "k_barrier_hessian");
                     if (nk[0]) CIPC_LAUNCH(k_hessian_lowrank<0>, div_up(nk[0], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
                         c->clsIdx[0].p, nk[0], bp, projectSPD, c->trip.p);
+                    if (nk[1]) CIPC_LAUNCH(k_hessian_lowrank<1>, div_up(nk[1], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                        c->clsIdx[1].p, nk[1], bp, projectSPD, c->trip.p);
+                    if (nk[2]) CIPC_LAUNCH(k_hessian_lowrank<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
+                        c->clsIdx[2].p, nk[2], bp, projectSPD, c->trip.p);
+                    if (nk[3]) CIPC_LAUNCH(k_barrier_hessian, div_up(nk[3], 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                        c->clsIdx[3].p, nk[3], (const u32*)nullptr, bp, projectSPD, c->trip.p);
                 }
-                if (nk[1]) CIPC_LAUNCH(k_hessian_lowrank<1>, div_up(nk[1], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
-                    c->clsIdx[1].p, nk[1], bp, projectSPD, c->trip.p);
-                if (nk[2]) CIPC_LAUNCH(k_hessian_lowrank<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
-                    c->clsIdx[2].p, nk[2], bp, projectSPD, c->trip.p);
-                if (nk[3]) CIPC_LAUNCH(k_barrier_hessian, div_up(nk[3], 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
-                    c->clsIdx[3].p, nk[3], bp, projectSPD, c->trip.p);
                 c->ctr["hessian_4pt"] = nk[0]; c->ctr["hessian_pe"] = nk[1]; c->ctr["hessian_pp"] = nk[2]; c->ctr["hessian_mollified"] = nk[3];
             }
         }

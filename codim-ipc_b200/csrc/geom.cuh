@@ -59,6 +59,14 @@ CIPC_HD xd xsqrt(xd a) { return xd(sqrt(a.v)); }
 CIPC_HD xd xmin(xd a, xd b) { return a.v < b.v ? a : b; }
 CIPC_HD xd xmax(xd a, xd b) { return a.v > b.v ? a : b; }
 CIPC_HD xd xabs(xd a) { return xd(fabs(a.v)); }
+CIPC_HD double cipc_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 
 template <class S>
 struct vec3 {

@@ -277,6 +277,149 @@ CIPC_HD void hess4_lowrank(bool ee, const dv3* x, double alpha, double beta, boo
     }
 }
 
+// ------------------------------------------------------------------ factored form for the two-phase kernel
+// Projected 4-point block as a sum of at most three outer products  H+ = sum_k y_k y_k^T  (the block has exactly
+// three non-negative directions).  Y: 3 x 12 doubles.  Same algebra as hess4_lowrank, with the block structure of
+// the Gram matrix (3x3 + two equal scalars) and the closed forms of eta_1, eta_2 written out by hand so that the
+// whole computation stays in registers:
+//     eta_1 = (0, -1/|u|, 0),  eta_2 = (0, (u^.v)/|n|, -|u|/|n|)        (t1 = u^, t2 = n^ x u^)
+CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, double* Y /*36*/)
+{
+    dv3 w, u, v;
+    if (!ee) { w = x[0] - x[1]; u = x[2] - x[1]; v = x[3] - x[1]; }
+    else { w = x[2] - x[0]; u = x[1] - x[0]; v = x[3] - x[2]; }
+    const dv3 n = cross(u, v);
+    const double nn = norm2(n), inn = 1.0 / sqrt(nn);
+    const dv3 nh(n.x * inn, n.y * inn, n.z * inn);
+    const double s = dot(w, nh);
+    const double uu = norm2(u), iu = 1.0 / sqrt(uu);
+    const dv3 t1(u.x * iu, u.y * iu, u.z * iu);
+    const dv3 t2 = cross(nh, t1);
+    // tangential part of w in the (u,v) frame: w_t = a u + b v  via the dual basis
+    const dv3 cu = cross(nh, v), cv = cross(u, nh);
+    const double a = -dot(cu, w) * inn, b = -dot(cv, w) * inn;
+    const double e1u = -iu;                       // eta_1 = (0, e1u, 0)
+    const double e2u = dot(t1, v) * inn, e2v = -uu * iu * inn; // eta_2 = (0, e2u, e2v)
+    double cz[4], c1[4], c2[4];
+    if (!ee) {
+        cz[0] = 1.0; cz[1] = -1.0 + a + b; cz[2] = -a; cz[3] = -b;
+        c1[0] = 0.0; c1[1] = -e1u; c1[2] = e1u; c1[3] = 0.0;
+        c2[0] = 0.0; c2[1] = -e2u - e2v; c2[2] = e2u; c2[3] = e2v;
+    }
+    else {
+        cz[0] = -1.0 + a; cz[1] = -a; cz[2] = 1.0 + b; cz[3] = -b;
+        c1[0] = -e1u; c1[1] = e1u; c1[2] = 0.0; c1[3] = 0.0;
+        c2[0] = -e2u; c2[1] = e2u; c2[2] = -e2v; c2[3] = e2v;
+    }
+    double gzz = 0, gz1 = 0, gz2 = 0, g11 = 0, g12 = 0, g22 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        gzz += cz[k] * cz[k]; gz1 += cz[k] * c1[k]; gz2 += cz[k] * c2[k];
+        g11 += c1[k] * c1[k]; g12 += c1[k] * c2[k]; g22 += c2[k] * c2[k];
+    }
+    // Cholesky of the 3x3 Gram block
+    const double l00 = sqrt(gzz), il00 = 1.0 / l00;
+    const double l10 = gz1 * il00, l20 = gz2 * il00;
+    const double l11 = sqrt(g11 - l10 * l10), il11 = 1.0 / l11;
+    const double l21 = (g12 - l20 * l10) * il11;
+    const double l22 = sqrt(g22 - l20 * l20 - l21 * l21), il22 = 1.0 / l22;
+    // M = L^T C L in the orthonormalised basis (upper triangle, 5x5)
+    const double lam0 = 4.0 * alpha * s * s + 2.0 * beta, mu = 2.0 * beta * s * s, gg = l00 * 2.0 * beta * s;
+    double A[5][5];
+    A[0][0] = lam0 * l00 * l00 - mu * (l10 * l10 + l20 * l20);
+    A[0][1] = -mu * (l10 * l11 + l20 * l21);
+    A[0][2] = -mu * l20 * l22;
+    A[1][1] = -mu * (l11 * l11 + l21 * l21);
+    A[1][2] = -mu * l21 * l22;
+    A[2][2] = -mu * l22 * l22;
+    A[0][3] = gg * l10; A[0][4] = gg * l20;
+    A[1][3] = gg * l11; A[1][4] = gg * l21;
+    A[2][3] = 0.0; A[2][4] = gg * l22;
+    A[3][3] = 0.0; A[3][4] = 0.0; A[4][4] = 0.0;
+    double V[5][5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    double fro = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = i; j < 5; ++j) fro += (i == j ? 1.0 : 2.0) * A[i][j] * A[i][j];
+    const double tol = 1e-26 * fro; // off-diagonal norm <= 1e-13 ||M||: eigenvector error far below the 1e-9 gate
+    for (int sweep = 0; sweep < 10; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 5; ++q) off += A[p][q] * A[p][q];
+        if (off <= tol) break;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 5; ++q) {
+                const double apq = A[p][q];
+                if (apq * apq > 1e-34 * fro) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = cipc_rsqrt(t * t + 1.0), sn = t * c;
+                    A[p][p] -= t * apq;
+                    A[q][q] += t * apq;
+                    A[p][q] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        if (k != p && k != q) { // upper-triangle accessors with compile-time indices
+                            double& akp = (k < p) ? A[k][p] : A[p][k];
+                            double& akq = (k < q) ? A[k][q] : A[q][k];
+                            const double vp = akp, vq = akq;
+                            akp = c * vp - sn * vq;
+                            akq = sn * vp + c * vq;
+                        }
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + c * vkq;
+                    }
+                }
+            }
+    }
+    // bring the three largest eigenvalues (the only possibly positive ones) to columns 0..2
+    double lam[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) lam[i] = A[i][i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 5; ++j) {
+            const bool sw = lam[j] > lam[i];
+            const double tl = lam[i];
+            lam[i] = sw ? lam[j] : lam[i];
+            lam[j] = sw ? tl : lam[j];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double tv = V[k][i];
+                V[k][i] = sw ? V[k][j] : V[k][i];
+                V[k][j] = sw ? tv : V[k][j];
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double sc = lam[k] > 0.0 ? sqrt(lam[k]) : 0.0;
+        // f = L~^-T (sc v): back substitution with L~ = blockdiag(L_N, l00, l00)
+        const double f4 = sc * V[4][k] * il00, f3 = sc * V[3][k] * il00;
+        const double f2 = sc * V[2][k] * il22;
+        const double f1 = (sc * V[1][k] - l21 * f2) * il11;
+        const double f0 = (sc * V[0][k] - l10 * f1 - l20 * f2) * il00;
+        const dv3 tt(f3 * t1.x + f4 * t2.x, f3 * t1.y + f4 * t2.y, f3 * t1.z + f4 * t2.z);
+#pragma unroll
+        for (int I = 0; I < 4; ++I) {
+            const double cn = f0 * cz[I] + f1 * c1[I] + f2 * c2[I];
+            Y[12 * k + 3 * I + 0] = cn * nh.x + cz[I] * tt.x;
+            Y[12 * k + 3 * I + 1] = cn * nh.y + cz[I] * tt.y;
+            Y[12 * k + 3 * I + 2] = cn * nh.z + cz[I] * tt.z;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ point-edge stencil (rank 4)
 // x = (p, e0, e1).  Basis [z(x)n, eps(x)n, z(x)u^, z(x)b^] with z = A^T(1,-t), eps = A^T(0,1).
 template <class Emit>
@@ -335,6 +478,102 @@ CIPC_HD void hess_pe_lowrank(const dv3& p, const dv3& e0, const dv3& e1, double 
                 for (int c = 0; c < 3; ++c) Bk[3 * rr + c] = T[rr][0] * R[c][0] + T[rr][1] * R[c][1] + T[rr][2] * R[c][2];
             emit(I, J, Bk);
         }
+}
+
+// Projected point-edge block as at most two outer products (the block has two non-negative directions).
+// Basis [cz(x)n, ce(x)n, cz(x)u^]; the fourth vector cz(x)b^ carries the eigenvalue 2 beta |cz|^2 < 0 and drops out.
+CIPC_HD void hess_pe_factor(const dv3& p, const dv3& e0, const dv3& e1, double alpha, double beta, double* Y /*18*/)
+{
+    const dv3 w = p - e0, u = e1 - e0;
+    const double L = norm2(u), iL = 1.0 / L, t = dot(w, u) * iL;
+    const dv3 r(w.x - t * u.x, w.y - t * u.y, w.z - t * u.z);
+    const double d = norm2(r), rn = sqrt(d), irn = 1.0 / rn, iun = cipc_rsqrt(L);
+    const dv3 nh(r.x * irn, r.y * irn, r.z * irn), uh(u.x * iun, u.y * iun, u.z * iun);
+    const double cz[3] = {1.0, -1.0 + t, -t};
+    const double ce[3] = {0.0, -1.0, 1.0};
+    const double gzz = cz[0] * cz[0] + cz[1] * cz[1] + cz[2] * cz[2], gze = cz[1] * ce[1] + cz[2] * ce[2];
+    const double l00 = sqrt(gzz), il00 = 1.0 / l00, l10 = gze * il00, l11 = sqrt(2.0 - l10 * l10), il11 = 1.0 / l11;
+    const double lam1 = 4.0 * alpha * d + 2.0 * beta, c11 = -2.0 * beta * d * iL, c12 = -2.0 * beta * rn * iun;
+    double A[3][3];
+    A[0][0] = l00 * l00 * lam1 + l10 * l10 * c11;
+    A[0][1] = l10 * c11 * l11;
+    A[0][2] = l10 * c12 * l00;
+    A[1][1] = l11 * l11 * c11;
+    A[1][2] = l11 * c12 * l00;
+    A[2][2] = 0.0;
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    const double fro = A[0][0] * A[0][0] + A[1][1] * A[1][1] + 2.0 * (A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2]);
+    const double tol = 1e-26 * fro;
+    for (int sweep = 0; sweep < 10; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        if (off <= tol) break;
+#pragma unroll
+        for (int pI = 0; pI < 2; ++pI)
+#pragma unroll
+            for (int q = pI + 1; q < 3; ++q) {
+                const double apq = A[pI][q];
+                if (apq * apq > 1e-34 * fro) {
+                    const double theta = (A[q][q] - A[pI][pI]) / (2.0 * apq);
+                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = cipc_rsqrt(tt * tt + 1.0), sn = tt * c;
+                    A[pI][pI] -= tt * apq;
+                    A[q][q] += tt * apq;
+                    A[pI][q] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (k != pI && k != q) {
+                            double& akp = (k < pI) ? A[k][pI] : A[pI][k];
+                            double& akq = (k < q) ? A[k][q] : A[q][k];
+                            const double vp = akp, vq = akq;
+                            akp = c * vp - sn * vq;
+                            akq = sn * vp + c * vq;
+                        }
+                        const double vkp = V[k][pI], vkq = V[k][q];
+                        V[k][pI] = c * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + c * vkq;
+                    }
+                }
+            }
+    }
+    double lam[3] = {A[0][0], A[1][1], A[2][2]};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 3; ++j) {
+            const bool sw = lam[j] > lam[i];
+            const double tl = lam[i];
+            lam[i] = sw ? lam[j] : lam[i];
+            lam[j] = sw ? tl : lam[j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double tv = V[k][i];
+                V[k][i] = sw ? V[k][j] : V[k][i];
+                V[k][j] = sw ? tv : V[k][j];
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double sc = lam[k] > 0.0 ? sqrt(lam[k]) : 0.0;
+        const double f2 = sc * V[2][k] * il00;
+        const double f1 = sc * V[1][k] * il11;
+        const double f0 = (sc * V[0][k] - l10 * f1) * il00;
+#pragma unroll
+        for (int I = 0; I < 3; ++I) {
+            const double cn = f0 * cz[I] + f1 * ce[I], cu_ = f2 * cz[I];
+            Y[9 * k + 3 * I + 0] = cn * nh.x + cu_ * uh.x;
+            Y[9 * k + 3 * I + 1] = cn * nh.y + cu_ * uh.y;
+            Y[9 * k + 3 * I + 2] = cn * nh.z + cu_ * uh.z;
+        }
+    }
+}
+// Projected point-point block: one outer product, y = sqrt(max(4 alpha |d|^2 + 2 beta, 0)/(|d|^2)) (d, -d)   (beta < 0)
+CIPC_HD void hess_pp_factor(const dv3& a, const dv3& b, double alpha, double beta, double* Y /*6*/)
+{
+    const dv3 dl = a - b;
+    const double d2 = norm2(dl);
+    const double lam = 4.0 * alpha * d2 + 2.0 * beta;
+    const double k = lam > 0.0 ? sqrt(lam / d2) : 0.0;
+    Y[0] = k * dl.x; Y[1] = k * dl.y; Y[2] = k * dl.z; Y[3] = -Y[0]; Y[4] = -Y[1]; Y[5] = -Y[2];
 }
 
 // ------------------------------------------------------------------ point-point stencil (closed form)

@@ -73,6 +73,22 @@ void probe_hess_lowrank(int kind, const double* x, double alpha, double beta, in
     else if (kind == 1) hess_pe_lowrank(v[0], v[1], v[2], alpha, beta, project != 0, emit);
     else hess4_lowrank(kind == 3, v, alpha, beta, project != 0, emit);
 }
+// factored form (two-phase kernel): H+ = sum_k y_k y_k^T
+void probe_hess_factor(int kind, const double* x, double alpha, double beta, double* H)
+{
+    const dv3 v[4] = {Dv(x), Dv(x + 3), Dv(x + 6), Dv(x + 9)};
+    const int n = (kind == 0) ? 6 : (kind == 1 ? 9 : 12), ny = (kind == 0) ? 1 : (kind == 1 ? 2 : 3);
+    double Y[36];
+    if (kind == 0) hess_pp_factor(v[0], v[1], alpha, beta, Y);
+    else if (kind == 1) hess_pe_factor(v[0], v[1], v[2], alpha, beta, Y);
+    else hess4_factor(kind == 3, v, alpha, beta, Y);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double s = 0;
+            for (int k = 0; k < ny; ++k) s += Y[k * n + i] * Y[k * n + j];
+            H[i * n + j] = s;
+        }
+}
 void probe_psd_jacobi(int n, double* H)
 {
     if (n == 6) psd_project_jacobi<6>(H);

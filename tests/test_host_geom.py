@@ -82,6 +82,10 @@ def test_lowrank_hessian_equals_dense_projection(probe):
                     ref = (V * np.maximum(w, 0)) @ V.T
                     assert (np.abs(w) > 1e-9 * np.abs(w).max()).sum() <= 5  # rank <= 5: the structure hess.cuh relies on
                 assert np.linalg.norm(out.reshape(n, n) - ref) <= 1e-10 * np.linalg.norm(H)
+            # factored form used by the two-phase kernel (valid for a barrier: alpha > 0 > beta)
+            out = np.zeros(n * n)
+            probe.probe_hess_factor(kind, _dp(x), C.c_double(alpha), C.c_double(beta), _dp(out))
+            assert np.linalg.norm(out.reshape(n, n) - ref) <= 1e-10 * np.linalg.norm(H)
 
 
 def test_dense_jacobi_projection(probe):
