@@ -287,19 +287,21 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (barrier Hessian): algorithmic bytes per constraint
-    #   read 16 B stencil + 16 B info + 4 vertices x 32 B, write 144 (or 81/36) triplets x 16 B
+    # ---- roofline of the dominant kernel: k_hessian_expand<0> (triplet expansion of the PT/EE blocks)
+    #   algorithmic bytes per 4-point stencil: write 144 triplets x 16 B, read 3 x 12 doubles (factor) + 32 B header
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = nC * (16 + 16 + 4 * 32) + nTrip * 16
+    n4 = ctx.counter("hessian_4pt")
+    alg_bytes = n4 * (144 * 16 + 36 * 8 + 32)
     achieved = alg_bytes / (kH * 1e-3) / 1e9 if kH and kH > 0 else None
-    roof = {"bound": "hbm", "kernel": "k_barrier_hessian", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "k_hessian_expand<0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel_ms": kH, "algorithmic_bytes": int(alg_bytes),
+            "units_per_launch": int(n4), "bytes_per_unit": 144 * 16 + 36 * 8 + 32,
             "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}
-    tr_path = os.path.join(ROOT, "profiles", "traffic_k_barrier_hessian.json")
+    tr_path = os.path.join(ROOT, "profiles", "traffic_k_hessian_expand.json")
     if os.path.exists(tr_path):
         try:
             tj = json.load(open(tr_path))

@@ -1,0 +1,299 @@
+// shim/FEM/IPC.h -- drop-in replacement of the reference's Library/FEM/IPC.h contact entry points.
+//
+// Build the reference with `-I <this repo>/codim-ipc_b200/shim -I <this repo>/include` placed BEFORE
+// `-I Library` (CMakeLists.txt:24) and link libcipc_b200.so: every `#include <FEM/IPC.h>` of the reference
+// (FEM/FEM_EXPORTER.h:10, FEM/TimeStepper/IMPLICIT_EULER.h:6, ADMM.h:6, SHAPE_UP.h:6) then lands here.
+// No reference source is edited and every caller / pybind export compiles unchanged.
+//
+// How it works: the reference's own header is pulled in underneath with its six contact templates
+// renamed to *_CPU (so everything else it defines -- Compute_Inversion_Free_StepSize, the root finders,
+// Check_Edge_Tri_Intersect, the 2-D branches -- stays available), and six templates with the reference's
+// exact names and signatures are defined on top:
+//
+//   <double, dim=3, shell=false, elasticIPC=false>  -> CUDA path through the C ABI (include/cipc_b200.h).
+//        This is the instantiation every Projects/FEMShell scene runs (initialize_OIPC).  Any CUDA
+//        failure prints a message and exit(-1)s like the reference's own invariant checks; there is
+//        no CPU fallback for this instantiation.
+//   anything else (float, dim=2, shell pairing, elasticIPC) -> the reference's own CPU template, untouched
+//        (those instantiations are outside the scope of the graft).
+//
+// Reference signatures: FEM/IPC.h:19-36, 742-748, 943-948, 1258-1265, 1879-1890, 2246-2249.
+#pragma once
+
+#define Compute_Constraint_Set Compute_Constraint_Set_CPU
+#define Compute_Barrier Compute_Barrier_CPU
+#define Compute_Barrier_Gradient Compute_Barrier_Gradient_CPU
+#define Compute_Barrier_Hessian Compute_Barrier_Hessian_CPU
+#define Compute_Intersection_Free_StepSize Compute_Intersection_Free_StepSize_CPU
+#define Compute_Min_Dist2 Compute_Min_Dist2_CPU
+#include_next <FEM/IPC.h>
+#undef Compute_Constraint_Set
+#undef Compute_Barrier
+#undef Compute_Barrier_Gradient
+#undef Compute_Barrier_Hessian
+#undef Compute_Intersection_Free_StepSize
+#undef Compute_Min_Dist2
+
+#include <cipc_b200.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <type_traits>
+#include <vector>
+
+namespace JGSL {
+namespace cipc_shim {
+
+inline void die(cipc_ctx* ctx, int st, const char* where)
+{
+    if (st == CIPC_OK) return;
+    if (st == CIPC_ERR_NONPOSITIVE_DIST) printf("non-positive distance detected during barrier evaluation!\n"); // IPC.h:773-776
+    else if (st == CIPC_ERR_ZERO_STEP) printf("zero step size from CCD!\n");                                    // IPC.h:2014-2032
+    else printf("cipc_b200: %s failed with status %d: %s\n", where, st, ctx ? cipc_last_error(ctx) : "no context");
+    exit(-1);
+}
+
+struct State {
+    cipc_ctx* ctx = nullptr;
+    // identity of the constraint set that is resident on the device (what Compute_Constraint_Set last handed out)
+    const void* csPtr = nullptr;
+    size_t csSize = 0;
+    std::vector<int> csSample;
+    std::vector<double> stage3, stage2; // packed staging
+    std::vector<int32_t> nnx;
+    std::vector<uint8_t> dbc;
+};
+inline State& state()
+{
+    static State s;
+    if (!s.ctx) {
+        const char* dev = getenv("CIPC_DEVICE");
+        int st = cipc_create(dev ? atoi(dev) : 0, 0, 1, &s.ctx);
+        if (st != CIPC_OK) { printf("cipc_b200: no CUDA device; the contact path has no CPU fallback\n"); exit(-1); }
+    }
+    return s;
+}
+
+// positions: MESH_NODE<T,3> = BASE_STORAGE<VECTOR<T,3>>; element i is 4 contiguous doubles.  When the
+// elements are contiguous (32-byte stride, the Cabana AoSoA of a single VECTOR member) upload in place,
+// otherwise gather through Get_Unchecked.
+template <class NODES>
+inline void upload_positions(State& s, NODES& X, int (*setter)(cipc_ctx*, const double*, int), const char* what)
+{
+    const size_t n = X.size;
+    const double* p0 = std::get<0>(X.Get_Unchecked(0)).data;
+    bool contiguous = true;
+    const size_t probe[3] = {1, n / 2, n - 1};
+    for (size_t k : probe)
+        if (k < n && std::get<0>(X.Get_Unchecked(k)).data != p0 + 4 * k) contiguous = false;
+    if (contiguous) { die(s.ctx, setter(s.ctx, p0, 32), what); return; }
+    s.stage3.resize(3 * n);
+    for (size_t i = 0; i < n; ++i) {
+        const double* d = std::get<0>(X.Get_Unchecked(i)).data;
+        s.stage3[3 * i] = d[0]; s.stage3[3 * i + 1] = d[1]; s.stage3[3 * i + 2] = d[2];
+    }
+    die(s.ctx, setter(s.ctx, s.stage3.data(), 24), what);
+}
+template <class ATTR>
+inline void upload_rest(State& s, ATTR& nodeAttr)
+{
+    const size_t n = nodeAttr.size;
+    s.stage3.resize(3 * n);
+    for (size_t i = 0; i < n; ++i) {
+        const double* d = std::get<FIELDS<ATTR>::x0>(nodeAttr.Get_Unchecked(i)).data;
+        s.stage3[3 * i] = d[0]; s.stage3[3 * i + 1] = d[1]; s.stage3[3 * i + 2] = d[2];
+    }
+    die(s.ctx, cipc_set_rest_positions(s.ctx, s.stage3.data(), 24), "cipc_set_rest_positions");
+}
+inline void upload_topology(State& s, size_t nV, const std::vector<int>& boundaryNode, const std::vector<VECTOR<int, 2>>& boundaryEdge,
+    const std::vector<VECTOR<int, 3>>& boundaryTri, size_t nRod, const std::map<int, std::set<int>>& NNExclusion,
+    const VECTOR<int, 2>& codimBNStartInd, const std::vector<bool>& DBCb)
+{
+    s.dbc.resize(nV);
+    for (size_t i = 0; i < nV; ++i) s.dbc[i] = DBCb[i] ? 1 : 0;
+    s.nnx.clear();
+    for (const auto& kv : NNExclusion)
+        for (int m : kv.second) { s.nnx.push_back(kv.first); s.nnx.push_back(m); }
+    const int32_t cd[2] = {codimBNStartInd[0], codimBNStartInd[1]};
+    static_assert(sizeof(VECTOR<int, 2>) == 16 && sizeof(VECTOR<int, 3>) == 16, "VECTOR<int,k> is a 16-byte record");
+    die(s.ctx, cipc_set_topology(s.ctx, (int)nV, (int)boundaryNode.size(), boundaryNode.data(), (int)boundaryEdge.size(),
+            boundaryEdge.empty() ? nullptr : boundaryEdge[0].data, 4, (int)boundaryTri.size(), boundaryTri.empty() ? nullptr : boundaryTri[0].data, 4,
+            (int)nRod, cd, s.dbc.data(), (int)(s.nnx.size() / 2), s.nnx.data(), nullptr, nullptr, nullptr),
+        "cipc_set_topology");
+}
+// the barrier calls receive the constraint set by const reference; skip the upload when it is (by pointer, size
+// and a strided sample) the set Compute_Constraint_Set just produced, which is what every reference call site passes
+inline void ensure_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs, const std::vector<VECTOR<double, 2>>& info)
+{
+    bool same = (cs.data() == s.csPtr && cs.size() == s.csSize);
+    if (same) {
+        const size_t step = cs.size() / 257 + 1;
+        size_t k = 0;
+        for (size_t i = 0; i < cs.size() && same; i += step, ++k)
+            for (int d = 0; d < 4; ++d) same = same && (cs[i][d] == s.csSample[4 * k + d]);
+    }
+    if (same) return;
+    s.stage2.resize(2 * cs.size());
+    for (size_t i = 0; i < cs.size(); ++i) { s.stage2[2 * i] = info[i][0]; s.stage2[2 * i + 1] = info[i][1]; }
+    die(s.ctx, cipc_set_constraints(s.ctx, cs.empty() ? nullptr : cs[0].data, s.stage2.data(), (int)cs.size()), "cipc_set_constraints");
+    s.csPtr = nullptr;
+}
+inline void remember_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs)
+{
+    s.csPtr = cs.data(); s.csSize = cs.size();
+    s.csSample.clear();
+    const size_t step = cs.size() / 257 + 1;
+    for (size_t i = 0; i < cs.size(); i += step)
+        for (int d = 0; d < 4; ++d) s.csSample.push_back(cs[i][d]);
+}
+
+template <class T, int dim, bool shell, bool elasticIPC>
+constexpr bool on_gpu = std::is_same<T, double>::value && dim == 3 && !shell && !elasticIPC;
+
+} // namespace cipc_shim
+
+// ------------------------------------------------------------------ FEM/IPC.h:19-36
+template <class T, int dim, bool shell = false, bool elasticIPC = false>
+void Compute_Constraint_Set(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeAttr, const std::vector<int>& boundaryNode,
+    const std::vector<VECTOR<int, 2>>& boundaryEdge, const std::vector<VECTOR<int, 3>>& boundaryTri, const std::vector<int>& particle,
+    const std::vector<VECTOR<int, 2>>& rod, const std::map<int, std::set<int>>& NNExclusion, const std::vector<T>& BNArea,
+    const std::vector<T>& BEArea, const std::vector<T>& BTArea, const VECTOR<int, 2>& codimBNStartInd, const std::vector<bool>& DBCb,
+    T dHat2, T thickness, bool getPTEE, std::vector<VECTOR<int, dim + 1>>& constraintSet, std::vector<VECTOR<int, 2>>& cs_PTEE,
+    std::vector<VECTOR<T, 2>>& stencilInfo)
+{
+    if constexpr (!cipc_shim::on_gpu<T, dim, shell, elasticIPC>) {
+        Compute_Constraint_Set_CPU<T, dim, shell, elasticIPC>(X, nodeAttr, boundaryNode, boundaryEdge, boundaryTri, particle, rod, NNExclusion,
+            BNArea, BEArea, BTArea, codimBNStartInd, DBCb, dHat2, thickness, getPTEE, constraintSet, cs_PTEE, stencilInfo);
+    }
+    else {
+        if (getPTEE) { // false at every call site of the reference
+            Compute_Constraint_Set_CPU<T, dim, shell, elasticIPC>(X, nodeAttr, boundaryNode, boundaryEdge, boundaryTri, particle, rod,
+                NNExclusion, BNArea, BEArea, BTArea, codimBNStartInd, DBCb, dHat2, thickness, getPTEE, constraintSet, cs_PTEE, stencilInfo);
+            return;
+        }
+        TIMER_FLAG("Compute_Constraint_Set");
+        cipc_shim::State& s = cipc_shim::state();
+        cipc_shim::upload_topology(s, X.size, boundaryNode, boundaryEdge, boundaryTri, rod.size(), NNExclusion, codimBNStartInd, DBCb);
+        cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+        cipc_shim::upload_rest(s, nodeAttr);
+        int n = 0;
+        cipc_shim::die(s.ctx, cipc_constraint_set(s.ctx, 0, dHat2, thickness, &n), "cipc_constraint_set");
+        constraintSet.resize(n); // the reference resize(0)s and refills (IPC.h:587-590)
+        stencilInfo.resize(n);
+        s.stage2.resize(2 * (size_t)n);
+        cipc_shim::die(s.ctx, cipc_get_constraints(s.ctx, n ? constraintSet[0].data : nullptr, s.stage2.data()), "cipc_get_constraints");
+        for (int i = 0; i < n; ++i) { stencilInfo[i][0] = s.stage2[2 * i]; stencilInfo[i][1] = s.stage2[2 * i + 1]; }
+        cipc_shim::remember_constraints(s, constraintSet);
+    }
+}
+
+// ------------------------------------------------------------------ FEM/IPC.h:742-748
+template <class T, int dim, bool elasticIPC = false>
+void Compute_Barrier(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeAttr, const std::vector<VECTOR<int, dim + 1>>& constraintSet,
+    const std::vector<VECTOR<T, 2>>& stencilInfo, T dHat2, T kappa[], T thickness, T& E)
+{
+    if constexpr (!cipc_shim::on_gpu<T, dim, false, elasticIPC>) {
+        Compute_Barrier_CPU<T, dim, elasticIPC>(X, nodeAttr, constraintSet, stencilInfo, dHat2, kappa, thickness, E);
+    }
+    else {
+        TIMER_FLAG("Compute_Barrier");
+        cipc_shim::State& s = cipc_shim::state();
+        cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+        cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
+        cipc_shim::die(s.ctx, cipc_barrier_energy(s.ctx, 0, dHat2, kappa, thickness, &E), "cipc_barrier_energy");
+    }
+}
+
+// ------------------------------------------------------------------ FEM/IPC.h:943-948
+template <class T, int dim, bool elasticIPC = false>
+void Compute_Barrier_Gradient(MESH_NODE<T, dim>& X, const std::vector<VECTOR<int, dim + 1>>& constraintSet,
+    const std::vector<VECTOR<T, 2>>& stencilInfo, T dHat2, T kappa[], T thickness, MESH_NODE_ATTR<T, dim>& nodeAttr)
+{
+    if constexpr (!cipc_shim::on_gpu<T, dim, false, elasticIPC>) {
+        Compute_Barrier_Gradient_CPU<T, dim, elasticIPC>(X, constraintSet, stencilInfo, dHat2, kappa, thickness, nodeAttr);
+    }
+    else {
+        TIMER_FLAG("Compute_Barrier_Gradient");
+        cipc_shim::State& s = cipc_shim::state();
+        cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+        cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
+        const size_t n = X.size;
+        s.stage3.assign(3 * n, 0.0);
+        cipc_shim::die(s.ctx, cipc_barrier_gradient(s.ctx, 0, dHat2, kappa, thickness, s.stage3.data(), 24), "cipc_barrier_gradient");
+        for (size_t i = 0; i < n; ++i) { // nodeAttr.g += (IPC.h:1034-1042); g lives inside the AoSoA record of node i
+            VECTOR<T, dim>& g = std::get<FIELDS<MESH_NODE_ATTR<T, dim>>::g>(nodeAttr.Get_Unchecked(i));
+            g[0] += s.stage3[3 * i]; g[1] += s.stage3[3 * i + 1]; g[2] += s.stage3[3 * i + 2];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ FEM/IPC.h:1258-1265
+template <class T, int dim, bool elasticIPC = false>
+void Compute_Barrier_Hessian(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeAttr, const std::vector<VECTOR<int, dim + 1>>& constraintSet,
+    const std::vector<VECTOR<T, 2>>& stencilInfo, T dHat2, T kappa[], T thickness, bool projectSPD, std::vector<Eigen::Triplet<T>>& triplets)
+{
+    if constexpr (!cipc_shim::on_gpu<T, dim, false, elasticIPC>) {
+        Compute_Barrier_Hessian_CPU<T, dim, elasticIPC>(X, nodeAttr, constraintSet, stencilInfo, dHat2, kappa, thickness, projectSPD, triplets);
+    }
+    else {
+        TIMER_FLAG("Compute_Barrier_Hessian");
+        static_assert(sizeof(Eigen::Triplet<T>) == sizeof(cipc_triplet), "Eigen::Triplet<double> is {int,int,double}");
+        cipc_shim::State& s = cipc_shim::state();
+        cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+        cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
+        int64_t n = 0;
+        cipc_shim::die(s.ctx, cipc_barrier_hessian(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian");
+        const size_t start = triplets.size(); // the new blocks are APPENDED (IPC.h:1371,1388)
+        triplets.resize(start + (size_t)n);
+        if (n) cipc_shim::die(s.ctx, cipc_get_triplets(s.ctx, reinterpret_cast<cipc_triplet*>(triplets.data() + start)), "cipc_get_triplets");
+    }
+}
+
+// ------------------------------------------------------------------ FEM/IPC.h:1879-1890
+template <class T, int dim, bool shell = false, bool elasticIPC = false>
+void Compute_Intersection_Free_StepSize(MESH_NODE<T, dim>& X, const std::vector<int>& boundaryNode,
+    const std::vector<VECTOR<int, 2>>& boundaryEdge, const std::vector<VECTOR<int, 3>>& boundaryTri, const std::vector<int>& particle,
+    const std::vector<VECTOR<int, 2>>& rod, const std::map<int, std::set<int>>& NNExclusion, const VECTOR<int, 2>& codimBNStartInd,
+    const std::vector<bool>& DBCb, const std::vector<T>& searchDir, T thickness, T& stepSize)
+{
+    if constexpr (!cipc_shim::on_gpu<T, dim, shell, elasticIPC>) {
+        Compute_Intersection_Free_StepSize_CPU<T, dim, shell, elasticIPC>(X, boundaryNode, boundaryEdge, boundaryTri, particle, rod, NNExclusion,
+            codimBNStartInd, DBCb, searchDir, thickness, stepSize);
+    }
+    else {
+        TIMER_FLAG("Compute_Intersection_Free_StepSize");
+        cipc_shim::State& s = cipc_shim::state();
+        cipc_shim::upload_topology(s, X.size, boundaryNode, boundaryEdge, boundaryTri, rod.size(), NNExclusion, codimBNStartInd, DBCb);
+        cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+        cipc_shim::die(s.ctx, cipc_set_search_dir(s.ctx, searchDir.data()), "cipc_set_search_dir");
+        cipc_shim::die(s.ctx, cipc_step_size(s.ctx, 0, thickness, &stepSize), "cipc_step_size");
+    }
+}
+
+// ------------------------------------------------------------------ FEM/IPC.h:2246-2249
+template <class T, int dim, bool elasticIPC = false>
+void Compute_Min_Dist2(MESH_NODE<T, dim>& X, const std::vector<VECTOR<int, dim + 1>>& constraintSet, T thickness, std::vector<T>& dist2,
+    T& minDist2)
+{
+    if constexpr (!cipc_shim::on_gpu<T, dim, false, elasticIPC>) {
+        Compute_Min_Dist2_CPU<T, dim, elasticIPC>(X, constraintSet, thickness, dist2, minDist2);
+    }
+    else {
+        TIMER_FLAG("Compute_Min_Dist");
+        cipc_shim::State& s = cipc_shim::state();
+        cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+        if (!(constraintSet.data() == s.csPtr && constraintSet.size() == s.csSize)) {
+            s.stage2.assign(2 * constraintSet.size(), 1.0);
+            cipc_shim::die(s.ctx, cipc_set_constraints(s.ctx, constraintSet.empty() ? nullptr : constraintSet[0].data, s.stage2.data(),
+                               (int)constraintSet.size()), "cipc_set_constraints");
+            s.csPtr = nullptr;
+        }
+        dist2.resize(constraintSet.size());
+        cipc_shim::die(s.ctx, cipc_min_dist2(s.ctx, thickness, dist2.data(), &minDist2), "cipc_min_dist2");
+    }
+}
+
+} // namespace JGSL
