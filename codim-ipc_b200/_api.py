@@ -56,7 +56,7 @@ def load_library():
     L.cipc_event_elapsed_ms.restype = C.c_double
     L.cipc_counter.restype = C.c_int64
     L.cipc_kernel_launches.restype = C.c_int64
-    for f in ("cipc_dev_positions", "cipc_dev_gradient", "cipc_dev_scalars"):
+    for f in ("cipc_dev_positions", "cipc_dev_gradient", "cipc_dev_scalars", "cipc_dev_triplets"):
         getattr(L, f).restype = C.c_void_p
     _lib = L
     return L
@@ -233,6 +233,13 @@ class ContactContext:
 
     def min_dist2_dev(self, thickness):
         self._ck(self.L.cipc_min_dist2_dev(self.h, C.c_double(thickness)))
+
+    def dev_triplets(self):
+        """device pointer of the (row, col, value) stream of the last barrier_hessian (expanded in HBM on first use)"""
+        p = self.L.cipc_dev_triplets(self.h)
+        if not p:
+            raise CipcError(CIPC_ERR_CUDA, self.L.cipc_last_error(self.h).decode())
+        return p
 
     def sync(self):
         self._ck(self.L.cipc_sync(self.h))

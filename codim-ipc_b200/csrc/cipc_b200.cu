@@ -17,6 +17,9 @@
 #include "prims.cuh"
 
 #include <cooperative_groups.h>
+#include <immintrin.h>
+#include <atomic>
+#include <thread>
 #include <algorithm>
 #include <cmath>
 #include <memory>
@@ -886,6 +889,21 @@ __global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restric
                         put_triplet(o + (I * 3 + a) * nn + J * 3 + b2, vids[I] * 3 + a, vids[J] * 3 + b2, H[(I * 3 + a) * nn + J * 3 + b2]);
     }
 }
+// dense-path blocks (mollified / rejected stencils) packed for the host: block k at dst + 144 k, meta[k] = (offset, count)
+__global__ void k_gather_dense(const int4* __restrict__ cs, const u32* __restrict__ off, const u32* __restrict__ list, const u32* __restrict__ nDev,
+    const cipc_triplet* __restrict__ trip, cipc_triplet* __restrict__ dst, uint2* __restrict__ meta)
+{
+    const u32 n = *nDev;
+    for (u32 k = blockIdx.x; k < n; k += gridDim.x) {
+        const u32 i = list[k];
+        const int d = block_dim_of(cs[i]);
+        const u32 cnt = (u32)(d * d), o = off[i];
+        if (threadIdx.x == 0) meta[k] = make_uint2(o, cnt);
+        const int4* src = reinterpret_cast<const int4*>(trip + o);
+        int4* out = reinterpret_cast<int4*>(dst + (size_t)k * 144);
+        for (u32 t = threadIdx.x; t < cnt; t += blockDim.x) out[t] = src[t];
+    }
+}
 template <int N>
 __global__ void k_test_make_pd(double* H, int count)
 {
@@ -1043,6 +1061,13 @@ struct cipc_ctx {
     DevBuf<cipc_triplet> trip;
     DevBuf<u32> tripOff, clsIdx[4];
     DevBuf<double> Y;
+    bool factorValid = false, expanded = true;
+    double *Y0 = nullptr, *Y1 = nullptr, *Y2 = nullptr;
+    void *h0 = nullptr, *h1 = nullptr, *h2 = nullptr;
+    u32 nk[4] = {0, 0, 0, 0};
+    DevBuf<cipc_triplet> denseBuf;
+    DevBuf<uint2> denseMeta;
+    PinnedBuf pinY, pinH, pinD, pinM;
     DevBuf<double4> yhdr; // YHdr records (32 B each)
     int64_t nTrip = 0;
     PinnedBuf pin;
@@ -1347,6 +1372,103 @@ int do_min_dist(cipc_ctx* c, bool wantDist)
 }
 
 } // namespace
+
+// ---- triplet delivery
+// device side: expand the factors into the triplet stream (needed only when the triplets are consumed on the GPU)
+void expand_on_device(cipc_ctx* c)
+{
+    if (!c->factorValid || c->expanded) return;
+    const u32* nk = c->nk;
+    {
+        cipc_ctx::Scope sk(c, "k_barrier_hessian"); // the dominant kernel: triplet expansion of the PT/EE blocks
+        if (nk[0]) CIPC_LAUNCH(k_hessian_expand<0>, div_up((u64)nk[0] * 144, 256), 256, 0, c->st, c->Y0, (const YHdr*)c->h0, (u64)nk[0] * 144, c->trip.p);
+    }
+    if (nk[1]) CIPC_LAUNCH(k_hessian_expand<1>, div_up((u64)nk[1] * 81, 256), 256, 0, c->st, c->Y1, (const YHdr*)c->h1, (u64)nk[1] * 81, c->trip.p);
+    if (nk[2]) CIPC_LAUNCH(k_hessian_expand<2>, div_up((u64)nk[2] * 36, 256), 256, 0, c->st, c->Y2, (const YHdr*)c->h2, (u64)nk[2] * 36, c->trip.p);
+    c->expanded = true;
+}
+// host side: y y^T expansion of one stencil with streaming 16-byte stores (the destination is never read back)
+template <int NB, int NY>
+inline void expand_one_host(const double* y, const YHdr& h, cipc_triplet* out, bool aligned)
+{
+    constexpr int NN = 3 * NB;
+    int idx[NN];
+    for (int r = 0; r < NN; ++r) idx[r] = h.v[r / 3] * 3 + r % 3;
+    cipc_triplet* o = out + h.off;
+    for (int r = 0; r < NN; ++r)
+        for (int c = 0; c < NN; ++c) {
+            double v = 0.0;
+            for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
+            long long vb;
+            memcpy(&vb, &v, 8);
+            const __m128i q = _mm_set_epi64x(vb, (long long)(((unsigned long long)(unsigned)idx[c] << 32) | (unsigned)idx[r]));
+            if (aligned) _mm_stream_si128(reinterpret_cast<__m128i*>(o + r * NN + c), q);
+            else _mm_storeu_si128(reinterpret_cast<__m128i*>(o + r * NN + c), q);
+        }
+}
+// Delivers the triplets of the last projected Hessian to host memory: ships the compact factors (8x fewer
+// bytes over PCIe than the triplet stream) and expands them with all host threads.
+void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
+{
+    const u32* nk = c->nk;
+    const size_t yD = (size_t)nk[0] * 36 + (size_t)nk[1] * 18 + (size_t)nk[2] * 6, nH = (size_t)nk[0] + nk[1] + nk[2];
+    double* hY = (double*)c->pinY.reserve(yD * 8 + 64);
+    YHdr* hH = (YHdr*)c->pinH.reserve(nH * sizeof(YHdr) + 64);
+    u32 nDense = 0;
+    CIPC_CUDA(cudaMemcpyAsync(&nDense, c->counters.p + 15, 4, cudaMemcpyDeviceToHost, c->st));
+    if (yD) CIPC_CUDA(cudaMemcpyAsync(hY, c->Y.p, yD * 8, cudaMemcpyDeviceToHost, c->st));
+    if (nH) CIPC_CUDA(cudaMemcpyAsync(hH, c->yhdr.p, nH * sizeof(YHdr), cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    cipc_triplet* hD = nullptr;
+    uint2* hM = nullptr;
+    if (nDense) {
+        c->denseBuf.reserve((size_t)nDense * 144, c->st);
+        c->denseMeta.reserve(nDense, c->st);
+        CIPC_LAUNCH(k_gather_dense, std::min<u32>(nDense, 4736u), 64, 0, c->st, c->cs.p, c->tripOff.p, c->clsIdx[3].p, c->counters.p + 15, c->trip.p,
+            c->denseBuf.p, c->denseMeta.p);
+        hD = (cipc_triplet*)c->pinD.reserve((size_t)nDense * 144 * sizeof(cipc_triplet));
+        hM = (uint2*)c->pinM.reserve((size_t)nDense * sizeof(uint2));
+        CIPC_CUDA(cudaMemcpyAsync(hD, c->denseBuf.p, (size_t)nDense * 144 * sizeof(cipc_triplet), cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaMemcpyAsync(hM, c->denseMeta.p, (size_t)nDense * sizeof(uint2), cudaMemcpyDeviceToHost, c->st));
+    }
+    // expansion of the factored stencils overlaps the dense D2H
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const double* y0 = hY; const double* y1 = y0 + (size_t)nk[0] * 36; const double* y2 = y1 + (size_t)nk[1] * 18;
+    const YHdr* g0 = hH; const YHdr* g1 = g0 + nk[0]; const YHdr* g2 = g1 + nk[1];
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("CIPC_HOST_THREADS")) nt = atoi(e);
+    nt = std::max(1, std::min(nt, 256));
+    const size_t CH = 2048; // stencils per work item
+    const size_t items0 = (nk[0] + CH - 1) / CH, items1 = (nk[1] + CH - 1) / CH, items2 = (nk[2] + CH - 1) / CH;
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            size_t it = next.fetch_add(1);
+            if (it >= items0 + items1 + items2) break;
+            if (it < items0) {
+                const size_t a = it * CH, b = std::min<size_t>(a + CH, nk[0]);
+                for (size_t q = a; q < b; ++q) if (g0[q].off != 0xffffffffu) expand_one_host<4, 3>(y0 + q * 36, g0[q], out, aligned);
+            }
+            else if (it < items0 + items1) {
+                const size_t a = (it - items0) * CH, b = std::min<size_t>(a + CH, nk[1]);
+                for (size_t q = a; q < b; ++q) if (g1[q].off != 0xffffffffu) expand_one_host<3, 2>(y1 + q * 18, g1[q], out, aligned);
+            }
+            else {
+                const size_t a = (it - items0 - items1) * CH, b = std::min<size_t>(a + CH, nk[2]);
+                for (size_t q = a; q < b; ++q) if (g2[q].off != 0xffffffffu) expand_one_host<2, 1>(y2 + q * 6, g2[q], out, aligned);
+            }
+        }
+        _mm_sfence();
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    if (nDense) {
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        for (u32 k = 0; k < nDense; ++k) memcpy(out + hM[k].x, hD + (size_t)k * 144, (size_t)hM[k].y * sizeof(cipc_triplet));
+    }
+}
 
 // ========================================================================================= C ABI
 extern "C" {
@@ -1674,6 +1796,7 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
         c->begin_call();
         const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
         c->nTrip = 0;
+        c->factorValid = false;
         if (c->nC) {
             cipc_ctx::Scope sc(c, "barrier_H");
             c->tripOff.reserve(c->nC, c->st);
@@ -1716,12 +1839,10 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
                         if (nk[2]) CIPC_LAUNCH(k_hessian_factor<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
                             c->clsIdx[2].p, nk[2], bp, Y2, h2, dl, dn);
                     }
-                    {
-                        cipc_ctx::Scope sk(c, "k_barrier_hessian"); // the dominant kernel: triplet expansion
-                        if (nk[0]) CIPC_LAUNCH(k_hessian_expand<0>, div_up((u64)nk[0] * 144, 256), 256, 0, c->st, Y0, h0, (u64)nk[0] * 144, c->trip.p);
-                    }
-                    if (nk[1]) CIPC_LAUNCH(k_hessian_expand<1>, div_up((u64)nk[1] * 81, 256), 256, 0, c->st, Y1, h1, (u64)nk[1] * 81, c->trip.p);
-                    if (nk[2]) CIPC_LAUNCH(k_hessian_expand<2>, div_up((u64)nk[2] * 36, 256), 256, 0, c->st, Y2, h2, (u64)nk[2] * 36, c->trip.p);
+                    c->factorValid = true;
+                    c->expanded = false;
+                    c->Y0 = Y0; c->Y1 = Y1; c->Y2 = Y2; c->h0 = h0; c->h1 = h1; c->h2 = h2;
+                    for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
                     // mollified stencils + rejected ones: dense eigen path, list length read on the device
                     CIPC_LAUNCH(k_barrier_hessian, 592, 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
                         (const u32*)dn, bp, projectSPD, c->trip.p);
@@ -1747,12 +1868,22 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 {
     return guarded(ctx, [&]() {
-        if (ctx->nTrip) {
+        if (!ctx->nTrip) return (int)CIPC_OK;
+        const char* dma = getenv("CIPC_TRIPLETS_DMA"); // =1: always copy the expanded stream over PCIe
+        if (ctx->factorValid && !(dma && dma[0] == '1')) deliver_triplets_host(ctx, out);
+        else {
+            expand_on_device(ctx);
             CIPC_CUDA(cudaMemcpyAsync(out, ctx->trip.p, (size_t)ctx->nTrip * sizeof(cipc_triplet), cudaMemcpyDeviceToHost, ctx->st));
             CIPC_CUDA(cudaStreamSynchronize(ctx->st));
         }
         return (int)CIPC_OK;
     });
+}
+cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx)
+{
+    if (!ctx) return nullptr;
+    int r = guarded(ctx, [&]() { ctx->begin_call(); expand_on_device(ctx); return (int)CIPC_OK; });
+    return r == CIPC_OK ? ctx->trip.p : nullptr;
 }
 int cipc_step_size_dev(cipc_ctx* ctx, int elastic, double thickness, double stepIn)
 {

@@ -82,8 +82,12 @@ int cipc_barrier_gradient(cipc_ctx* ctx, int elasticIPC, double dHat2, const dou
 /* computes all (PSD-projected) blocks on the device; nTriplets_out = 144/81/36 per constraint */
 int cipc_barrier_hessian(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
                          int projectSPD, int64_t* nTriplets_out);
-/* copies the triplets of the last cipc_barrier_hessian to `out` (caller appends them, IPC.h:1371-1388) */
+/* delivers the triplets of the last cipc_barrier_hessian to host memory `out` (caller appends them, IPC.h:1371-1388).
+ * Projected blocks travel over PCIe as compact factors (288 B instead of 2304 B per PT/EE stencil) and are expanded by
+ * the host cores (CIPC_HOST_THREADS, default all); CIPC_TRIPLETS_DMA=1 copies the expanded device stream instead. */
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out);
+/* the same triplet stream resident in HBM (expanded on the device on first use); NULL on error */
+cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx);
 
 /* ---- Compute_Intersection_Free_StepSize --------------------------------------------------- */
 /* stepSize_inout: in = current upper bound, out = min(bound [possibly shrunk by the span rule,

@@ -74,3 +74,25 @@ def test_rank_partition_covers_all_pairs():
     assert np.array_equal(sort_cs(merged), sort_cs(cs_full))
     assert min(parts[1], parts[3]) == full.step_size(sc["xi"], 1.0)
     full.close()
+
+
+def test_triplet_delivery_paths_agree(ctx, monkeypatch):
+    """host expansion of the compact factors == PCIe copy of the device-expanded stream"""
+    from codim_ipc_b200 import scenes
+    sc = scenes.mixed_small()
+    ctx.set_scene(sc)
+    ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+    a = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True).copy()
+    monkeypatch.setenv("CIPC_TRIPLETS_DMA", "1")
+    b = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True).copy()
+    monkeypatch.delenv("CIPC_TRIPLETS_DMA")
+    assert len(a) == len(b) > 0
+    assert np.array_equal(a["row"], b["row"]) and np.array_equal(a["col"], b["col"])
+    assert np.abs(a["val"] - b["val"]).max() <= 1e-13 * np.abs(b["val"]).max()
+    monkeypatch.setenv("CIPC_HESSIAN_DENSE", "1")  # dense 12x12 eigen path for every stencil: the cross-check of the low-rank path
+    c = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True).copy()
+    monkeypatch.delenv("CIPC_HESSIAN_DENSE")
+    assert np.array_equal(a["row"], c["row"])
+    from helpers import max_block_rel_err
+    cs, _ = ctx.get_constraints()
+    assert max_block_rel_err(cs, a["val"], c["val"]) <= 1e-10
