@@ -245,6 +245,8 @@ def main():
         trip_h = trip_raw.view(cipc.TRIPLET_DTYPE).reshape(-1)
         import ctypes as C
 
+        pcie = [0]
+
         def e2e_step():
             h2d = d2h = 0
             # Compute_Constraint_Set: X, x0 in; constraintSet, stencilInfo out
@@ -259,7 +261,8 @@ def main():
             g_h[:] = 0
             ctx.barrier_gradient(dHat2, kappa, xi, g_h); d2h += nV * 24
             ctx.set_positions(X4); h2d += X4.nbytes
-            tr = ctx.barrier_hessian(dHat2, kappa, xi, True, out=trip_h); d2h += len(tr) * 16
+            tr = ctx.barrier_hessian(dHat2, kappa, xi, True, out=trip_h); d2h += len(tr) * 16  # bytes delivered to the host buffer
+            pcie[0] = sum(ctx.counter(k) * b for k, b in (("hessian_4pt", 320), ("hessian_pe", 176), ("hessian_pp", 80))) + ctx.counter("hessian_mollified") * 2312
             # Compute_Intersection_Free_StepSize: X, searchDir in; step out
             ctx.set_positions(X4); ctx.set_search_dir(p_h); h2d += X4.nbytes + p_h.nbytes
             a = ctx.step_size(xi, 1.0); d2h += 8
@@ -281,7 +284,9 @@ def main():
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(t.item()), "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        e2e = {"value": float(t.item()), "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "d2h = bytes delivered into host buffers; the Hessian triplets (%d B) cross PCIe as %d B of factors and are expanded "
+                       "by the host cores inside cipc_get_triplets" % (len(trip_h[:nTrip]) * 16, pcie[0])}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

@@ -1416,9 +1416,22 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     YHdr* hH = (YHdr*)c->pinH.reserve(nH * sizeof(YHdr) + 64);
     u32 nDense = 0;
     CIPC_CUDA(cudaMemcpyAsync(&nDense, c->counters.p + 15, 4, cudaMemcpyDeviceToHost, c->st));
-    if (yD) CIPC_CUDA(cudaMemcpyAsync(hY, c->Y.p, yD * 8, cudaMemcpyDeviceToHost, c->st));
     if (nH) CIPC_CUDA(cudaMemcpyAsync(hH, c->yhdr.p, nH * sizeof(YHdr), cudaMemcpyDeviceToHost, c->st));
     CIPC_CUDA(cudaStreamSynchronize(c->st));
+    // the factors are copied in pieces; host threads start expanding as soon as the piece they need has landed
+    const size_t PIECE = (size_t)8 << 20; // doubles (64 MiB)
+    std::vector<cudaEvent_t> evs;
+    std::vector<size_t> evEnd;
+    for (size_t o = 0; o < yD; o += PIECE) {
+        const size_t len = std::min(PIECE, yD - o);
+        CIPC_CUDA(cudaMemcpyAsync(hY + o, c->Y.p + o, len * 8, cudaMemcpyDeviceToHost, c->st));
+        cudaEvent_t e;
+        CIPC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CIPC_CUDA(cudaEventRecord(e, c->st));
+        evs.push_back(e);
+        evEnd.push_back(o + len);
+    }
+    std::atomic<size_t> landed(0);
     cipc_triplet* hD = nullptr;
     uint2* hM = nullptr;
     if (nDense) {
@@ -1441,20 +1454,26 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     const size_t CH = 2048; // stencils per work item
     const size_t items0 = (nk[0] + CH - 1) / CH, items1 = (nk[1] + CH - 1) / CH, items2 = (nk[2] + CH - 1) / CH;
     std::atomic<size_t> next(0);
+    auto wait_for = [&](size_t needEnd) {
+        while (landed.load(std::memory_order_acquire) < needEnd) std::this_thread::yield();
+    };
     auto worker = [&]() {
         for (;;) {
             size_t it = next.fetch_add(1);
             if (it >= items0 + items1 + items2) break;
             if (it < items0) {
                 const size_t a = it * CH, b = std::min<size_t>(a + CH, nk[0]);
+                wait_for(b * 36);
                 for (size_t q = a; q < b; ++q) if (g0[q].off != 0xffffffffu) expand_one_host<4, 3>(y0 + q * 36, g0[q], out, aligned);
             }
             else if (it < items0 + items1) {
                 const size_t a = (it - items0) * CH, b = std::min<size_t>(a + CH, nk[1]);
+                wait_for((size_t)nk[0] * 36 + b * 18);
                 for (size_t q = a; q < b; ++q) if (g1[q].off != 0xffffffffu) expand_one_host<3, 2>(y1 + q * 18, g1[q], out, aligned);
             }
             else {
                 const size_t a = (it - items0 - items1) * CH, b = std::min<size_t>(a + CH, nk[2]);
+                wait_for((size_t)nk[0] * 36 + (size_t)nk[1] * 18 + b * 6);
                 for (size_t q = a; q < b; ++q) if (g2[q].off != 0xffffffffu) expand_one_host<2, 1>(y2 + q * 6, g2[q], out, aligned);
             }
         }
@@ -1462,8 +1481,16 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     };
     std::vector<std::thread> th;
     for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+    bool copyFailed = false;
+    for (size_t k = 0; k < evs.size(); ++k) { // this thread publishes the pieces as they land, then joins the work
+        if (cudaEventSynchronize(evs[k]) != cudaSuccess) copyFailed = true;
+        landed.store(copyFailed ? yD : evEnd[k], std::memory_order_release);
+    }
+    landed.store(yD, std::memory_order_release);
     worker();
     for (auto& t : th) t.join();
+    for (auto e : evs) cudaEventDestroy(e);
+    if (copyFailed) throw CudaError("device-to-host copy of the Hessian factors failed");
     if (nDense) {
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         for (u32 k = 0; k < nDense; ++k) memcpy(out + hM[k].x, hD + (size_t)k * 144, (size_t)hM[k].y * sizeof(cipc_triplet));
