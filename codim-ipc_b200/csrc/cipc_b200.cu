@@ -94,6 +94,7 @@ __device__ __forceinline__ int ux(u64 p) { return (int)(p & 0x1fffffu); }
 __device__ __forceinline__ int uy(u64 p) { return (int)((p >> 21) & 0x1fffffu); }
 __device__ __forceinline__ int uz(u64 p) { return (int)((p >> 42) & 0x1fffffu); }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+constexpr int FINE_SUB = 16; // quantised-AABB pre-test resolution: FINE_SUB steps per voxel
 
 // ===================================================================== reductions for the grids
 __global__ void k_edge_len_partial(const double4* __restrict__ X, const int2* __restrict__ BE, int nBE, double* partial)
@@ -149,7 +150,7 @@ __global__ void k_bbox(const double4* __restrict__ X, const double4* __restrict_
 // ===================================================================== voxel boxes
 // Constraint-set grid (our own; any superset of the AABB-gap test is valid):
 // every primitive's AABB inflated by r (~dHat/2).  prim ids: nodes [0,nBN), edges, triangles.
-__global__ void k_boxes_ccs(Topo T, const double4* __restrict__ X, GridDesc G, double r, u64* boxLo, u64* boxHi, u32* cnt)
+__global__ void k_boxes_ccs(Topo T, const double4* __restrict__ X, GridDesc G, double r, u64* boxLo, u64* boxHi, ulonglong2* fine, u32* cnt)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int nP = T.nBN + T.nBE + T.nBT;
@@ -168,19 +169,23 @@ __global__ void k_boxes_ccs(Topo T, const double4* __restrict__ X, GridDesc G, d
     else { const int4 t = T.BT[g - T.nBN - T.nBE]; acc(t.x, true); acc(t.y, false); acc(t.z, false); }
     const double o[3] = {G.ox, G.oy, G.oz};
     const int gd[3] = {G.gx, G.gy, G.gz};
-    int l[3], h[3];
+    int l[3], h[3], fl[3], fh[3];
     for (int d = 0; d < 3; ++d) {
-        l[d] = clampi((int)floor((lo[d] - r - o[d]) * G.inv), 0, gd[d] - 1);
-        h[d] = clampi((int)floor((hi[d] + r - o[d]) * G.inv), 0, gd[d] - 1);
+        // FINE_SUB-times finer coordinates of the same inflated box; the voxel index is the fine index / FINE_SUB
+        fl[d] = clampi((int)floor((lo[d] - r - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
+        fh[d] = clampi((int)floor((hi[d] + r - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
+        l[d] = fl[d] / FINE_SUB;
+        h[d] = fh[d] / FINE_SUB;
     }
     boxLo[g] = pack3(l[0], l[1], l[2]);
     boxHi[g] = pack3(h[0], h[1], h[2]);
+    fine[g] = make_ulonglong2(pack3(fl[0], fl[1], fl[2]), pack3(fh[0], fh[1], fh[2]));
     cnt[g] = (u32)(h[0] - l[0] + 1) * (u32)(h[1] - l[1] + 1) * (u32)(h[2] - l[2] + 1);
 }
 // Swept grid of the step-size search: per boundary-node slot, the voxel range of
 // [min(x, x+a p) - xi/2, max(x, x+a p) + xi/2]  (SPATIAL_HASH.h:522-529), arithmetic order kept.
 __global__ void k_node_boxes_ccd(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double alpha, double halfXi,
-    GridDesc G, u64* nodeLo, u64* nodeHi)
+    double guard, GridDesc G, u64* nodeLo, u64* nodeHi, ulonglong2* nodeFine)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T.nBN) return;
@@ -188,30 +193,40 @@ __global__ void k_node_boxes_ccd(Topo T, const double4* __restrict__ X, const do
     const double4 x = X[v], p = P[v];
     const double c[3] = {x.x, x.y, x.z};
     const double e[3] = {__dadd_rn(x.x, __dmul_rn(alpha, p.x)), __dadd_rn(x.y, __dmul_rn(alpha, p.y)), __dadd_rn(x.z, __dmul_rn(alpha, p.z))};
+    const double f[3] = {__dadd_rn(x.x, p.x), __dadd_rn(x.y, p.y), __dadd_rn(x.z, p.z)}; // full step, as the swept AABB test uses it
     const double o[3] = {G.ox, G.oy, G.oz};
     const int gd[3] = {G.gx, G.gy, G.gz};
-    int l[3], h[3];
+    int l[3], h[3], fl[3], fh[3];
     for (int d = 0; d < 3; ++d) {
         const double mn = __dsub_rn(fmin(c[d], e[d]), halfXi), mx = __dadd_rn(fmax(c[d], e[d]), halfXi);
         l[d] = clampi((int)floor(__dmul_rn(__dsub_rn(mn, o[d]), G.inv)), 0, gd[d] - 1);
         h[d] = clampi((int)floor(__dmul_rn(__dsub_rn(mx, o[d]), G.inv)), 0, gd[d] - 1);
+        // conservative quantised full-step box (any pair passing the swept AABB test with gap xi overlaps here)
+        fl[d] = clampi((int)floor((fmin(c[d], f[d]) - halfXi - guard - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
+        fh[d] = clampi((int)floor((fmax(c[d], f[d]) + halfXi + guard - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
     }
     nodeLo[i] = pack3(l[0], l[1], l[2]);
     nodeHi[i] = pack3(h[0], h[1], h[2]);
+    nodeFine[i] = make_ulonglong2(pack3(fl[0], fl[1], fl[2]), pack3(fh[0], fh[1], fh[2]));
 }
 // edges / triangles: union of their vertices' node boxes (SPATIAL_HASH.h:555-592)
-__global__ void k_prim_boxes_ccd(Topo T, const u64* __restrict__ nodeLo, const u64* __restrict__ nodeHi, u64* boxLo, u64* boxHi, u32* cnt)
+__global__ void k_prim_boxes_ccd(Topo T, const u64* __restrict__ nodeLo, const u64* __restrict__ nodeHi, const ulonglong2* __restrict__ nodeFine,
+    u64* boxLo, u64* boxHi, ulonglong2* fine, u32* cnt)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int nP = T.nBN + T.nBE + T.nBT;
     if (g >= nP) return;
-    int l[3], h[3];
+    int l[3], h[3], fl[3], fh[3];
     auto acc = [&](int sv, bool first) {
         const u64 a = nodeLo[sv], b = nodeHi[sv];
+        const ulonglong2 q = nodeFine[sv];
         const int al[3] = {ux(a), uy(a), uz(a)}, bh[3] = {ux(b), uy(b), uz(b)};
+        const int ql[3] = {ux(q.x), uy(q.x), uz(q.x)}, qh[3] = {ux(q.y), uy(q.y), uz(q.y)};
         for (int d = 0; d < 3; ++d) {
             l[d] = first ? al[d] : min(l[d], al[d]);
             h[d] = first ? bh[d] : max(h[d], bh[d]);
+            fl[d] = first ? ql[d] : min(fl[d], ql[d]);
+            fh[d] = first ? qh[d] : max(fh[d], qh[d]);
         }
     };
     if (g < T.nBN) acc(g, true);
@@ -219,6 +234,7 @@ __global__ void k_prim_boxes_ccd(Topo T, const u64* __restrict__ nodeLo, const u
     else { const int4 t = T.BT[g - T.nBN - T.nBE]; acc(T.v2sv[t.x], true); acc(T.v2sv[t.y], false); acc(T.v2sv[t.z], false); }
     boxLo[g] = pack3(l[0], l[1], l[2]);
     boxHi[g] = pack3(h[0], h[1], h[2]);
+    fine[g] = make_ulonglong2(pack3(fl[0], fl[1], fl[2]), pack3(fh[0], fh[1], fh[2]));
     cnt[g] = (u32)(h[0] - l[0] + 1) * (u32)(h[1] - l[1] + 1) * (u32)(h[2] - l[2] + 1);
 }
 // one (cell<<2|kind, local id) entry per covered voxel
@@ -295,44 +311,56 @@ __device__ __forceinline__ bool min_corner(u32 cell, u64 loA, u64 loB, const Gri
     return cell == mx + (u32)G.gx * (my + (u32)G.gy * mz);
 }
 
-// One thread per sorted hash entry in [e0, e1).  CCD=false: constraint-set pass (gap test with
-// dist = dHat).  CCD=true: step-size pass (swept AABB test with dist = thickness, full search dir).
+// quantised AABBs overlap in all three axes
+__device__ __forceinline__ bool fine_overlap(const ulonglong2 a, const ulonglong2 b)
+{
+    return ux(a.x) <= ux(b.y) && ux(b.x) <= ux(a.y) && uy(a.x) <= uy(b.y) && uy(b.x) <= uy(a.y) && uz(a.x) <= uz(b.y) && uz(b.x) <= uz(a.y);
+}
+// One WARP per voxel cell in [c0, c1): the queries of the cell (points, then edges) are walked in order and the 32
+// lanes test 32 targets of the run at a time, so the id / box / topology loads of a warp instruction are contiguous
+// or broadcast.  Per pair, cheapest test first: quantised AABB (16 B gather), min-corner rule (8 B gather), topology
+// filters, then the coordinates and the reference's exact AABB test.
+// CCD=false: constraint-set pass (gap test with dist = dHat).  CCD=true: step-size pass (swept AABB test with
+// dist = thickness, full search direction).
 template <bool CCD>
 __global__ void __launch_bounds__(256) k_pairs(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double dist_,
-    const u32* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ headScan, const u32* __restrict__ heads,
-    const u32* __restrict__ ks, u32 e0, u32 e1, const u64* __restrict__ boxLo, GridDesc G, CandOut out)
+    const u32* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ ks, u32 c0, u32 c1,
+    const u64* __restrict__ boxLo, const ulonglong2* __restrict__ fine, GridDesc G, CandOut out)
 {
-    const u32 i = e0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= e1) return;
-    const u32 key = keys[i], kind = key & 3u;
-    if (kind == 2) return;
-    const u32 cell = key >> 2, c = headScan[i] + heads[i] - 1u;
-    const int id = (int)vals[i];
+    const u32 cellIdx = c0 + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    if (cellIdx >= c1) return;
+    const u32 lane = threadIdx.x & 31;
+    const u32 p0 = ks[cellIdx * 4], e0 = ks[cellIdx * 4 + 1], t0 = ks[cellIdx * 4 + 2], end = ks[cellIdx * 4 + 3];
+    const u32 cell = keys[p0] >> 2;
     const xd dist(dist_);
-    const int tOff = T.nBN + T.nBE;
-    if (kind == 0) {
-        const int svI = id, vI = T.BN[svI];
+    const int eOff = T.nBN, tOff = T.nBN + T.nBE;
+    // ---- point queries
+    for (u32 i = p0; i < e0; ++i) {
+        const int svI = (int)vals[i], vI = T.BN[svI];
         const u64 loA = boxLo[svI];
+        const ulonglong2 fA = fine[svI];
         const xv3 p = ldx(X, vI);
         xv3 dp;
         if (CCD) dp = ldx(P, vI);
-        for (u32 j = ks[c * 4 + 2]; j < ks[c * 4 + 3]; ++j) {
+        for (u32 j = t0 + lane; j < end; j += 32) {
             const int t = (int)vals[j];
+            if (!fine_overlap(fA, fine[tOff + t])) continue;
             if (!min_corner(cell, loA, boxLo[tOff + t], G)) continue;
             const int4 tri = T.BT[t];
             if (!pt_pair_ok(T, vI, tri)) continue;
-            const xv3 t0 = ldx(X, tri.x), t1 = ldx(X, tri.y), t2 = ldx(X, tri.z);
+            const xv3 t0_ = ldx(X, tri.x), t1 = ldx(X, tri.y), t2 = ldx(X, tri.z);
             bool ok;
-            if (CCD) ok = pt_ccd_broadphase(p, t0, t1, t2, dp, ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
-            else ok = pt_cd_broadphase(p, t0, t1, t2, dist);
+            if (CCD) ok = pt_ccd_broadphase(p, t0_, t1, t2, dp, ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
+            else ok = pt_cd_broadphase(p, t0_, t1, t2, dist);
             if (ok) cand_push(out, 0, svI, t);
         }
         // rod / particle points against rod edges (IPC.h:271-326; step size: particles only, :2098-2135)
         if (T.nRod > 0 && svI >= (CCD ? T.codim1 : T.codim0)) {
-            for (u32 j = ks[c * 4 + 1]; j < ks[c * 4 + 2]; ++j) {
+            for (u32 j = e0 + lane; j < t0; j += 32) {
                 const int e = (int)vals[j];
                 if (e < T.nBE - T.nRod) continue;
-                if (!min_corner(cell, loA, boxLo[T.nBN + e], G)) continue;
+                if (!fine_overlap(fA, fine[eOff + e])) continue;
+                if (!min_corner(cell, loA, boxLo[eOff + e], G)) continue;
                 const int2 ed = T.BE[e];
                 if (vI == ed.x || vI == ed.y) continue;
                 if ((T.flags[vI] & 1) && (T.flags[ed.x] & 1) && (T.flags[ed.y] & 1)) continue;
@@ -343,11 +371,11 @@ __global__ void __launch_bounds__(256) k_pairs(Topo T, const double4* __restrict
                 if (ok) cand_push(out, 2, svI, e);
             }
         }
-        // particle against later boundary-node slots (IPC.h:328-352, :2137-2163)
+        // particle against later boundary-node slots (IPC.h:328-352, :2137-2163); slots ascend inside a run
         if (svI >= T.codim1) {
-            for (u32 j = ks[c * 4 + 0]; j < ks[c * 4 + 1]; ++j) {
+            for (u32 j = i + 1 + lane; j < e0; j += 32) {
                 const int svJ = (int)vals[j];
-                if (svJ <= svI) continue;
+                if (!fine_overlap(fA, fine[svJ])) continue;
                 if (!min_corner(cell, loA, boxLo[svJ], G)) continue;
                 const int vJ = T.BN[svJ];
                 if ((T.flags[vI] & 1) && (T.flags[vJ] & 1)) continue;
@@ -357,17 +385,19 @@ __global__ void __launch_bounds__(256) k_pairs(Topo T, const double4* __restrict
             }
         }
     }
-    else {
-        const int eI = id;
+    // ---- edge queries: edge ids ascend inside a run, so j > i <=> eJ > eI
+    for (u32 i = e0; i + 1 < t0; ++i) {
+        const int eI = (int)vals[i];
         const int2 a = T.BE[eI];
-        const u64 loA = boxLo[T.nBN + eI];
+        const u64 loA = boxLo[eOff + eI];
+        const ulonglong2 fA = fine[eOff + eI];
         const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y);
         xv3 da0, da1;
         if (CCD) { da0 = ldx(P, a.x); da1 = ldx(P, a.y); }
-        for (u32 j = ks[c * 4 + 1]; j < ks[c * 4 + 2]; ++j) {
+        for (u32 j = i + 1 + lane; j < t0; j += 32) {
             const int eJ = (int)vals[j];
-            if (eJ <= eI) continue;
-            if (!min_corner(cell, loA, boxLo[T.nBN + eJ], G)) continue;
+            if (!fine_overlap(fA, fine[eOff + eJ])) continue;
+            if (!min_corner(cell, loA, boxLo[eOff + eJ], G)) continue;
             const int2 b = T.BE[eJ];
             if (!ee_pair_ok(T, a, b)) continue;
             const xv3 b0 = ldx(X, b.x), b1 = ldx(X, b.y);
@@ -1042,6 +1072,7 @@ struct cipc_ctx {
     DevBuf<double> stageD;
     // hash
     DevBuf<u64> boxLo, boxHi, nodeLo, nodeHi;
+    DevBuf<ulonglong2> fine, nodeFine;
     DevBuf<u32> cnt, keys, vals, heads, headScan, ks;
     SortWork sortwk;
     ScanWork scanwk;
@@ -1228,7 +1259,7 @@ bool size_grid(const double* mn, const double* mx, double voxelSize, GridDesc& G
     long g[3];
     for (int d = 0; d < 3; ++d) {
         g[d] = std::max(1L, (long)std::ceil(range[d] * inv)) + (plusOne ? 1 : 0);
-        if (g[d] > (1L << 21) - 1) return false;
+        if (g[d] > (1L << 17) - 1) return false; // FINE_SUB x finer coordinates must fit 21 bits
     }
     if ((double)g[0] * g[1] * g[2] >= (double)(1L << 30)) return false;
     G.ox = mn[0]; G.oy = mn[1]; G.oz = mn[2]; G.inv = inv;
@@ -1240,8 +1271,9 @@ bool size_grid(const double* mn, const double* mx, double voxelSize, GridDesc& G
 template <bool CCD>
 void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
 {
-    const u32 nE = H.nEntries;
-    const u32 e0 = (u32)((u64)nE * c->rank / c->world), e1 = (u32)((u64)nE * (c->rank + 1) / c->world);
+    // this rank's share: a contiguous range of voxel cells of the sorted hash
+    const u32 nCells = H.nCells;
+    const u32 e0 = (u32)((u64)nCells * c->rank / c->world), e1 = (u32)((u64)nCells * (c->rank + 1) / c->world);
     for (int k = 0; k < 4; ++k) counts[k] = 0;
     if (e1 <= e0) return;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -1253,8 +1285,8 @@ void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
         }
         out.count = c->counters.p;
         CIPC_CUDA(cudaMemsetAsync(c->counters.p, 0, 16 * sizeof(u32), c->st));
-        CIPC_LAUNCH(k_pairs<CCD>, div_up(e1 - e0, 256), 256, 0, c->st, c->T, c->X.p, c->P.p, dist, c->keys.p, c->vals.p,
-            c->headScan.p, c->heads.p, c->ks.p, e0, e1, c->boxLo.p, H.G, out);
+        CIPC_LAUNCH(k_pairs<CCD>, div_up((size_t)(e1 - e0) * 32, 256), 256, 0, c->st, c->T, c->X.p, c->P.p, dist, c->keys.p, c->vals.p,
+            c->ks.p, e0, e1, c->boxLo.p, c->fine.p, H.G, out);
         CIPC_CUDA(cudaMemcpyAsync(counts, c->counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         bool ok = true;
@@ -1335,9 +1367,14 @@ int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
         if (!size_grid(mn, mx, voxelSize, H.G, true)) return CIPC_ERR_GRID;
         const int nP = T.nBN + T.nBE + T.nBT;
         c->boxLo.reserve(nP, c->st); c->boxHi.reserve(nP, c->st); c->cnt.reserve(nP, c->st);
-        c->nodeLo.reserve(T.nBN, c->st); c->nodeHi.reserve(T.nBN, c->st);
-        CIPC_LAUNCH(k_node_boxes_ccd, div_up(T.nBN, TB), TB, 0, c->st, T, c->X.p, c->P.p, alpha, thickness / 2, H.G, c->nodeLo.p, c->nodeHi.p);
-        CIPC_LAUNCH(k_prim_boxes_ccd, div_up(nP, TB), TB, 0, c->st, T, c->nodeLo.p, c->nodeHi.p, c->boxLo.p, c->boxHi.p, c->cnt.p);
+        c->nodeLo.reserve(T.nBN, c->st); c->nodeHi.reserve(T.nBN, c->st); c->nodeFine.reserve(T.nBN, c->st); c->fine.reserve(nP, c->st);
+        double mag = 0;
+        for (int d = 0; d < 3; ++d) mag = std::max(mag, std::max(std::fabs(mn[d]), std::fabs(mx[d])));
+        const double guard = 16.0 * 2.220446049250313e-16 * (mag + 1.0 / H.G.inv);
+        CIPC_LAUNCH(k_node_boxes_ccd, div_up(T.nBN, TB), TB, 0, c->st, T, c->X.p, c->P.p, alpha, thickness / 2, guard, H.G, c->nodeLo.p, c->nodeHi.p,
+            c->nodeFine.p);
+        CIPC_LAUNCH(k_prim_boxes_ccd, div_up(nP, TB), TB, 0, c->st, T, c->nodeLo.p, c->nodeHi.p, c->nodeFine.p, c->boxLo.p, c->boxHi.p, c->fine.p,
+            c->cnt.p);
         build_cell_lists(c, H);
     }
     u32 counts[4];
@@ -1696,8 +1733,8 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             for (int d = 0; d < 3; ++d) { mn[d] -= r; mx[d] += r; }
             if (!size_grid(mn, mx, voxelSize, H.G, true)) return (int)CIPC_ERR_GRID;
             const int nP = T.nBN + T.nBE + T.nBT;
-            c->boxLo.reserve(nP, c->st); c->boxHi.reserve(nP, c->st); c->cnt.reserve(nP, c->st);
-            CIPC_LAUNCH(k_boxes_ccs, div_up(nP, TB), TB, 0, c->st, T, c->X.p, H.G, r, c->boxLo.p, c->boxHi.p, c->cnt.p);
+            c->boxLo.reserve(nP, c->st); c->boxHi.reserve(nP, c->st); c->cnt.reserve(nP, c->st); c->fine.reserve(nP, c->st);
+            CIPC_LAUNCH(k_boxes_ccs, div_up(nP, TB), TB, 0, c->st, T, c->X.p, H.G, r, c->boxLo.p, c->boxHi.p, c->fine.p, c->cnt.p);
             build_cell_lists(c, H);
         }
         u32 counts[4];
