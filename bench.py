@@ -101,6 +101,7 @@ def run_reference_arm(args):
     from oracle import cipc_oracle as O
     sample, scale = CPU_SAMPLE[args.workload]
     sc = make_scene(sample)
+    O.set_num_threads(os.cpu_count())  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     cores = O.num_threads()
     times = []
     for i in range(args.warmup + args.steps):
@@ -321,6 +322,7 @@ def main():
     cpu = None
     if not args.no_cpu:
         from oracle import cipc_oracle as O
+        O.set_num_threads(os.cpu_count())
         sample, scale = CPU_SAMPLE[args.workload]
         scs = make_scene(sample)
         tcpu, st, nCs = cpu_contact_stage(scs)
