@@ -885,10 +885,14 @@ __global__ void __launch_bounds__(256) k_hessian_expand(const double* __restrict
     cipc_triplet* __restrict__ trip)
 {
     constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, PER = NN * NN;
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const u32 q = (u32)(t / PER);
-    const int e = (int)(t - (u64)q * PER);
+    // one 64-bit division per thread for the block base, everything else in small 32-bit arithmetic
+    const u64 base = (u64)blockIdx.x * 256u;
+    if (base + threadIdx.x >= total) return;
+    const u32 q0 = (u32)(base / PER);
+    const u32 x = (u32)(base - (u64)q0 * PER) + threadIdx.x; // < PER + 256
+    const u32 dq = x / PER;
+    const u32 q = q0 + dq;
+    const int e = (int)(x - dq * PER);
     const int r = e / NN, c = e - r * NN;
     const YHdr h = hdr[q];
     if (h.off == 0xffffffffu) return;
