@@ -689,7 +689,7 @@ __global__ void k_block_sizes(const int4* __restrict__ cs, u32 n, u32* sz)
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int d = block_dim_of(cs[i]);
-    sz[i] = (u32)(d * d);
+    sz[i] = (u32)(d * d / 9); // offsets are kept in units of 9 triplets (144 = 16*9, 81 = 9*9, 36 = 4*9): 32 bits reach 38G triplets
 }
 // Builds the n x n block of one stencil into H (row-major, n = 3*nb), returns nb and vertex ids.
 __device__ void stencil_hessian(const double4* __restrict__ X, const double4* __restrict__ X0, const int4 c, double w,
@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(128) k_hessian_lowrank(const double4* __restri
     const double d = stencil_dist2(X, s) - bp.thickness2;
     const double alpha = wm * barrier_H(bp.elastic, d, bp.dHat2, bp.k0);
     const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
-    cipc_triplet* o = trip + off[i];
+    cipc_triplet* o = trip + (size_t)off[i] * 9;
     constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2);
     constexpr int NN = 3 * NB;
     int vid[4] = {s.v[0], s.v[1], s.v[2], s.v[3]};
@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(256) k_hessian_expand(const double* __restrict
 #pragma unroll
     for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
     const int ri = r / 3, ci = c / 3;
-    put_triplet(trip + (size_t)h.off + e, h.v[ri] * 3 + (r - 3 * ri), h.v[ci] * 3 + (c - 3 * ci), v);
+    put_triplet(trip + (size_t)h.off * 9 + e, h.v[ri] * 3 + (r - 3 * ri), h.v[ci] * 3 + (c - 3 * ci), v);
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 __global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restric
         int vids[4], nb;
         stencil_hessian(X, X0, cs[i], info[i].x, bp, projectSPD != 0, H, vids, nb);
         const int nn = 3 * nb;
-        cipc_triplet* o = trip + off[i];
+        cipc_triplet* o = trip + (size_t)off[i] * 9;
         for (int I = 0; I < nb; ++I)
             for (int a = 0; a < 3; ++a)
                 for (int J = 0; J < nb; ++J)
@@ -932,8 +932,9 @@ __global__ void k_gather_dense(const int4* __restrict__ cs, const u32* __restric
         const u32 i = list[k];
         const int d = block_dim_of(cs[i]);
         const u32 cnt = (u32)(d * d), o = off[i];
+        const size_t o9 = (size_t)o * 9;
         if (threadIdx.x == 0) meta[k] = make_uint2(o, cnt);
-        const int4* src = reinterpret_cast<const int4*>(trip + o);
+        const int4* src = reinterpret_cast<const int4*>(trip + o9);
         int4* out = reinterpret_cast<int4*>(dst + (size_t)k * 144);
         for (u32 t = threadIdx.x; t < cnt; t += blockDim.x) out[t] = src[t];
     }
@@ -1435,7 +1436,7 @@ inline void expand_one_host(const double* y, const YHdr& h, cipc_triplet* out, b
     constexpr int NN = 3 * NB;
     int idx[NN];
     for (int r = 0; r < NN; ++r) idx[r] = h.v[r / 3] * 3 + r % 3;
-    cipc_triplet* o = out + h.off;
+    cipc_triplet* o = out + (size_t)h.off * 9;
     for (int r = 0; r < NN; ++r)
         for (int c = 0; c < NN; ++c) {
             double v = 0.0;
@@ -1534,7 +1535,7 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     if (copyFailed) throw CudaError("device-to-host copy of the Hessian factors failed");
     if (nDense) {
         CIPC_CUDA(cudaStreamSynchronize(c->st));
-        for (u32 k = 0; k < nDense; ++k) memcpy(out + hM[k].x, hD + (size_t)k * 144, (size_t)hM[k].y * sizeof(cipc_triplet));
+        for (u32 k = 0; k < nDense; ++k) memcpy(out + (size_t)hM[k].x * 9, hD + (size_t)k * 144, (size_t)hM[k].y * sizeof(cipc_triplet));
     }
 }
 
@@ -1873,9 +1874,8 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
             u32 tot;
             CIPC_CUDA(cudaMemcpyAsync(&tot, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
             CIPC_CUDA(cudaStreamSynchronize(c->st));
-            if ((u64)c->nC * 144 > 0xffffffffull) return (int)CIPC_ERR_UNSUPPORTED; // 32-bit triplet offsets
-            c->nTrip = tot;
-            c->trip.reserve(tot, c->st);
+            c->nTrip = (int64_t)tot * 9;
+            c->trip.reserve((size_t)c->nTrip, c->st);
             const char* dense = getenv("CIPC_HESSIAN_DENSE"); // cross-check switch: force the dense eigen path for every stencil
             if (dense && dense[0] == '1') {
                 cipc_ctx::Scope sk(c, "k_barrier_hessian");
