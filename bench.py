@@ -250,7 +250,8 @@ def main():
 
         def e2e_step():
             h2d = d2h = 0
-            # Compute_Constraint_Set: X, x0 in; constraintSet, stencilInfo out
+            # Compute_Constraint_Set: topology (content-hashed, re-uploaded only on change), X, x0 in; constraintSet, stencilInfo out
+            ctx.set_topology(nV, sc["BN"], BE4, BT4, 0, sc["codim"], sc["DBC"])
             ctx.set_positions(X4); ctx.set_rest_positions(X04); h2d += 2 * X4.nbytes
             n = ctx.constraint_set(dHat2, xi, fetch=False)
             ctx._ck(ctx.L.cipc_get_constraints(ctx.h, cs_h.ctypes.data_as(C.POINTER(C.c_int32)), info_h.ctypes.data_as(C.POINTER(C.c_double))))
@@ -264,7 +265,8 @@ def main():
             ctx.set_positions(X4); h2d += X4.nbytes
             tr = ctx.barrier_hessian(dHat2, kappa, xi, True, out=trip_h); d2h += len(tr) * 16  # bytes delivered to the host buffer
             pcie[0] = sum(ctx.counter(k) * b for k, b in (("hessian_4pt", 320), ("hessian_pe", 176), ("hessian_pp", 80))) + ctx.counter("hessian_mollified") * 2312
-            # Compute_Intersection_Free_StepSize: X, searchDir in; step out
+            # Compute_Intersection_Free_StepSize: topology check, X, searchDir in; step out
+            ctx.set_topology(nV, sc["BN"], BE4, BT4, 0, sc["codim"], sc["DBC"])
             ctx.set_positions(X4); ctx.set_search_dir(p_h); h2d += X4.nbytes + p_h.nbytes
             a = ctx.step_size(xi, 1.0); d2h += 8
             # Compute_Min_Dist2 x2: X in; dist2, min out

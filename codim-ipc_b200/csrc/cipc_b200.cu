@@ -1160,14 +1160,24 @@ int guarded(cipc_ctx* ctx, F f)
     }
 }
 
+// change detector for the topology arrays: four independent multiply-xorshift lanes over 32-byte strides
+// (memory-bandwidth bound, ~10 GB/s per core); not a cryptographic hash
 u64 fnv(const void* p, size_t n, u64 h)
 {
     const unsigned char* c = (const unsigned char*)p;
-    // 8 bytes at a time is enough for a change detector
+    u64 a = h ^ 0x9E3779B97F4A7C15ULL, b = h + 0xC2B2AE3D27D4EB4FULL, d = ~h, e = h * 0x100000001b3ULL;
     size_t i = 0;
-    for (; i + 8 <= n; i += 8) { u64 w; memcpy(&w, c + i, 8); h = (h ^ w) * 0x100000001b3ULL; h ^= h >> 29; }
+    for (; i + 32 <= n; i += 32) {
+        u64 w[4];
+        memcpy(w, c + i, 32);
+        a = (a ^ w[0]) * 0x100000001b3ULL; a ^= a >> 29;
+        b = (b ^ w[1]) * 0x9FB21C651E98DF25ULL; b ^= b >> 31;
+        d = (d ^ w[2]) * 0xD6E8FEB86659FD93ULL; d ^= d >> 32;
+        e = (e ^ w[3]) * 0xFF51AFD7ED558CCDULL; e ^= e >> 33;
+    }
+    h = a ^ (b * 3) ^ (d * 5) ^ (e * 7);
     for (; i < n; ++i) h = (h ^ c[i]) * 0x100000001b3ULL;
-    return h;
+    return h ^ (h >> 29) ^ (u64)n;
 }
 
 void upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int stride_bytes)
