@@ -245,7 +245,11 @@ def main():
         trip_raw = torch.empty((nT_cap, 2), dtype=torch.float64).pin_memory().numpy()
         trip_h = trip_raw.view(cipc.TRIPLET_DTYPE).reshape(-1)
         import ctypes as C
-
+        # the reference's containers: VECTOR<int,2|3> are 16-byte records (stride 4 ints)
+        BE4 = np.zeros((len(sc["BE"]), 4), np.int32); BE4[:, :2] = sc["BE"]
+        BT4 = np.zeros((len(sc["BT"]), 4), np.int32); BT4[:, :3] = sc["BT"]
+        ctx.set_topology(nV, sc["BN"], BE4, BT4, 0, sc["codim"], sc["DBC"])
+        ctx.set_positions(X4); ctx.set_rest_positions(X04); ctx.set_search_dir(p_h)
         pcie = [0]
 
         def e2e_step():
