@@ -1439,24 +1439,36 @@ void expand_on_device(cipc_ctx* c)
     if (nk[2]) CIPC_LAUNCH(k_hessian_expand<2>, div_up((u64)nk[2] * 36, 256), 256, 0, c->st, c->Y2, (const YHdr*)c->h2, (u64)nk[2] * 36, c->trip.p);
     c->expanded = true;
 }
-// host side: y y^T expansion of one stencil with streaming 16-byte stores (the destination is never read back)
+// host side: y y^T expansion of one stencil with streaming 16-byte stores (the destination is never read back).
+// Values of one row are formed two at a time in SSE registers; (row, col) pairs are pre-packed per stencil.
 template <int NB, int NY>
 inline void expand_one_host(const double* y, const YHdr& h, cipc_triplet* out, bool aligned)
 {
-    constexpr int NN = 3 * NB;
-    int idx[NN];
-    for (int r = 0; r < NN; ++r) idx[r] = h.v[r / 3] * 3 + r % 3;
-    cipc_triplet* o = out + (size_t)h.off * 9;
-    for (int r = 0; r < NN; ++r)
-        for (int c = 0; c < NN; ++c) {
-            double v = 0.0;
-            for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
-            long long vb;
-            memcpy(&vb, &v, 8);
-            const __m128i q = _mm_set_epi64x(vb, (long long)(((unsigned long long)(unsigned)idx[c] << 32) | (unsigned)idx[r]));
-            if (aligned) _mm_stream_si128(reinterpret_cast<__m128i*>(o + r * NN + c), q);
-            else _mm_storeu_si128(reinterpret_cast<__m128i*>(o + r * NN + c), q);
+    constexpr int NN = 3 * NB, NP = (NN + 1) / 2 * 2;
+    unsigned idx[NP];
+    for (int r = 0; r < NN; ++r) idx[r] = (unsigned)(h.v[r / 3] * 3 + r % 3);
+    double yy[NY][NP];
+    for (int k = 0; k < NY; ++k) {
+        for (int c = 0; c < NN; ++c) yy[k][c] = y[k * NN + c];
+        for (int c = NN; c < NP; ++c) yy[k][c] = 0.0;
+    }
+    __m128i* o = reinterpret_cast<__m128i*>(out + (size_t)h.off * 9);
+    for (int r = 0; r < NN; ++r) {
+        const long long rr = (long long)idx[r];
+        __m128d yr[NY];
+        for (int k = 0; k < NY; ++k) yr[k] = _mm_set1_pd(yy[k][r]);
+        for (int c = 0; c < NN; c += 2) {
+            __m128d v = _mm_mul_pd(yr[0], _mm_loadu_pd(&yy[0][c]));
+            for (int k = 1; k < NY; ++k) v = _mm_add_pd(v, _mm_mul_pd(yr[k], _mm_loadu_pd(&yy[k][c])));
+            const __m128i vi = _mm_castpd_si128(v);
+            const __m128i t0 = _mm_unpacklo_epi64(_mm_cvtsi64_si128(((long long)idx[c] << 32) | rr), vi);
+            if (aligned) _mm_stream_si128(o + r * NN + c, t0); else _mm_storeu_si128(o + r * NN + c, t0);
+            if (c + 1 < NN) {
+                const __m128i t1 = _mm_unpacklo_epi64(_mm_cvtsi64_si128(((long long)idx[c + 1] << 32) | rr), _mm_unpackhi_epi64(vi, vi));
+                if (aligned) _mm_stream_si128(o + r * NN + c + 1, t1); else _mm_storeu_si128(o + r * NN + c + 1, t1);
+            }
         }
+    }
 }
 // Delivers the triplets of the last projected Hessian to host memory: ships the compact factors (8x fewer
 // bytes over PCIe than the triplet stream) and expands them with all host threads.
