@@ -238,8 +238,34 @@ __global__ void k_prim_boxes_ccd(Topo T, const u64* __restrict__ nodeLo, const u
     cnt[g] = (u32)(h[0] - l[0] + 1) * (u32)(h[1] - l[1] + 1) * (u32)(h[2] - l[2] + 1);
 }
 // one (cell<<2|kind, local id) entry per covered voxel
+// Multi-GPU: a rank owns a slab [s0, s1) of voxel indices along `axis`; only entries inside it are emitted and sorted.
+struct Slab {
+    int axis, s0, s1;
+};
+__device__ __forceinline__ int uax(u64 p, int axis) { return axis == 0 ? ux(p) : (axis == 1 ? uy(p) : uz(p)); }
+// entries per voxel layer along the slab axis (summed over all primitives): the host balances slabs on it
+__global__ void k_slab_hist(int nP, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, int axis, u32* hist)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nP) return;
+    const u64 a = boxLo[g], b = boxHi[g];
+    const u32 ex[3] = {(u32)(ux(b) - ux(a) + 1), (u32)(uy(b) - uy(a) + 1), (u32)(uz(b) - uz(a) + 1)};
+    const u32 per = (axis == 0) ? ex[1] * ex[2] : (axis == 1 ? ex[0] * ex[2] : ex[0] * ex[1]);
+    for (int i = uax(a, axis); i <= uax(b, axis); ++i) atomicAdd(&hist[i], per);
+}
+__global__ void k_clip_counts(int nP, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, Slab sl, u32* cnt)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nP) return;
+    const u64 a = boxLo[g], b = boxHi[g];
+    int l[3] = {ux(a), uy(a), uz(a)}, h[3] = {ux(b), uy(b), uz(b)};
+    l[sl.axis] = max(l[sl.axis], sl.s0);
+    h[sl.axis] = min(h[sl.axis], sl.s1 - 1);
+    cnt[g] = (h[sl.axis] < l[sl.axis]) ? 0u : (u32)(h[0] - l[0] + 1) * (u32)(h[1] - l[1] + 1) * (u32)(h[2] - l[2] + 1);
+}
+// one (cell<<2|kind, local id) entry per covered voxel (inside the rank's slab)
 __global__ void k_emit_entries(Topo T, GridDesc G, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi,
-    const u32* __restrict__ off, u32* keys, u32* vals)
+    const u32* __restrict__ off, Slab sl, u32* keys, u32* vals)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int nP = T.nBN + T.nBE + T.nBT;
@@ -249,10 +275,13 @@ __global__ void k_emit_entries(Topo T, GridDesc G, const u64* __restrict__ boxLo
     else if (g < T.nBN + T.nBE) { kind = 1; id = g - T.nBN; }
     else { kind = 2; id = g - T.nBN - T.nBE; }
     const u64 a = boxLo[g], b = boxHi[g];
+    int l[3] = {ux(a), uy(a), uz(a)}, h[3] = {ux(b), uy(b), uz(b)};
+    l[sl.axis] = max(l[sl.axis], sl.s0);
+    h[sl.axis] = min(h[sl.axis], sl.s1 - 1);
     u32 o = off[g];
-    for (int iz = uz(a); iz <= uz(b); ++iz)
-        for (int iy = uy(a); iy <= uy(b); ++iy)
-            for (int ix = ux(a); ix <= ux(b); ++ix) {
+    for (int iz = l[2]; iz <= h[2]; ++iz)
+        for (int iy = l[1]; iy <= h[1]; ++iy)
+            for (int ix = l[0]; ix <= h[0]; ++ix) {
                 const u32 cell = (u32)ix + (u32)G.gx * ((u32)iy + (u32)G.gy * (u32)iz);
                 keys[o] = (cell << 2) | kind;
                 vals[o] = id;
@@ -1078,6 +1107,7 @@ struct cipc_ctx {
     // hash
     DevBuf<u64> boxLo, boxHi, nodeLo, nodeHi;
     DevBuf<ulonglong2> fine, nodeFine;
+    DevBuf<u32> slabHist;
     DevBuf<u32> cnt, keys, vals, heads, headScan, ks;
     SortWork sortwk;
     ScanWork scanwk;
@@ -1237,6 +1267,32 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
 {
     const Topo& T = c->T;
     const int nP = T.nBN + T.nBE + T.nBT;
+    Slab sl{0, 0, 1 << 30};
+    if (c->world > 1) {
+        // this rank's slab along the axis with the most voxel layers, balanced on the number of hash entries
+        const int gd[3] = {H.G.gx, H.G.gy, H.G.gz};
+        sl.axis = (gd[0] >= gd[1] && gd[0] >= gd[2]) ? 0 : (gd[1] >= gd[2] ? 1 : 2);
+        const int nl = gd[sl.axis];
+        c->slabHist.reserve(nl, c->st);
+        CIPC_CUDA(cudaMemsetAsync(c->slabHist.p, 0, (size_t)nl * 4, c->st));
+        CIPC_LAUNCH(k_slab_hist, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl.axis, c->slabHist.p);
+        std::vector<u32> hist(nl);
+        CIPC_CUDA(cudaMemcpyAsync(hist.data(), c->slabHist.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        double total = 0;
+        for (u32 v : hist) total += v;
+        auto bound = [&](int r) { // first layer whose prefix reaches total * r / world
+            if (r <= 0) return 0;
+            if (r >= c->world) return nl;
+            const double target = total * r / c->world;
+            double acc = 0;
+            for (int i = 0; i < nl; ++i) { acc += hist[i]; if (acc >= target) return i + 1; }
+            return nl;
+        };
+        sl.s0 = bound(c->rank);
+        sl.s1 = bound(c->rank + 1);
+        CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
+    }
     device_excl_scan(c->cnt.p, c->cnt.p, nP, c->scanwk, c->st);
     u32 nE;
     CIPC_CUDA(cudaMemcpyAsync(&nE, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
@@ -1244,7 +1300,7 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
     H.nEntries = nE;
     c->keys.reserve(nE, c->st); c->vals.reserve(nE, c->st); c->heads.reserve(nE, c->st); c->headScan.reserve(nE, c->st);
     if (nE == 0) { H.nCells = 0; return; }
-    CIPC_LAUNCH(k_emit_entries, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, c->cnt.p, c->keys.p, c->vals.p);
+    CIPC_LAUNCH(k_emit_entries, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, c->cnt.p, sl, c->keys.p, c->vals.p);
     const double cells = (double)H.G.gx * H.G.gy * H.G.gz;
     int bits = 2;
     while ((double)(1ULL << (bits - 2)) < cells) ++bits;
@@ -1286,9 +1342,8 @@ bool size_grid(const double* mn, const double* mx, double voxelSize, GridDesc& G
 template <bool CCD>
 void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
 {
-    // this rank's share: a contiguous range of voxel cells of the sorted hash
-    const u32 nCells = H.nCells;
-    const u32 e0 = (u32)((u64)nCells * c->rank / c->world), e1 = (u32)((u64)nCells * (c->rank + 1) / c->world);
+    // the hash only holds this rank's slab of voxels (build_cell_lists), so every local cell is processed here
+    const u32 e0 = 0, e1 = H.nCells;
     for (int k = 0; k < 4; ++k) counts[k] = 0;
     if (e1 <= e0) return;
     for (int attempt = 0; attempt < 3; ++attempt) {

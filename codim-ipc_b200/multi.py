@@ -1,9 +1,9 @@
 """Multi-GPU glue for the contact path: one process per GPU, `torch.distributed` for the plumbing.
 
 Partitioning: positions, rest positions, search direction and the primitive
-lists are replicated; every rank builds the full cell-sorted hash and enumerates candidate pairs only
-for its contiguous slice of the sorted hash entries (= a contiguous range of voxel cells).  Pairs
-are therefore disjoint across ranks and their union is the single-GPU candidate set.  The only
+lists are replicated; every rank owns a slab of voxel layers (balanced on the number of hash entries),
+builds the cell-sorted hash of that slab only and enumerates the candidate pairs whose min-corner voxel
+lies in it.  Pairs are therefore disjoint across ranks and their union is the single-GPU candidate set.  The only
 exchanges the path needs are
 
     step size        all-reduce(min) of one f64                 (IPC.h:2166,2241: min over all pairs)
