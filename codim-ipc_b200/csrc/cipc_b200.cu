@@ -753,11 +753,7 @@ __device__ void stencil_hessian(const double4* __restrict__ X, const double4* __
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) H[i * n + j] += q * dg[i] * dg[j];
         for (int k = 0; k < nb; ++k) vids[k] = s.v[k];
-        if (projectSPD) {
-            if (nb == 4) psd_project_jacobi<12>(H);
-            else if (nb == 3) psd_project_jacobi<9>(H);
-            else psd_project_jacobi<6>(H);
-        }
+        (void)projectSPD; // the caller projects (shared-memory Jacobi on the translation-reduced block)
         return;
     }
     // mollified stencils: 12 x 12 in the (ea0, ea1, eb0, eb1) frame (IPC.h:1472-1475, 1526-1537, 1588-1599)
@@ -799,7 +795,6 @@ __device__ void stencil_hessian(const double4* __restrict__ X, const double4* __
     for (int i = 0; i < 12; ++i)
         for (int j = 0; j < 12; ++j)
             H[i * 12 + j] += w * (bG * (G[i] * eg[j] + eg[i] * G[j]) + (e * bH) * G[i] * G[j]);
-    if (projectSPD) psd_project_jacobi<12>(H);
 }
 // class of a stencil for the Hessian pass: 0 = PT / EE, 1 = PE, 2 = PP (low-rank fast paths), 3 = mollified (dense path)
 __global__ void k_classify(const int4* __restrict__ cs, u32 n, u32* idx0, u32* idx1, u32* idx2, u32* idx3, u32* counts)
@@ -933,16 +928,20 @@ __global__ void __launch_bounds__(256) k_hessian_expand(const double* __restrict
     put_triplet(trip + (size_t)h.off * 9 + e, h.v[ri] * 3 + (r - 3 * ri), h.v[ci] * 3 + (c - 3 * ci), v);
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
-__global__ void __launch_bounds__(64) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
+constexpr int DENSE_BD = 64;                              // threads per block of the dense path
+constexpr int DENSE_SMEM = 2 * 81 * DENSE_BD * 8;         // 9x9 matrix + eigenvectors per thread
+__global__ void __launch_bounds__(DENSE_BD) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
     const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
     const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip)
 {
+    extern __shared__ double dense_sm[];
     if (nDev) n = *nDev; // list length produced on the device (fallbacks of the factor kernels)
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const u32 i = idx ? idx[k] : k;
         double H[144];
         int vids[4], nb;
-        stencil_hessian(X, X0, cs[i], info[i].x, bp, projectSPD != 0, H, vids, nb);
+        stencil_hessian(X, X0, cs[i], info[i].x, bp, false, H, vids, nb);
+        if (projectSPD) psd_project_reduced_smem(H, nb, dense_sm, threadIdx.x, DENSE_BD);
         const int nn = 3 * nb;
         cipc_triplet* o = trip + (size_t)off[i] * 9;
         for (int I = 0; I < nb; ++I)
@@ -1643,6 +1642,7 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
         c->counters.reserve(16, c->st);
         c->errFlag.reserve(1, c->st);
         CIPC_CUDA(cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->st));
+        CIPC_CUDA(cudaFuncSetAttribute(k_barrier_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
     }
     catch (const std::exception& e) {
@@ -1956,7 +1956,7 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
             const char* dense = getenv("CIPC_HESSIAN_DENSE"); // cross-check switch: force the dense eigen path for every stencil
             if (dense && dense[0] == '1') {
                 cipc_ctx::Scope sk(c, "k_barrier_hessian");
-                CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, DENSE_BD), DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
                     (const u32*)nullptr, c->nC, (const u32*)nullptr, bp, projectSPD, c->trip.p);
             }
             else {
@@ -1989,7 +1989,7 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
                     c->Y0 = Y0; c->Y1 = Y1; c->Y2 = Y2; c->h0 = h0; c->h1 = h1; c->h2 = h2;
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
                     // mollified stencils + rejected ones: dense eigen path, list length read on the device
-                    CIPC_LAUNCH(k_barrier_hessian, 592, 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
+                    CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
                         (const u32*)dn, bp, projectSPD, c->trip.p);
                 }
                 else {
@@ -2000,7 +2000,7 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
                         c->clsIdx[1].p, nk[1], bp, projectSPD, c->trip.p);
                     if (nk[2]) CIPC_LAUNCH(k_hessian_lowrank<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
                         c->clsIdx[2].p, nk[2], bp, projectSPD, c->trip.p);
-                    if (nk[3]) CIPC_LAUNCH(k_barrier_hessian, div_up(nk[3], 64), 64, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                    if (nk[3]) CIPC_LAUNCH(k_barrier_hessian, div_up(nk[3], DENSE_BD), DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
                         c->clsIdx[3].p, nk[3], (const u32*)nullptr, bp, projectSPD, c->trip.p);
                 }
                 c->ctr["hessian_4pt"] = nk[0]; c->ctr["hessian_pe"] = nk[1]; c->ctr["hessian_pp"] = nk[2]; c->ctr["hessian_mollified"] = nk[3];

@@ -68,4 +68,97 @@ CIPC_HD void psd_project_jacobi(double* A)
         }
 }
 
+
+#if defined(__CUDACC__)
+// Dense fallback used on the device for stencils without a low-rank fast path (mollified stencils, stencils
+// outside the barrier's support).  Every block annihilates rigid translations (H t = 0 for t = (c,c,..,c)), so it
+// is first compressed with an orthonormal Helmert basis Q of the translation-free subspace:  M = Q H Q^T is
+// (N-3) x (N-3), H+ = Q^T M+ Q.  The cyclic Jacobi iteration then runs on M with matrix and eigenvectors held in
+// SHARED memory, element (i,j) of thread t at sm[(i*K+j)*BD + t] (bank-conflict free), instead of thread-local
+// arrays that spill to L1/L2.  H: N x N row-major (N = 3*nb) in local memory, replaced by its PSD projection.
+__device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, int tid, int BD)
+{
+    const int N = 3 * nb, K = N - 3;
+    double* A = sm;                 // K*K
+    double* V = sm + 81 * BD;       // K*K (capacity 81 each)
+#define SA(i, j) A[((i) * K + (j)) * BD + tid]
+#define SV(i, j) V[((i) * K + (j)) * BD + tid]
+    // Helmert rows h_k (k = 1..nb-1): k entries 1/sqrt(k(k+1)), then -k/sqrt(k(k+1)), then zeros
+    double hc[3], hd[3];
+    for (int k = 1; k < nb; ++k) { const double s = 1.0 / sqrt((double)(k * (k + 1))); hc[k - 1] = s; hd[k - 1] = -k * s; }
+    auto helm = [&](int k, int I) { return I < k + 1 ? hc[k] : (I == k + 1 ? hd[k] : 0.0); }; // k = 0..nb-2
+    double fro = 0.0;
+    for (int k = 0; k < nb - 1; ++k)
+        for (int a = 0; a < 3; ++a)
+            for (int l = 0; l < nb - 1; ++l)
+                for (int b = 0; b < 3; ++b) {
+                    double s = 0.0;
+                    for (int I = 0; I <= k + 1; ++I) {
+                        const double hI = helm(k, I);
+                        for (int J = 0; J <= l + 1; ++J) s += hI * helm(l, J) * H[(3 * I + a) * N + 3 * J + b];
+                    }
+                    SA(3 * k + a, 3 * l + b) = s;
+                    SV(3 * k + a, 3 * l + b) = (k == l && a == b) ? 1.0 : 0.0;
+                    fro += s * s;
+                }
+    if (fro > 0.0) {
+        const double tol = 1e-28 * fro;
+        for (int sweep = 0; sweep < 14; ++sweep) {
+            double off = 0.0;
+            for (int p = 0; p < K; ++p)
+                for (int q = p + 1; q < K; ++q) { const double v = SA(p, q); off += v * v; }
+            if (off <= tol) break;
+            for (int p = 0; p < K - 1; ++p)
+                for (int q = p + 1; q < K; ++q) {
+                    const double apq = SA(p, q);
+                    if (apq * apq <= 1e-36 * fro) continue;
+                    const double app = SA(p, p), aqq = SA(q, q);
+                    const double theta = (aqq - app) / (2.0 * apq);
+                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double c = rsqrt(t * t + 1.0), s = t * c;
+                    for (int k = 0; k < K; ++k) {
+                        if (k != p && k != q) {
+                            const double akp = SA(k, p), akq = SA(k, q);
+                            const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+                            SA(k, p) = np_; SA(p, k) = np_;
+                            SA(k, q) = nq_; SA(q, k) = nq_;
+                        }
+                        const double vkp = SV(k, p), vkq = SV(k, q);
+                        SV(k, p) = c * vkp - s * vkq;
+                        SV(k, q) = s * vkp + c * vkq;
+                    }
+                    SA(p, p) = app - t * apq;
+                    SA(q, q) = aqq + t * apq;
+                    SA(p, q) = 0.0;
+                    SA(q, p) = 0.0;
+                }
+        }
+    }
+    // M+ = sum_{lambda>0} lambda v v^T, kept in A (upper part recomputed fully)
+    double lam[9];
+    for (int i = 0; i < K; ++i) { const double l = SA(i, i); lam[i] = l > 0.0 ? l : 0.0; }
+    for (int i = 0; i < K; ++i)
+        for (int j = i; j < K; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) s += lam[k] * SV(i, k) * SV(j, k);
+            SA(i, j) = s;
+            SA(j, i) = s;
+        }
+    // H+ = Q^T M+ Q
+    for (int I = 0; I < nb; ++I)
+        for (int a = 0; a < 3; ++a)
+            for (int J = 0; J < nb; ++J)
+                for (int b = 0; b < 3; ++b) {
+                    double s = 0.0;
+                    for (int k = (I > 0 ? I - 1 : 0); k < nb - 1; ++k) {
+                        const double hI = helm(k, I);
+                        for (int l = (J > 0 ? J - 1 : 0); l < nb - 1; ++l) s += hI * helm(l, J) * SA(3 * k + a, 3 * l + b);
+                    }
+                    H[(3 * I + a) * N + 3 * J + b] = s;
+                }
+#undef SA
+#undef SV
+}
+#endif
+
 } // namespace cipc
