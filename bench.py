@@ -252,37 +252,51 @@ def main():
         ctx.set_positions(X4); ctx.set_rest_positions(X04); ctx.set_search_dir(p_h)
         pcie = [0]
 
+        calls = {}
+
+        def tick(name, t0):
+            calls[name] = calls.get(name, 0.0) + (time.perf_counter() - t0)
+            return time.perf_counter()
+
         def e2e_step():
             h2d = d2h = 0
+            t0 = time.perf_counter()
             # Compute_Constraint_Set: topology (content-hashed, re-uploaded only on change), X, x0 in; constraintSet, stencilInfo out
             ctx.set_topology(nV, sc["BN"], BE4, BT4, 0, sc["codim"], sc["DBC"])
             ctx.set_positions(X4); ctx.set_rest_positions(X04); h2d += 2 * X4.nbytes
             n = ctx.constraint_set(dHat2, xi, fetch=False)
             ctx._ck(ctx.L.cipc_get_constraints(ctx.h, cs_h.ctypes.data_as(C.POINTER(C.c_int32)), info_h.ctypes.data_as(C.POINTER(C.c_double))))
             d2h += n * 32
+            t0 = tick("Compute_Constraint_Set", t0)
             # Compute_Barrier / _Gradient / _Hessian: X in (the shim keeps the constraint set it just produced resident)
             ctx.set_positions(X4); h2d += X4.nbytes
             E = ctx.barrier_energy(dHat2, kappa, xi, 0.0); d2h += 8
+            t0 = tick("Compute_Barrier", t0)
             ctx.set_positions(X4); h2d += X4.nbytes
             g_h[:] = 0
             ctx.barrier_gradient(dHat2, kappa, xi, g_h); d2h += nV * 24
+            t0 = tick("Compute_Barrier_Gradient", t0)
             ctx.set_positions(X4); h2d += X4.nbytes
             tr = ctx.barrier_hessian(dHat2, kappa, xi, True, out=trip_h); d2h += len(tr) * 16  # bytes delivered to the host buffer
             pcie[0] = sum(ctx.counter(k) * b for k, b in (("hessian_4pt", 320), ("hessian_pe", 176), ("hessian_pp", 80))) + ctx.counter("hessian_mollified") * 2312
+            t0 = tick("Compute_Barrier_Hessian", t0)
             # Compute_Intersection_Free_StepSize: topology check, X, searchDir in; step out
             ctx.set_topology(nV, sc["BN"], BE4, BT4, 0, sc["codim"], sc["DBC"])
             ctx.set_positions(X4); ctx.set_search_dir(p_h); h2d += X4.nbytes + p_h.nbytes
             a = ctx.step_size(xi, 1.0); d2h += 8
+            t0 = tick("Compute_Intersection_Free_StepSize", t0)
             # Compute_Min_Dist2 x2: X in; dist2, min out
             for _ in range(2):
                 ctx.set_positions(X4); h2d += X4.nbytes
                 m = C.c_double(0)
                 ctx._ck(ctx.L.cipc_min_dist2(ctx.h, C.c_double(xi), d_h.ctypes.data_as(C.POINTER(C.c_double)), C.byref(m))); d2h += n * 8 + 8
+            t0 = tick("Compute_Min_Dist2_x2", t0)
             return h2d, d2h, (E, a, m.value)
 
         for _ in range(max(1, args.warmup - 1)):
             e2e_step()
         sync_all()
+        calls.clear()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             h2d, d2h, res = e2e_step()
@@ -293,7 +307,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": float(t.item()), "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "note": "d2h = bytes delivered into host buffers; the Hessian triplets (%d B) cross PCIe as %d B of factors and are expanded "
-                       "by the host cores inside cipc_get_triplets" % (len(trip_h[:nTrip]) * 16, pcie[0])}
+                       "by the host cores inside cipc_get_triplets" % (len(trip_h[:nTrip]) * 16, pcie[0]),
+               "calls_ms": {k: round(1e3 * v / args.steps, 3) for k, v in calls.items()}}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
