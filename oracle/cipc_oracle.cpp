@@ -939,6 +939,226 @@ static void compute_min_dist2(const Scene& s, const std::vector<I4>& cs, double 
     minDist2 -= thickness * thickness;
 }
 
+// ======================================================================= friction (FEM/FRICTION.h, FEM/FRICTION_UTILS.h)
+// SURVEY 8(f)-1.  Lagged friction on the non-mollified part of the contact constraint set.
+struct FrictionSet {
+    std::vector<I4> cs;
+    std::vector<std::array<double, 2>> closest;   // closestPoint (beta / gamma / yita)
+    std::vector<std::array<double, 6>> basis;     // tanBasis, column-major 3x2: col0 xyz, col1 xyz
+    std::vector<double> normalForce;
+};
+static inline V3 normalized(const V3& a) // Eigen::normalized(): v / sqrt(squaredNorm) when the norm is positive
+{
+    const double z = norm2(a);
+    return z > 0 ? a / std::sqrt(z) : a;
+}
+// FRICTION_UTILS.h:10-39
+static inline double f0_SF(double x2, double epsvh)
+{
+    if (x2 >= epsvh * epsvh) return std::sqrt(x2);
+    return x2 * (-std::sqrt(x2) / 3.0 + epsvh) / (epsvh * epsvh) + epsvh / 3.0;
+}
+static inline double f1_SF_div(double x2, double epsvh)
+{
+    if (x2 >= epsvh * epsvh) return 1 / std::sqrt(x2);
+    return (-std::sqrt(x2) + 2.0 * epsvh) / (epsvh * epsvh);
+}
+static inline double f2_SF_term(double, double epsvh) { return -1 / (epsvh * epsvh); }
+static inline void set_basis(std::array<double, 6>& B, const V3& c0, const V3& c1)
+{
+    B = {c0.x, c0.y, c0.z, c1.x, c1.y, c1.z};
+}
+// FRICTION_UTILS.h:41-52, 107-118, 184-194, 229-245
+static inline void pt_tangent_basis(const V3&, const V3& v1, const V3& v2, const V3& v3, std::array<double, 6>& B)
+{
+    const V3 v12 = v2 - v1;
+    set_basis(B, normalized(v12), normalized(cross(cross(v12, v3 - v1), v12)));
+}
+static inline void ee_tangent_basis(const V3& v0, const V3& v1, const V3& v2, const V3& v3, std::array<double, 6>& B)
+{
+    const V3 v01 = v1 - v0;
+    set_basis(B, normalized(v01), normalized(cross(cross(v01, v3 - v2), v01)));
+}
+static inline void pe_tangent_basis(const V3& v0, const V3& v1, const V3& v2, std::array<double, 6>& B)
+{
+    const V3 v12 = v2 - v1;
+    set_basis(B, normalized(v12), normalized(cross(v12, v0 - v1)));
+}
+static inline void pp_tangent_basis(const V3& v0, const V3& v1, std::array<double, 6>& B)
+{
+    const V3 v01 = v1 - v0;
+    const V3 xC = cross(V3(1, 0, 0), v01), yC = cross(V3(0, 1, 0), v01);
+    if (norm2(xC) > norm2(yC)) set_basis(B, normalized(xC), normalized(cross(v01, xC)));
+    else set_basis(B, normalized(yC), normalized(cross(v01, yC)));
+}
+// FRICTION_UTILS.h:54-66, 120-142, 196-204
+static inline void pt_closest_point(const V3& v0, const V3& v1, const V3& v2, const V3& v3, double& b1, double& b2)
+{
+    const V3 r0 = v2 - v1, r1 = v3 - v1, rel = v0 - v1;
+    ldlt2_solve(dot(r0, r0), dot(r1, r0), dot(r1, r1), dot(r0, rel), dot(r1, rel), b1, b2);
+}
+static inline void ee_closest_point(const V3& v0, const V3& v1, const V3& v2, const V3& v3, double& g1, double& g2)
+{
+    const V3 e20 = v0 - v2, e01 = v1 - v0, e23 = v3 - v2;
+    ldlt2_solve(norm2(e01), -dot(e23, e01), norm2(e23), -dot(e20, e01), dot(e20, e23), g1, g2);
+}
+static inline double pe_closest_point(const V3& v0, const V3& v1, const V3& v2)
+{
+    const V3 e12 = v2 - v1;
+    return dot(v0 - v1, e12) / norm2(e12);
+}
+// vertex coefficients of the relative displacement u = sum_k coef_k dx_k (FRICTION_UTILS.h: *_RelDX / *_TT)
+static inline int friction_coefs(const I4& c, const std::array<double, 2>& cp, int* v, double* coef, int& mult)
+{
+    mult = 1;
+    if (c[0] >= 0) { // EE
+        v[0] = c[0]; v[1] = c[1]; v[2] = c[2]; v[3] = c[3];
+        coef[0] = 1.0 - cp[0]; coef[1] = cp[0]; coef[2] = cp[1] - 1.0; coef[3] = -cp[1];
+        return 4;
+    }
+    v[0] = -c[0] - 1; v[1] = c[1]; v[2] = c[2]; v[3] = c[3];
+    if (c[2] < 0) { coef[0] = 1.0; coef[1] = -1.0; mult = -c[3]; return 2; }                                   // PP
+    if (c[3] < 0) { coef[0] = 1.0; coef[1] = cp[0] - 1.0; coef[2] = -cp[0]; mult = -c[3]; return 3; }          // PE
+    coef[0] = 1.0; coef[1] = -1.0 + cp[0] + cp[1]; coef[2] = -cp[0]; coef[3] = -cp[1];                         // PT
+    return 4;
+}
+// FRICTION.h:16-124
+static void compute_friction_basis(const Scene& s, bool elastic, const std::vector<I4>& contactCs, const std::vector<D2>& info,
+    double dHat2, const double* kappa, double thickness, FrictionSet& F)
+{
+    if (elastic) thickness = 0;
+    const double thickness2 = thickness * thickness;
+    dHat2 += 2 * std::sqrt(dHat2) * thickness;
+    F.cs.clear();
+    for (const auto& c : contactCs)
+        if (!(c[0] >= 0 && (c[2] < 0 || c[3] < 0))) F.cs.push_back(c);
+    const size_t n = F.cs.size();
+    F.closest.assign(n, {0.0, 0.0});
+    F.basis.resize(n);
+    F.normalForce.resize(n);
+    for (size_t cI = 0; cI < n; ++cI) {
+        const I4& c = F.cs[cI];
+        double dist2;
+        if (c[0] >= 0) {
+            const V3 a0 = s.x(c[0]), a1 = s.x(c[1]), b0 = s.x(c[2]), b1 = s.x(c[3]);
+            ee_closest_point(a0, a1, b0, b1, F.closest[cI][0], F.closest[cI][1]);
+            ee_tangent_basis(a0, a1, b0, b1, F.basis[cI]);
+            dist2 = ee_dist2(a0, a1, b0, b1);
+        }
+        else {
+            const V3 p = s.x(-c[0] - 1);
+            if (c[2] < 0) { pp_tangent_basis(p, s.x(c[1]), F.basis[cI]); dist2 = pp_dist2(p, s.x(c[1])); }
+            else if (c[3] < 0) {
+                F.closest[cI][0] = pe_closest_point(p, s.x(c[1]), s.x(c[2]));
+                pe_tangent_basis(p, s.x(c[1]), s.x(c[2]), F.basis[cI]);
+                dist2 = pe_dist2(p, s.x(c[1]), s.x(c[2]));
+            }
+            else {
+                pt_closest_point(p, s.x(c[1]), s.x(c[2]), s.x(c[3]), F.closest[cI][0], F.closest[cI][1]);
+                pt_tangent_basis(p, s.x(c[1]), s.x(c[2]), s.x(c[3]), F.basis[cI]);
+                dist2 = pt_dist2(p, s.x(c[1]), s.x(c[2]), s.x(c[3]));
+            }
+        }
+        const double bGrad = barrier_gradient(elastic, dist2 - thickness2, dHat2, kappa);
+        // the reference indexes stencilInfo with the FILTERED index (FRICTION.h:112); weights are 1 when !elasticIPC
+        F.normalForce[cI] = -bGrad * 2 * std::sqrt(dist2) * info[cI][0];
+    }
+}
+// FRICTION.h:126-170
+static void compute_friction_coef(const std::vector<I4>& cs, const std::vector<int>& compNodeRange, const std::vector<double>& muComp,
+    std::vector<double>& normalForce, double& mu)
+{
+    mu = 1;
+    auto comp = [&](int v) {
+        for (size_t k = 0; k < compNodeRange.size(); ++k) if (v < compNodeRange[k]) return (int)k;
+        return -1;
+    };
+#pragma omp parallel for schedule(static)
+    for (long cI = 0; cI < (long)cs.size(); ++cI) {
+        const I4& c = cs[cI];
+        const int c0 = comp(c[0] >= 0 ? c[0] : -c[0] - 1), c1 = comp(c[0] >= 0 ? c[2] : c[1]);
+        normalForce[cI] *= muComp[c0 + c1 * compNodeRange.size()];
+    }
+}
+static inline void friction_rel(const Scene& s, const double* Xn, const FrictionSet& F, size_t cI, int* v, double* coef, int& nb, int& mult,
+    double* u2, V3& rel3)
+{
+    nb = friction_coefs(F.cs[cI], F.closest[cI], v, coef, mult);
+    rel3 = V3(0, 0, 0);
+    for (int k = 0; k < nb; ++k) rel3 = rel3 + coef[k] * (s.x(v[k]) - V3(Xn + 3 * v[k]));
+    const auto& B = F.basis[cI];
+    u2[0] = dot(V3(B[0], B[1], B[2]), rel3);
+    u2[1] = dot(V3(B[3], B[4], B[5]), rel3);
+}
+// FRICTION.h:172-252
+static void compute_friction_potential(const Scene& s, const double* Xn, const FrictionSet& F, double epsvh2, double mu, double& E)
+{
+    const double epsvh = std::sqrt(epsvh2);
+    std::vector<double> EI(F.cs.size());
+    for (size_t cI = 0; cI < F.cs.size(); ++cI) {
+        int v[4], nb, mult; double coef[4], u[2]; V3 r;
+        friction_rel(s, Xn, F, cI, v, coef, nb, mult, u, r);
+        EI[cI] = f0_SF(u[0] * u[0] + u[1] * u[1], epsvh) * F.normalForce[cI];
+        if (F.cs[cI][3] < -1) EI[cI] *= -F.cs[cI][3];
+    }
+    E += mu * std::accumulate(EI.begin(), EI.end(), 0.0);
+}
+// FRICTION.h:254-379
+static void compute_friction_gradient(const Scene& s, const double* Xn, const FrictionSet& F, double epsvh2, double mu, double* g)
+{
+    const double epsvh = std::sqrt(epsvh2);
+    for (size_t cI = 0; cI < F.cs.size(); ++cI) {
+        int v[4], nb, mult; double coef[4], u[2]; V3 r;
+        friction_rel(s, Xn, F, cI, v, coef, nb, mult, u, r);
+        const double sc = f1_SF_div(u[0] * u[0] + u[1] * u[1], epsvh) * mult * mu * F.normalForce[cI];
+        const auto& B = F.basis[cI];
+        const V3 t3(sc * (B[0] * u[0] + B[3] * u[1]), sc * (B[1] * u[0] + B[4] * u[1]), sc * (B[2] * u[0] + B[5] * u[1]));
+        for (int k = 0; k < nb; ++k) { g[3 * v[k]] += coef[k] * t3.x; g[3 * v[k] + 1] += coef[k] * t3.y; g[3 * v[k] + 2] += coef[k] * t3.z; }
+    }
+}
+// FRICTION.h:381-663
+static void compute_friction_hessian(const Scene& s, const double* Xn, const FrictionSet& F, double epsvh2, double mu, bool projectSPD,
+    std::vector<Triplet>& triplets)
+{
+    const double epsvh = std::sqrt(epsvh2);
+    std::vector<size_t> start(F.cs.size());
+    size_t cur = triplets.size();
+    for (size_t cI = 0; cI < F.cs.size(); ++cI) { start[cI] = cur; const int n = block_dim(F.cs[cI]); cur += (size_t)n * n; }
+    triplets.resize(cur);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long cI = 0; cI < (long)F.cs.size(); ++cI) {
+        int v[4], nb, mult; double coef[4], u[2]; V3 r;
+        friction_rel(s, Xn, F, cI, v, coef, nb, mult, u, r);
+        const double x2 = u[0] * u[0] + u[1] * u[1], xn = std::sqrt(x2);
+        const double f1 = f1_SF_div(x2, epsvh), f2 = f2_SF_term(x2, epsvh);
+        const double sc = mult * mu * F.normalForce[cI];
+        double inner[4];
+        if (x2 >= epsvh2) {
+            const double ub[2] = {-u[1], u[0]}, k = sc * f1 / x2;
+            inner[0] = k * ub[0] * ub[0]; inner[1] = inner[2] = k * ub[0] * ub[1]; inner[3] = k * ub[1] * ub[1];
+        }
+        else if (xn == 0) { inner[0] = inner[3] = sc * f1; inner[1] = inner[2] = 0; }
+        else {
+            inner[0] = (f2 / xn) * u[0] * u[0] + f1; inner[1] = inner[2] = (f2 / xn) * u[0] * u[1]; inner[3] = (f2 / xn) * u[1] * u[1] + f1;
+            if (projectSPD) make_pd(2, inner);
+            for (int k = 0; k < 4; ++k) inner[k] *= sc;
+        }
+        // H = TT^T inner TT, TT = coef (x) basis^T
+        const auto& B = F.basis[cI];
+        double M[9]; // basis inner basis^T (3x3)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                M[3 * a + b] = B[a] * (inner[0] * B[b] + inner[1] * B[3 + b]) + B[3 + a] * (inner[2] * B[b] + inner[3] * B[3 + b]);
+        const int n = 3 * nb;
+        Triplet* out = triplets.data() + start[cI];
+        for (int i = 0; i < nb; ++i)
+            for (int j = 0; j < nb; ++j)
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        out[(i * 3 + a) * n + j * 3 + b] = Triplet{v[i] * 3 + a, v[j] * 3 + b, coef[i] * coef[j] * M[3 * a + b]};
+    }
+}
+
 } // namespace cipc_oracle
 
 // ======================================================================= C API (ctypes)
@@ -1097,6 +1317,71 @@ void oracle_barrier_fn(int elastic, double d, double dHat, const double* kappa, 
     out3[1] = barrier_gradient(elastic != 0, d, dHat, kappa);
     out3[2] = barrier_hessian(elastic != 0, d, dHat, kappa);
 }
+// ---- friction
+static FrictionSet g_F;
+int oracle_friction_basis(void* h, int elastic, const int* cs, const double* info, int n, double dHat2, const double* kappa, double thickness)
+{
+    std::vector<I4> c; std::vector<D2> w;
+    set_cs(cs, info, n, c, w);
+    compute_friction_basis(((SceneHolder*)h)->s, elastic != 0, c, w, dHat2, kappa, thickness, g_F);
+    return (int)g_F.cs.size();
+}
+void oracle_fetch_friction(int* cs, double* closest, double* basis, double* nf)
+{
+    for (size_t i = 0; i < g_F.cs.size(); ++i) {
+        for (int k = 0; k < 4; ++k) cs[4 * i + k] = g_F.cs[i][k];
+        closest[2 * i] = g_F.closest[i][0]; closest[2 * i + 1] = g_F.closest[i][1];
+        for (int k = 0; k < 6; ++k) basis[6 * i + k] = g_F.basis[i][k];
+        nf[i] = g_F.normalForce[i];
+    }
+}
+void oracle_set_friction(const int* cs, const double* closest, const double* basis, const double* nf, int n)
+{
+    g_F.cs.resize(n); g_F.closest.resize(n); g_F.basis.resize(n); g_F.normalForce.resize(n);
+    for (int i = 0; i < n; ++i) {
+        g_F.cs[i] = {cs[4 * i], cs[4 * i + 1], cs[4 * i + 2], cs[4 * i + 3]};
+        g_F.closest[i] = {closest[2 * i], closest[2 * i + 1]};
+        for (int k = 0; k < 6; ++k) g_F.basis[i][k] = basis[6 * i + k];
+        g_F.normalForce[i] = nf[i];
+    }
+}
+double oracle_friction_coef(int nComp, const int* compNodeRange, const double* muComp)
+{
+    std::vector<int> r(compNodeRange, compNodeRange + nComp);
+    std::vector<double> m(muComp, muComp + (size_t)nComp * nComp);
+    double mu;
+    compute_friction_coef(g_F.cs, r, m, g_F.normalForce, mu);
+    return mu;
+}
+void oracle_friction_potential(void* h, const double* Xn, double epsvh2, double mu, double* E)
+{
+    compute_friction_potential(((SceneHolder*)h)->s, Xn, g_F, epsvh2, mu, *E);
+}
+void oracle_friction_gradient(void* h, const double* Xn, double epsvh2, double mu, double* g)
+{
+    compute_friction_gradient(((SceneHolder*)h)->s, Xn, g_F, epsvh2, mu, g);
+}
+long oracle_friction_hessian(void* h, const double* Xn, double epsvh2, double mu, int projectSPD)
+{
+    g_trip.clear();
+    compute_friction_hessian(((SceneHolder*)h)->s, Xn, g_F, epsvh2, mu, projectSPD != 0, g_trip);
+    return (long)g_trip.size();
+}
+// probes of FRICTION_UTILS.h: kind 0 PP, 1 PE, 2 PT, 3 EE -> basis (6, column-major) and closest point (2)
+void oracle_friction_utils(int kind, const double* x, double* basis, double* closest)
+{
+    const V3 a(x), b(x + 3), c(x + 6), d(x + 9);
+    std::array<double, 6> B;
+    closest[0] = closest[1] = 0;
+    switch (kind) {
+    case 0: pp_tangent_basis(a, b, B); break;
+    case 1: pe_tangent_basis(a, b, c, B); closest[0] = pe_closest_point(a, b, c); break;
+    case 2: pt_tangent_basis(a, b, c, d, B); pt_closest_point(a, b, c, d, closest[0], closest[1]); break;
+    default: ee_tangent_basis(a, b, c, d, B); ee_closest_point(a, b, c, d, closest[0], closest[1]); break;
+    }
+    for (int k = 0; k < 6; ++k) basis[k] = B[k];
+}
+void oracle_friction_f(double x2, double epsvh, double* out3) { out3[0] = f0_SF(x2, epsvh); out3[1] = f1_SF_div(x2, epsvh); out3[2] = f2_SF_term(x2, epsvh); }
 void oracle_make_pd(int n, double* H) { make_pd(n, H); }
 void oracle_sym_eig(int n, const double* A, double* V, double* d) { sym_eig(n, A, V, d); }
 

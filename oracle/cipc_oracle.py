@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _REF = None
+_REFDRV = None
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -32,8 +33,8 @@ def build(force=False):
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "libcipc_oracle.so"], stdout=subprocess.DEVNULL)
-    ref_so = os.path.join(_HERE, "_ref", "libcipc_refdist.so")
-    if os.path.isdir("/root/reference/Library/Math/Distance") and (force or not os.path.exists(ref_so)):
+    ref_sos = [os.path.join(_HERE, "_ref", f) for f in ("libcipc_refdist.so", "libcipc_refdrv.so")]
+    if os.path.isdir("/root/reference/Library/Math/Distance") and (force or not all(os.path.exists(f) for f in ref_sos)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -45,6 +46,8 @@ def lib():
         L.oracle_scene_create.restype = C.c_void_p
         L.oracle_barrier_hessian.restype = C.c_long
         L.oracle_dist2_unclassified.restype = C.c_double
+        L.oracle_friction_coef.restype = C.c_double
+        L.oracle_friction_hessian.restype = C.c_long
         _LIB = L
     return _LIB
 
@@ -65,6 +68,25 @@ def ref():
     return _REF
 
 
+def refdrv():
+    """The reference's own drivers (see RefScene), or None when oracle/_ref was never built."""
+    global _REFDRV
+    if _REFDRV is None:
+        p = os.path.join(_HERE, "_ref", "libcipc_refdrv.so")
+        if not os.path.exists(p):
+            build()
+        if not os.path.exists(p):
+            return None
+        R = C.CDLL(p)
+        R.ref_scene_create.restype = C.c_void_p
+        R.ref_barrier_hessian.restype = C.c_long
+        R.ref_friction_hessian.restype = C.c_long
+        R.ref_friction_coef.restype = C.c_double
+        R.ref_timer.restype = C.c_double
+        _REFDRV = R
+    return _REFDRV
+
+
 def num_threads():
     return lib().oracle_num_threads()
 
@@ -75,9 +97,15 @@ def set_num_threads(n):
 
 class OracleScene:
     """Holds contiguous copies of a scene dict (see codim-ipc_b200 scenes) for the oracle."""
+    _prefix = "oracle_"
+
+    def _lib(self):
+        return lib()
+
+    def _fn(self, name):
+        return getattr(self._lib(), self._prefix + name)
 
     def __init__(self, sc):
-        L = lib()
         self.X = np.ascontiguousarray(sc["X"], dtype=np.float64)
         self.X0 = np.ascontiguousarray(sc["X0"], dtype=np.float64)
         self.BN = np.ascontiguousarray(sc["BN"], dtype=np.int32)
@@ -90,30 +118,30 @@ class OracleScene:
                       for k in ("BNArea", "BEArea", "BTArea")]
         ap = [(_dp(a) if a is not None else None) for a in self.areas]
         cd = sc.get("codim", (len(self.BN), len(self.BN)))
-        self.h = C.c_void_p(L.oracle_scene_create(
+        self._fn("scene_create").restype = C.c_void_p
+        self.h = C.c_void_p(self._fn("scene_create")(
             self.nV, _dp(self.X), _dp(self.X0), len(self.BN), _ip(self.BN), len(self.BE), _ip(self.BE),
             len(self.BT), _ip(self.BT), int(sc.get("nRod", 0)), int(cd[0]), int(cd[1]),
             self.DBC.ctypes.data_as(C.POINTER(C.c_uint8)), len(self.nnx), _ip(self.nnx), ap[0], ap[1], ap[2]))
 
     def set_X(self, X):
         self.X = np.ascontiguousarray(X, dtype=np.float64)
-        lib().oracle_scene_set_X(self.h, _dp(self.X))
+        self._fn("scene_set_X")(self.h, _dp(self.X))
 
     def __del__(self):
         try:
-            lib().oracle_scene_destroy(self.h)
+            self._fn("scene_destroy")(self.h)
         except Exception:
             pass
 
     # ---- Compute_Constraint_Set
     def constraint_set(self, dHat2, thickness, elastic=False, use_hash=True, timers=None):
-        L = lib()
         tm = np.zeros(4)
-        n = L.oracle_constraint_set(self.h, int(elastic), C.c_double(dHat2), C.c_double(thickness), int(use_hash), _dp(tm))
+        n = self._fn("constraint_set")(self.h, int(elastic), C.c_double(dHat2), C.c_double(thickness), int(use_hash), _dp(tm))
         cs = np.zeros((n, 4), np.int32)
         info = np.zeros((n, 2), np.float64)
         if n:
-            L.oracle_fetch_constraints(_ip(cs), _dp(info))
+            self._fn("fetch_constraints")(_ip(cs), _dp(info))
         if timers is not None:
             timers[:] = tm
         return cs, info
@@ -123,7 +151,7 @@ class OracleScene:
         cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
         kappa = np.ascontiguousarray(kappa, np.float64)
         E = C.c_double(E0)
-        err = lib().oracle_barrier(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+        err = self._fn("barrier")(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
                                    C.c_double(thickness), C.byref(E))
         if err:
             raise FloatingPointError("non-positive distance during barrier evaluation")
@@ -134,26 +162,25 @@ class OracleScene:
         kappa = np.ascontiguousarray(kappa, np.float64)
         if g is None:
             g = np.zeros((self.nV, 3))
-        lib().oracle_barrier_gradient(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+        self._fn("barrier_gradient")(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
                                       C.c_double(thickness), _dp(g))
         return g
 
     def barrier_hessian(self, cs, info, dHat2, kappa, thickness, projectSPD=True, elastic=False):
         cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
         kappa = np.ascontiguousarray(kappa, np.float64)
-        L = lib()
-        n = L.oracle_barrier_hessian(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+        n = self._fn("barrier_hessian")(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
                                      C.c_double(thickness), int(projectSPD))
         rows = np.zeros(n, np.int32); cols = np.zeros(n, np.int32); vals = np.zeros(n)
         if n:
-            L.oracle_fetch_triplets(_ip(rows), _ip(cols), _dp(vals))
+            self._fn("fetch_triplets")(_ip(rows), _ip(cols), _dp(vals))
         return rows, cols, vals
 
     def barrier_hessian_notfetch(self, cs, info, dHat2, kappa, thickness, projectSPD=True, elastic=False):
         """computes the triplets inside the oracle without copying them out (CPU-baseline timing); returns their number"""
         cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
         kappa = np.ascontiguousarray(kappa, np.float64)
-        return lib().oracle_barrier_hessian(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
+        return self._fn("barrier_hessian")(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa),
                                             C.c_double(thickness), int(projectSPD))
 
     def step_size(self, searchDir, thickness, stepSize=1.0, elastic=False, use_hash=True, timers=None):
@@ -161,7 +188,7 @@ class OracleScene:
         a = C.c_double(stepSize)
         tm = np.zeros(3)
         npairs = C.c_long(0)
-        err = lib().oracle_step_size(self.h, int(elastic), _dp(p), C.c_double(thickness), int(use_hash), C.byref(a), _dp(tm),
+        err = self._fn("step_size")(self.h, int(elastic), _dp(p), C.c_double(thickness), int(use_hash), C.byref(a), _dp(tm),
                                      C.byref(npairs))
         if err:
             raise FloatingPointError("ACCD returned a zero step (reference would exit(-1))")
@@ -170,12 +197,73 @@ class OracleScene:
         self.last_pairs = npairs.value
         return a.value
 
+    # ---- friction (FEM/FRICTION.h); the friction set lives inside the oracle library between calls
+    def friction_basis(self, cs, info, dHat2, kappa, thickness, elastic=False):
+        cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
+        kappa = np.ascontiguousarray(kappa, np.float64)
+        n = self._fn("friction_basis")(self.h, int(elastic), _ip(cs), _dp(info), len(cs), C.c_double(dHat2), _dp(kappa), C.c_double(thickness))
+        return self.fetch_friction(n)
+
+    def fetch_friction(self, n):
+        fcs = np.zeros((n, 4), np.int32); cp = np.zeros((n, 2)); B = np.zeros((n, 6)); nf = np.zeros(n)
+        if n:
+            self._fn("fetch_friction")(_ip(fcs), _dp(cp), _dp(B), _dp(nf))
+        return fcs, cp, B, nf
+
+    def set_friction(self, fcs, cp, B, nf):
+        fcs = np.ascontiguousarray(fcs, np.int32); cp = np.ascontiguousarray(cp, np.float64)
+        B = np.ascontiguousarray(B, np.float64); nf = np.ascontiguousarray(nf, np.float64)
+        self._fn("set_friction")(_ip(fcs), _dp(cp), _dp(B), _dp(nf), len(fcs))
+
+    def friction_coef(self, compNodeRange, muComp):
+        r = np.ascontiguousarray(compNodeRange, np.int32); m = np.ascontiguousarray(muComp, np.float64)
+        return self._fn("friction_coef")(len(r), _ip(r), _dp(m))
+
+    def friction_potential(self, Xn, epsvh2, mu, E0=0.0):
+        Xn = np.ascontiguousarray(Xn, np.float64)
+        E = C.c_double(E0)
+        self._fn("friction_potential")(self.h, _dp(Xn), C.c_double(epsvh2), C.c_double(mu), C.byref(E))
+        return E.value
+
+    def friction_gradient(self, Xn, epsvh2, mu, g=None):
+        Xn = np.ascontiguousarray(Xn, np.float64)
+        if g is None:
+            g = np.zeros((self.nV, 3))
+        self._fn("friction_gradient")(self.h, _dp(Xn), C.c_double(epsvh2), C.c_double(mu), _dp(g))
+        return g
+
+    def friction_hessian(self, Xn, epsvh2, mu, projectSPD=True):
+        Xn = np.ascontiguousarray(Xn, np.float64)
+        n = self._fn("friction_hessian")(self.h, _dp(Xn), C.c_double(epsvh2), C.c_double(mu), int(projectSPD))
+        rows = np.zeros(n, np.int32); cols = np.zeros(n, np.int32); vals = np.zeros(n)
+        if n:
+            self._fn("fetch_triplets")(_ip(rows), _ip(cols), _dp(vals))
+        return rows, cols, vals
+
     def min_dist2(self, cs, thickness):
         cs = np.ascontiguousarray(cs, np.int32)
         d = np.zeros(len(cs))
         m = C.c_double(0)
-        lib().oracle_min_dist2(self.h, _ip(cs), len(cs), C.c_double(thickness), _dp(d), C.byref(m))
+        self._fn("min_dist2")(self.h, _ip(cs), len(cs), C.c_double(thickness), _dp(d), C.byref(m))
         return d, m.value
+
+
+class RefScene(OracleScene):
+    """Same interface, executed by the reference's OWN drivers (oracle/_ref/libcipc_refdrv.so: FEM/IPC.h,
+    Grid/SPATIAL_HASH.h, FEM/FRICTION.h compiled from /root/reference against the stubs in ref_build/stub)."""
+    _prefix = "ref_"
+
+    def _lib(self):
+        L = refdrv()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libcipc_refdrv.so is not built (needs /root/reference)")
+        return L
+
+    def timer(self, name):
+        return self._lib().ref_timer(name.encode())
+
+    def timer_reset(self):
+        self._lib().ref_timer_reset()
 
 
 # ---- per-stencil probes (kind: 0 PP, 1 PE, 2 PT, 3 EE, 4 EE cross-norm^2)
@@ -232,6 +320,23 @@ def barrier_fn(d, dHat, kappa, elastic=False, which="oracle"):
     out = np.zeros(3)
     fn = lib().oracle_barrier_fn if which == "oracle" else ref().ref_barrier_fn
     fn(int(elastic), C.c_double(d), C.c_double(dHat), _dp(k), _dp(out))
+    return out
+
+
+def friction_utils(kind, x, which="oracle"):
+    """tangent basis (6, column-major 3x2) and closest-point parameters (2) of FEM/FRICTION_UTILS.h; kind 0 PP, 1 PE, 2 PT, 3 EE"""
+    x = _x12(x)
+    B = np.zeros(6); cp = np.zeros(2); TT = np.zeros(24)
+    if which == "oracle":
+        lib().oracle_friction_utils(kind, _dp(x), _dp(B), _dp(cp))
+        return B, cp, None
+    ref().ref_friction_utils(kind, _dp(x), _dp(B), _dp(cp), _dp(TT))
+    return B, cp, TT[:2 * _NDOF[kind]].reshape(2, -1)
+
+
+def friction_f(x2, epsvh, which="oracle"):
+    out = np.zeros(3)
+    (lib().oracle_friction_f if which == "oracle" else ref().ref_friction_f)(C.c_double(x2), C.c_double(epsvh), _dp(out))
     return out
 
 

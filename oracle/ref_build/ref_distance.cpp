@@ -15,6 +15,7 @@ using std::log;
 #include <Math/Distance/EDGE_EDGE_MOLLIFIER.h>
 #include <Math/Distance/CCD.h>
 #include <Math/BARRIER.h>
+#include <FEM/FRICTION_UTILS.h>
 
 using namespace JGSL;
 typedef Eigen::Matrix<double, 3, 1> V3;
@@ -108,6 +109,39 @@ int ref_broadphase(int kind, const double* x, const double* dx, double dist)
     case 5: return Point_Edge_CCD_Broadphase(a, b, c, da, db, dc, dist);
     default: return Point_Point_CCD_Broadphase(a, b, da, db, dist);
     }
+}
+// FEM/FRICTION_UTILS.h probes: kind 0 PP, 1 PE, 2 PT, 3 EE -> tangent basis (column-major 3x2), closest point, TT (2 x 3nb row-major)
+void ref_friction_utils(int kind, const double* x, double* basis, double* closest, double* TTout)
+{
+    const V3 a(x), b(x + 3), c(x + 6), d(x + 9);
+    Eigen::Matrix<double, 3, 2> B;
+    Eigen::Matrix<double, 2, 1> cp; cp[0] = cp[1] = 0;
+    if (kind == 0) {
+        Point_Point_Tangent_Basis(a, b, B);
+        Eigen::Matrix<double, 2, 6> TT; Point_Point_TT(B, TT);
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 6; ++j) TTout[i * 6 + j] = TT(i, j);
+    }
+    else if (kind == 1) {
+        Point_Edge_Tangent_Basis(a, b, c, B); Point_Edge_Closest_Point(a, b, c, cp[0]);
+        Eigen::Matrix<double, 2, 9> TT; Point_Edge_TT(B, cp[0], TT);
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 9; ++j) TTout[i * 9 + j] = TT(i, j);
+    }
+    else if (kind == 2) {
+        Point_Triangle_Tangent_Basis(a, b, c, d, B); Point_Triangle_Closest_Point(a, b, c, d, cp);
+        Eigen::Matrix<double, 2, 12> TT; Point_Triangle_TT(B, cp[0], cp[1], TT);
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 12; ++j) TTout[i * 12 + j] = TT(i, j);
+    }
+    else {
+        Edge_Edge_Tangent_Basis(a, b, c, d, B); Edge_Edge_Closest_Point(a, b, c, d, cp);
+        Eigen::Matrix<double, 2, 12> TT; Edge_Edge_TT(B, cp[0], cp[1], TT);
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 12; ++j) TTout[i * 12 + j] = TT(i, j);
+    }
+    for (int j = 0; j < 2; ++j) for (int i = 0; i < 3; ++i) basis[3 * j + i] = B(i, j);
+    closest[0] = cp[0]; closest[1] = cp[1];
+}
+void ref_friction_f(double x2, double epsvh, double* out3)
+{
+    f0_SF(x2, epsvh, out3[0]); f1_SF_Div_RelDXNorm(x2, epsvh, out3[1]); f2_SF_Term(x2, epsvh, out3[2]);
 }
 void ref_barrier_fn(int elastic, double d, double dHat, const double* kappa_in, double* out3)
 {
