@@ -14,8 +14,10 @@ Workload: cfg5, the 1M-triangle stacked-cloth scene the BASELINE target is quote
   N > 1  : the same scene, candidate pairs partitioned across ranks by cell ranges of the sorted hash
            ("strong" scaling); NCCL all-reduces the step size (min), energy and gradient (sum), min-dist (min)
 
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded
-sample of the same workload, scaled to the full size (the reference itself cannot be built offline).
+`--impl reference` times the reference's own CPU implementation of the path -- FEM/IPC.h + Grid/SPATIAL_HASH.h
+compiled from its sources into oracle/_ref/libcipc_refdrv.so (stand-ins only for Eigen/Cabana/pybind11), or the
+oracle port when that library is absent -- with all host threads on a bounded sample of the same workload,
+scaled to the full size.
 """
 import argparse
 import json
@@ -77,12 +79,25 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_contact_stage(sc, threads=None):
-    """one contact stage on the CPU oracle; returns (seconds, per-stage dict, nConstraints)"""
+def cpu_backend():
+    """("reference", RefScene) when oracle/_ref/libcipc_refdrv.so -- the reference's own FEM/IPC.h + SPATIAL_HASH.h compiled
+    from its sources (oracle/Makefile `ref`) -- is present, else ("port", OracleScene): the oracle restatement"""
     from oracle import cipc_oracle as O
+    if O.refdrv() is not None:
+        return "reference", O.RefScene
+    return "port", O.OracleScene
+
+
+def cpu_contact_stage(sc, threads=None):
+    """one contact stage on the CPU (the reference's own drivers when built, else the oracle port);
+    returns (seconds, per-stage dict, nConstraints)"""
+    from oracle import cipc_oracle as O
+    kind, Scene = cpu_backend()
     if threads:
         O.set_num_threads(threads)
-    S = O.OracleScene(sc)
+        if kind == "reference":
+            O.refdrv().ref_set_num_threads(int(threads))
+    S = Scene(sc)
     st = {}
     t0 = time.perf_counter()
     cs, info = S.constraint_set(sc["dHat2"], sc["xi"]); t1 = time.perf_counter(); st["constraint_set"] = t1 - t0
@@ -101,20 +116,22 @@ def run_reference_arm(args):
     from oracle import cipc_oracle as O
     sample, scale = CPU_SAMPLE[args.workload]
     sc = make_scene(sample)
-    O.set_num_threads(os.cpu_count())  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
-    cores = O.num_threads()
+    cores = os.cpu_count()  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
+    kind = cpu_backend()[0]
     times = []
     for i in range(args.warmup + args.steps):
-        t, st, nC = cpu_contact_stage(sc)
+        t, st, nC = cpu_contact_stage(sc, cores)
         if i >= args.warmup:
             times.append(t)
     ms = 1e3 * float(np.mean(times)) * scale
-    desc = "oracle port (-O3 -mavx2 -mfma -fopenmp, reference's parallel structure) on %s (%d triangles, %d constraints), x%.0f to %s" % (
-        sample, len(sc["BT"]), nC, scale, args.workload)
+    what = ("the reference's own FEM/IPC.h + Grid/SPATIAL_HASH.h drivers (oracle/_ref, -O3 -mavx2 -mfma -fopenmp, Par_Each on OpenMP)"
+            if kind == "reference" else "oracle port (-O3 -mavx2 -mfma -fopenmp, reference's parallel structure)")
+    desc = "%s on %s (%d triangles, %d constraints), x%.0f to %s" % (what, sample, len(sc["BT"]), nC, scale, args.workload)
     line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "triangles": WORKLOADS[args.workload][0] ** 2 * 2 * WORKLOADS[args.workload][1]},
-            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": desc,
+                             "stages_s": {k: round(v, 4) for k, v in st.items()}},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -342,13 +359,13 @@ def main():
 
     cpu = None
     if not args.no_cpu:
-        from oracle import cipc_oracle as O
-        O.set_num_threads(os.cpu_count())
         sample, scale = CPU_SAMPLE[args.workload]
         scs = make_scene(sample)
-        tcpu, st, nCs = cpu_contact_stage(scs)
-        cpu = {"value": 1e3 * tcpu * scale, "unit": "ms", "cores": O.num_threads(), "kind": "port",
-               "sample": "one contact stage of the oracle on %s (%d triangles, %d constraints, %.1f s), scaled x%.0f by triangle count" % (
+        kind = cpu_backend()[0]
+        tcpu, st, nCs = cpu_contact_stage(scs, os.cpu_count())
+        cpu = {"value": 1e3 * tcpu * scale, "unit": "ms", "cores": os.cpu_count(), "kind": kind,
+               "sample": "one contact stage of %s on %s (%d triangles, %d constraints, %.1f s), scaled x%.0f by triangle count" % (
+                   "the reference's own drivers (oracle/_ref)" if kind == "reference" else "the oracle port",
                    sample, len(scs["BT"]), nCs, tcpu, scale),
                "stages_s": {k: round(v, 4) for k, v in st.items()}}
 

@@ -904,11 +904,11 @@ __global__ void __launch_bounds__(128, 3) k_hessian_factor(const double4* __rest
     for (int k = 0; k < NY * NN / 2; ++k) o[k] = make_double2(Y[2 * k], Y[2 * k + 1]);
     hdr[q] = h;
 }
-template <int CLS>
+template <int NB, int NY>
 __global__ void __launch_bounds__(256) k_hessian_expand(const double* __restrict__ Yin, const YHdr* __restrict__ hdr, u64 total,
     cipc_triplet* __restrict__ trip)
 {
-    constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, PER = NN * NN;
+    constexpr int NN = 3 * NB, PER = NN * NN;
     // one 64-bit division per thread for the block base, everything else in small 32-bit arithmetic
     const u64 base = (u64)blockIdx.x * 256u;
     if (base + threadIdx.x >= total) return;
@@ -926,6 +926,52 @@ __global__ void __launch_bounds__(256) k_hessian_expand(const double* __restrict
     for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
     const int ri = r / 3, ci = c / 3;
     put_triplet(trip + (size_t)h.off * 9 + e, h.v[ri] * 3 + (r - 3 * ri), h.v[ci] * 3 + (c - 3 * ci), v);
+}
+// Tiled expansion: a CTA stages the factors and headers of G consecutive stencils in shared memory with coalesced
+// 16-byte loads, then every thread forms G*PER/256 triplets from shared memory and issues that many independent
+// 16-byte stores back to back (a warp writes 512 contiguous bytes per instruction).  Versus one thread per triplet
+// this removes the load -> store dependency from the critical path: the write stream is limited by HBM, not by the
+// latency of the factor gathers.  STREAM selects st.global.cs (the triplet stream is never re-read by this library).
+template <int NB, int NY, int G, bool STREAM>
+__global__ void __launch_bounds__(256) k_hessian_expand_tiled(const double* __restrict__ Yin, const YHdr* __restrict__ hdr, u32 n,
+    cipc_triplet* __restrict__ trip)
+{
+    constexpr int NN = 3 * NB, PER = NN * NN, YD = NY * NN;
+    static_assert((G * YD) % 2 == 0, "factor tile must be a whole number of 16-byte words");
+    __shared__ __align__(16) double sY[G * YD];
+    __shared__ __align__(16) int sH[G * 8];
+    const u32 q0 = blockIdx.x * G;
+    const u32 g = min((u32)G, n - q0);
+    {
+        const double2* src = reinterpret_cast<const double2*>(Yin + (size_t)q0 * YD);
+        double2* dst = reinterpret_cast<double2*>(sY);
+        for (u32 t = threadIdx.x; t < g * YD / 2; t += 256) dst[t] = __ldcs(src + t);
+        const int4* hs = reinterpret_cast<const int4*>(hdr + q0);
+        int4* hd = reinterpret_cast<int4*>(sH);
+        for (u32 t = threadIdx.x; t < g * 2; t += 256) hd[t] = __ldcs(hs + t);
+    }
+    __syncthreads();
+    const u32 total = g * PER;
+#pragma unroll 4
+    for (u32 t = threadIdx.x; t < total; t += 256) {
+        const u32 q = t / PER;
+        const int e = (int)(t - q * PER);
+        const int r = e / NN, c = e - r * NN;
+        const int* h = sH + q * 8;
+        const u32 off = (u32)h[0];
+        if (off == 0xffffffffu) continue;
+        const double* y = sY + q * YD;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
+        const int ri = r / 3, ci = c / 3;
+        int4 o;
+        o.x = h[1 + ri] * 3 + (r - 3 * ri); o.y = h[1 + ci] * 3 + (c - 3 * ci);
+        const long long b = __double_as_longlong(v);
+        o.z = (int)(b & 0xffffffffLL); o.w = (int)(b >> 32);
+        int4* dst = reinterpret_cast<int4*>(trip + (size_t)off * 9 + e);
+        if (STREAM) __stcs(dst, o); else *dst = o;
+    }
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 constexpr int DENSE_BD = 64;                              // threads per block of the dense path
@@ -1130,6 +1176,7 @@ struct cipc_ctx {
     double *Y0 = nullptr, *Y1 = nullptr, *Y2 = nullptr;
     void *h0 = nullptr, *h1 = nullptr, *h2 = nullptr;
     u32 nk[4] = {0, 0, 0, 0};
+    int ny[3] = {3, 2, 1};  // factor vectors per stencil of class 0/1/2: barrier {3,2,1}, friction {2,2,2}
     DevBuf<cipc_triplet> denseBuf;
     DevBuf<uint2> denseMeta;
     PinnedBuf pinY, pinH, pinD, pinM;
@@ -1481,16 +1528,29 @@ int do_min_dist(cipc_ctx* c, bool wantDist)
 
 // ---- triplet delivery
 // device side: expand the factors into the triplet stream (needed only when the triplets are consumed on the GPU)
+template <int NB, int NY>
+void launch_expand(cipc_ctx* c, const double* Y, const void* hdr, u32 n)
+{
+    if (!n) return;
+    static const int variant = getenv("CIPC_EXPAND_VARIANT") ? atoi(getenv("CIPC_EXPAND_VARIANT")) : 0;
+    constexpr int PER = 9 * NB * NB;
+    if (variant == 1) CIPC_LAUNCH((k_hessian_expand_tiled<NB, NY, 32, true>), div_up(n, 32), 256, 0, c->st, Y, (const YHdr*)hdr, n, c->trip.p);
+    else if (variant == 2) CIPC_LAUNCH((k_hessian_expand_tiled<NB, NY, 32, false>), div_up(n, 32), 256, 0, c->st, Y, (const YHdr*)hdr, n, c->trip.p);
+    else if (variant == 3) CIPC_LAUNCH((k_hessian_expand_tiled<NB, NY, 16, true>), div_up(n, 16), 256, 0, c->st, Y, (const YHdr*)hdr, n, c->trip.p);
+    else if (variant == 4) CIPC_LAUNCH((k_hessian_expand_tiled<NB, NY, 64, true>), div_up(n, 64), 256, 0, c->st, Y, (const YHdr*)hdr, n, c->trip.p);
+    else CIPC_LAUNCH((k_hessian_expand<NB, NY>), div_up((u64)n * PER, 256), 256, 0, c->st, Y, (const YHdr*)hdr, (u64)n * PER, c->trip.p);
+}
 void expand_on_device(cipc_ctx* c)
 {
     if (!c->factorValid || c->expanded) return;
     const u32* nk = c->nk;
+    const bool fr = c->ny[0] == 2; // friction factors: two vectors per stencil in every class
     {
         cipc_ctx::Scope sk(c, "k_barrier_hessian"); // the dominant kernel: triplet expansion of the PT/EE blocks
-        if (nk[0]) CIPC_LAUNCH(k_hessian_expand<0>, div_up((u64)nk[0] * 144, 256), 256, 0, c->st, c->Y0, (const YHdr*)c->h0, (u64)nk[0] * 144, c->trip.p);
+        if (fr) launch_expand<4, 2>(c, c->Y0, c->h0, nk[0]); else launch_expand<4, 3>(c, c->Y0, c->h0, nk[0]);
     }
-    if (nk[1]) CIPC_LAUNCH(k_hessian_expand<1>, div_up((u64)nk[1] * 81, 256), 256, 0, c->st, c->Y1, (const YHdr*)c->h1, (u64)nk[1] * 81, c->trip.p);
-    if (nk[2]) CIPC_LAUNCH(k_hessian_expand<2>, div_up((u64)nk[2] * 36, 256), 256, 0, c->st, c->Y2, (const YHdr*)c->h2, (u64)nk[2] * 36, c->trip.p);
+    launch_expand<3, 2>(c, c->Y1, c->h1, nk[1]);
+    if (fr) launch_expand<2, 2>(c, c->Y2, c->h2, nk[2]); else launch_expand<2, 1>(c, c->Y2, c->h2, nk[2]);
     c->expanded = true;
 }
 // host side: y y^T expansion of one stencil with streaming 16-byte stores (the destination is never read back).
@@ -1529,7 +1589,9 @@ inline void expand_one_host(const double* y, const YHdr& h, cipc_triplet* out, b
 void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
 {
     const u32* nk = c->nk;
-    const size_t yD = (size_t)nk[0] * 36 + (size_t)nk[1] * 18 + (size_t)nk[2] * 6, nH = (size_t)nk[0] + nk[1] + nk[2];
+    const size_t yd0 = (size_t)c->ny[0] * 12, yd1 = (size_t)c->ny[1] * 9, yd2 = (size_t)c->ny[2] * 6; // doubles per stencil
+    const bool fr = c->ny[0] == 2;
+    const size_t yD = (size_t)nk[0] * yd0 + (size_t)nk[1] * yd1 + (size_t)nk[2] * yd2, nH = (size_t)nk[0] + nk[1] + nk[2];
     double* hY = (double*)c->pinY.reserve(yD * 8 + 64);
     YHdr* hH = (YHdr*)c->pinH.reserve(nH * sizeof(YHdr) + 64);
     u32 nDense = 0;
@@ -1564,7 +1626,7 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     }
     // expansion of the factored stencils overlaps the dense D2H
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    const double* y0 = hY; const double* y1 = y0 + (size_t)nk[0] * 36; const double* y2 = y1 + (size_t)nk[1] * 18;
+    const double* y0 = hY; const double* y1 = y0 + (size_t)nk[0] * yd0; const double* y2 = y1 + (size_t)nk[1] * yd1;
     const YHdr* g0 = hH; const YHdr* g1 = g0 + nk[0]; const YHdr* g2 = g1 + nk[1];
     int nt = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("CIPC_HOST_THREADS")) nt = atoi(e);
@@ -1581,18 +1643,20 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
             if (it >= items0 + items1 + items2) break;
             if (it < items0) {
                 const size_t a = it * CH, b = std::min<size_t>(a + CH, nk[0]);
-                wait_for(b * 36);
-                for (size_t q = a; q < b; ++q) if (g0[q].off != 0xffffffffu) expand_one_host<4, 3>(y0 + q * 36, g0[q], out, aligned);
+                wait_for(b * yd0);
+                if (fr) { for (size_t q = a; q < b; ++q) if (g0[q].off != 0xffffffffu) expand_one_host<4, 2>(y0 + q * yd0, g0[q], out, aligned); }
+                else for (size_t q = a; q < b; ++q) if (g0[q].off != 0xffffffffu) expand_one_host<4, 3>(y0 + q * yd0, g0[q], out, aligned);
             }
             else if (it < items0 + items1) {
                 const size_t a = (it - items0) * CH, b = std::min<size_t>(a + CH, nk[1]);
-                wait_for((size_t)nk[0] * 36 + b * 18);
-                for (size_t q = a; q < b; ++q) if (g1[q].off != 0xffffffffu) expand_one_host<3, 2>(y1 + q * 18, g1[q], out, aligned);
+                wait_for((size_t)nk[0] * yd0 + b * yd1);
+                for (size_t q = a; q < b; ++q) if (g1[q].off != 0xffffffffu) expand_one_host<3, 2>(y1 + q * yd1, g1[q], out, aligned);
             }
             else {
                 const size_t a = (it - items0 - items1) * CH, b = std::min<size_t>(a + CH, nk[2]);
-                wait_for((size_t)nk[0] * 36 + (size_t)nk[1] * 18 + b * 6);
-                for (size_t q = a; q < b; ++q) if (g2[q].off != 0xffffffffu) expand_one_host<2, 1>(y2 + q * 6, g2[q], out, aligned);
+                wait_for((size_t)nk[0] * yd0 + (size_t)nk[1] * yd1 + b * yd2);
+                if (fr) { for (size_t q = a; q < b; ++q) if (g2[q].off != 0xffffffffu) expand_one_host<2, 2>(y2 + q * yd2, g2[q], out, aligned); }
+                else for (size_t q = a; q < b; ++q) if (g2[q].off != 0xffffffffu) expand_one_host<2, 1>(y2 + q * yd2, g2[q], out, aligned);
             }
         }
         _mm_sfence();
@@ -1988,6 +2052,7 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
                     c->expanded = false;
                     c->Y0 = Y0; c->Y1 = Y1; c->Y2 = Y2; c->h0 = h0; c->h1 = h1; c->h2 = h2;
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
+                    c->ny[0] = 3; c->ny[1] = 2; c->ny[2] = 1;
                     // mollified stencils + rejected ones: dense eigen path, list length read on the device
                     CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
                         (const u32*)dn, bp, projectSPD, c->trip.p);
