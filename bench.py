@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--workload", default="cfg5_1m", choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-friction", action="store_true")
     ap.add_argument("--stage-report", action="store_true", help="print the per-stage device times to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -248,6 +249,21 @@ def main():
         stages[s] = ctx.stage_ms(s)
     counters["ccd_pairs"] = ctx.counter("ccd_pairs")
     ctx.min_dist2_dev(xi); stages["min_dist"] = ctx.stage_ms("min_dist")
+
+    # lagged friction (FEM/FRICTION.h) on the same constraint set: reported beside the metric, not inside `value`
+    friction = {}
+    if not args.no_friction:
+        rng = np.random.default_rng(17)
+        Xn = sc["X"] - rng.normal(size=sc["X"].shape) * np.where(rng.random(nV) < 0.5, 2e-6, 5e-5)[:, None]  # both sides of eps_v h = 1e-5
+        ctx.set_prev_positions(Xn)
+        for _ in range(2):
+            nF = ctx.friction_basis(dHat2, kappa, xi, fetch=False); friction["basis"] = ctx.stage_ms("friction_basis")
+            ctx.friction_energy_dev(1e-10, 0.4); friction["E"] = ctx.stage_ms("friction_E")
+            ctx.friction_gradient_dev(1e-10, 0.4, accumulate=False); friction["g"] = ctx.stage_ms("friction_g")
+            nFT = ctx.friction_hessian(1e-10, 0.4, True, fetch=False); friction["H_factor"] = ctx.stage_ms("friction_H")
+            ctx.dev_triplets(); friction["H_expand"] = ctx.stage_ms("k_barrier_hessian")
+        friction = {k: round(v, 4) for k, v in friction.items()}
+        friction["stencils"] = int(nF); friction["triplets"] = int(nFT)
 
     # ---- end-to-end through the host API (pinned host buffers; copies inside the timed region)
     e2e = None
@@ -375,7 +391,8 @@ def main():
                        "triplets_rank0": int(nTrip), "dHat": float(np.sqrt(dHat2)), "xi": float(xi), "l2": "flushed between timed steps (256 MiB write); working set >> L2",
                        "parallelism": "pairs partitioned by hash-cell ranges x%d" % world},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
-            "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters}
+            "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters,
+            "friction_stages_ms": friction}
     if args.stage_report:
         print(json.dumps(line["stages_ms"], indent=1), file=sys.stderr)
     print(json.dumps(line))

@@ -12,6 +12,12 @@ device is present, every call raises.
     Compute_Barrier_Hessian             IPC.h:1258-1265
     Compute_Intersection_Free_StepSize  IPC.h:1879-1890
     Compute_Min_Dist2                   IPC.h:2246-2249
+and the lagged-friction entry points of Library/FEM/FRICTION.h:
+    Compute_Friction_Basis              FRICTION.h:16-25
+    Compute_Friction_Coef               FRICTION.h:126-130
+    Compute_Friction_Potential          FRICTION.h:172-180
+    Compute_Friction_Gradient           FRICTION.h:254-262
+    Compute_Friction_Hessian            FRICTION.h:381-390
 """
 import ctypes as C
 import os
@@ -90,6 +96,7 @@ class ContactContext:
         self.rank, self.world = rank, world
         self.nV = 0
         self.nC = 0
+        self.nF = 0
         self._keep = []
 
     def close(self):
@@ -218,6 +225,73 @@ class ContactContext:
         m = C.c_double(0)
         self._ck(self.L.cipc_min_dist2(self.h, C.c_double(thickness), _p(d, C.c_double) if want_dist2 else None, C.byref(m)))
         return d, m.value
+
+    # ---- lagged friction (FEM/FRICTION.h) on the resident contact constraint set
+    def set_prev_positions(self, Xn):
+        A, s = self._vec3(Xn)
+        self._ck(self.L.cipc_set_prev_positions(self.h, _p(A, C.c_double), s))
+
+    def friction_basis(self, dHat2, kappa, thickness, elasticIPC=False, fetch=True):
+        k = (C.c_double * 3)(*[float(x) for x in kappa])
+        n = C.c_int(0)
+        self._ck(self.L.cipc_friction_basis(self.h, int(elasticIPC), C.c_double(dHat2), k, C.c_double(thickness), C.byref(n)))
+        self.nF = n.value
+        return self.get_friction_basis() if fetch else n.value
+
+    def get_friction_basis(self):
+        """-> (fricConstraintSet (n,4) int32, closestPoint (n,2), tanBasis (n,6) column-major 3x2, normalForce (n,))"""
+        n = self.nF
+        fcs = np.zeros((n, 4), np.int32); cp = np.zeros((n, 2)); B = np.zeros((n, 6)); nf = np.zeros(n)
+        self._ck(self.L.cipc_get_friction_basis(self.h, _p(fcs, C.c_int32), _p(cp, C.c_double), _p(B, C.c_double), _p(nf, C.c_double)))
+        return fcs, cp, B, nf
+
+    def set_friction_basis(self, fcs, closestPoint, tanBasis, normalForce):
+        fcs = np.ascontiguousarray(fcs, np.int32).reshape(-1, 4)
+        cp = np.ascontiguousarray(closestPoint, np.float64).reshape(-1, 2)
+        B = np.ascontiguousarray(tanBasis, np.float64).reshape(-1, 6)
+        nf = np.ascontiguousarray(normalForce, np.float64).reshape(-1)
+        if not (len(fcs) == len(cp) == len(B) == len(nf)):
+            raise ValueError("friction containers differ in length")
+        self._ck(self.L.cipc_set_friction_basis(self.h, _p(fcs, C.c_int32), _p(cp, C.c_double), _p(B, C.c_double), _p(nf, C.c_double), len(fcs)))
+        self.nF = len(fcs)
+
+    def friction_coef(self, compNodeRange, muComp):
+        r = np.ascontiguousarray(compNodeRange, np.int32).reshape(-1)
+        m = np.ascontiguousarray(muComp, np.float64).reshape(-1)
+        if m.size != r.size * r.size:
+            raise ValueError("muComp must have nComp x nComp entries")
+        mu = C.c_double(0)
+        self._ck(self.L.cipc_friction_coef(self.h, len(r), _p(r, C.c_int32), _p(m, C.c_double), C.byref(mu)))
+        return mu.value
+
+    def friction_energy(self, epsvh2, mu, E=0.0):
+        e = C.c_double(E)
+        self._ck(self.L.cipc_friction_energy(self.h, C.c_double(epsvh2), C.c_double(mu), C.byref(e)))
+        return e.value
+
+    def friction_gradient(self, epsvh2, mu, g=None):
+        if g is None:
+            g = np.zeros((self.nV, 3))
+        assert g.flags.c_contiguous and g.dtype == np.float64 and g.shape[0] == self.nV
+        self._ck(self.L.cipc_friction_gradient(self.h, C.c_double(epsvh2), C.c_double(mu), _p(g, C.c_double), g.shape[1] * 8))
+        return g
+
+    def friction_hessian(self, epsvh2, mu, projectSPD=True, fetch=True, out=None):
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_friction_hessian(self.h, C.c_double(epsvh2), C.c_double(mu), int(projectSPD), C.byref(n)))
+        if not fetch:
+            return n.value
+        trip = out if out is not None else np.zeros(n.value, TRIPLET_DTYPE)
+        assert len(trip) >= n.value and trip.dtype == TRIPLET_DTYPE
+        if n.value:
+            self._ck(self.L.cipc_get_triplets(self.h, trip.ctypes.data_as(C.c_void_p)))
+        return trip[:n.value]
+
+    def friction_energy_dev(self, epsvh2, mu):
+        self._ck(self.L.cipc_friction_energy_dev(self.h, C.c_double(epsvh2), C.c_double(mu)))
+
+    def friction_gradient_dev(self, epsvh2, mu, accumulate=True):
+        self._ck(self.L.cipc_friction_gradient_dev(self.h, C.c_double(epsvh2), C.c_double(mu), int(accumulate)))
 
     # ---- device-resident variants (results stay in HBM)
     def barrier_energy_dev(self, dHat2, kappa, thickness, elasticIPC=False):
@@ -352,3 +426,53 @@ def Compute_Min_Dist2(X, constraintSet, thickness, ctx=None):
     ctx.set_positions(X)
     ctx.set_constraints(constraintSet, np.ones((len(constraintSet), 2)))
     return ctx.min_dist2(thickness)
+
+
+# ---- FEM/FRICTION.h
+def Compute_Friction_Basis(X, contactConstraintSet, stencilInfo, dHat2, kappa, thickness, elasticIPC=False, ctx=None):
+    """-> (constraintSet, closestPoint, tanBasis, normalForce): the four output containers of FRICTION.h:16-25"""
+    ctx = ctx or default_context()
+    _ensure_nodes(ctx, X)
+    ctx.set_positions(X)
+    ctx.set_constraints(contactConstraintSet, stencilInfo)
+    return ctx.friction_basis(dHat2, kappa, thickness, elasticIPC)
+
+
+def Compute_Friction_Coef(constraintSet, closestPoint, tanBasis, compNodeRange, muComp, normalForce, ctx=None):
+    """-> (normalForce scaled per component pair, mu = 1).  The reference takes only constraintSet and normalForce; the
+    other two containers make the friction set resident when it is not the one the context produced last."""
+    ctx = ctx or default_context()
+    ctx.set_friction_basis(constraintSet, closestPoint, tanBasis, normalForce)
+    mu = ctx.friction_coef(compNodeRange, muComp)
+    return ctx.get_friction_basis()[3], mu
+
+
+def _friction_inputs(ctx, X, Xn, constraintSet, closestPoint, tanBasis, normalForce):
+    _ensure_nodes(ctx, X)
+    ctx.set_positions(X)
+    ctx.set_prev_positions(Xn)
+    ctx.set_friction_basis(constraintSet, closestPoint, tanBasis, normalForce)
+
+
+def Compute_Friction_Potential(X, Xn, constraintSet, closestPoint, tanBasis, normalForce, epsvh2, mu, E, ctx=None):
+    """-> E + friction potential (the reference accumulates into its T& E)"""
+    ctx = ctx or default_context()
+    _friction_inputs(ctx, X, Xn, constraintSet, closestPoint, tanBasis, normalForce)
+    return ctx.friction_energy(epsvh2, mu, E)
+
+
+def Compute_Friction_Gradient(X, Xn, constraintSet, closestPoint, tanBasis, normalForce, epsvh2, mu, g, ctx=None):
+    """g (nV,3|4) float64 is accumulated in place (nodeAttr.g +=) and returned"""
+    ctx = ctx or default_context()
+    _friction_inputs(ctx, X, Xn, constraintSet, closestPoint, tanBasis, normalForce)
+    return ctx.friction_gradient(epsvh2, mu, g)
+
+
+def Compute_Friction_Hessian(X, Xn, constraintSet, closestPoint, tanBasis, normalForce, epsvh2, mu, projectSPD, triplets=None, ctx=None):
+    """-> triplets with the friction blocks appended"""
+    ctx = ctx or default_context()
+    _friction_inputs(ctx, X, Xn, constraintSet, closestPoint, tanBasis, normalForce)
+    new = ctx.friction_hessian(epsvh2, mu, projectSPD)
+    if triplets is None or len(triplets) == 0:
+        return new
+    return np.concatenate([triplets, new])

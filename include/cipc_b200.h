@@ -98,10 +98,39 @@ int cipc_step_size(cipc_ctx* ctx, int elasticIPC, double thickness, double* step
 /* dist2 may be NULL; minDist2 = min_c dist2[c] - thickness^2 */
 int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2);
 
+/* ---- lagged friction: FEM/FRICTION.h, FEM/FRICTION_UTILS.h ------------------------------- */
+/* previous-step positions Xn (MESH_NODE storage, stride 32; 24 for packed xyz) */
+int cipc_set_prev_positions(cipc_ctx* ctx, const double* Xn, int stride_bytes);
+/* Compute_Friction_Basis<T,3,elasticIPC> (FRICTION.h:16-124) on the RESIDENT contact constraint set and positions:
+ * drops the mollified stencils (order of the others preserved), computes closestPoint, tanBasis and the lagged
+ * normalForce = -b'(d - xi^2) * 2 sqrt(d) * w.  The friction set stays resident; nF_out = its size. */
+int cipc_friction_basis(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness, int* nF_out);
+/* copies the resident friction set out in the reference's container layouts: fcs nF x 4 int32 (VECTOR<int,4>),
+ * closestPoint nF x 2 double (Eigen::Matrix<T,2,1>), tanBasis nF x 6 double (Eigen::Matrix<T,3,2>, column-major),
+ * normalForce nF double.  Any pointer may be NULL. */
+int cipc_get_friction_basis(cipc_ctx* ctx, int32_t* fcs, double* closestPoint, double* tanBasis, double* normalForce);
+/* makes a caller-owned friction set resident (when the caller's vectors are not the last ones produced);
+ * closestPoint / tanBasis may be NULL when only cipc_friction_coef follows */
+int cipc_set_friction_basis(cipc_ctx* ctx, const int32_t* fcs, const double* closestPoint, const double* tanBasis,
+                            const double* normalForce, int nF);
+/* Compute_Friction_Coef (FRICTION.h:126-170): resident normalForce[c] *= muComp[comp(v0) + comp(v1) * nComp]; *mu_out = 1 */
+int cipc_friction_coef(cipc_ctx* ctx, int nComp, const int32_t* compNodeRange, const double* muComp /* nComp x nComp */, double* mu_out);
+/* Compute_Friction_Potential (FRICTION.h:172-252): E_inout += mu * sum_c mult_c normalForce_c f0(|u_c|) */
+int cipc_friction_energy(cipc_ctx* ctx, double epsvh2, double mu, double* E_inout);
+/* Compute_Friction_Gradient (FRICTION.h:254-379): g[v] += ... (same stride convention as cipc_barrier_gradient) */
+int cipc_friction_gradient(cipc_ctx* ctx, double epsvh2, double mu, double* g, int g_stride_bytes);
+/* Compute_Friction_Hessian (FRICTION.h:381-663): 144/81/36 triplets per friction stencil; deliver them with
+ * cipc_get_triplets / cipc_dev_triplets exactly like the barrier Hessian's (the caller appends) */
+int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTriplets_out);
+/* device-resident variants: energy -> cipc_dev_scalars()[4]; gradient -> cipc_dev_gradient(), added to what is there
+ * when accumulate != 0 (e.g. after cipc_barrier_gradient_dev) */
+int cipc_friction_energy_dev(cipc_ctx* ctx, double epsvh2, double mu);
+int cipc_friction_gradient_dev(cipc_ctx* ctx, double epsvh2, double mu, int accumulate);
+
 /* ---- device-resident access (multi-GPU reductions, benchmarking) ----------------------------- */
 double* cipc_dev_positions(cipc_ctx* ctx);      /* nV x 4 doubles (x,y,z,pad) */
 double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient_dev */
-double* cipc_dev_scalars(cipc_ctx* ctx);        /* [0]=energy partial, [1]=step size, [2]=min dist2 of the last *_dev call */
+double* cipc_dev_scalars(cipc_ctx* ctx);        /* [0]=barrier energy, [1]=step size, [2]=min dist2, [4]=friction energy of the last *_dev call */
 /* same stages with every result left on the device (no D2H): */
 int cipc_barrier_energy_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
 int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
