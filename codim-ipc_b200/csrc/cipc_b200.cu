@@ -332,110 +332,159 @@ __device__ __forceinline__ void cand_push(const CandOut& o, int which, int a, in
     const u32 idx = base + g.thread_rank();
     if (idx < o.cap[which]) o.buf[which][idx] = make_int2(a, b);
 }
-// a pair of boxes that share cell `cell` is handled only in the cell that is the minimum corner
-// of the boxes' intersection
-__device__ __forceinline__ bool min_corner(u32 cell, u64 loA, u64 loB, const GridDesc& G)
+// ---- per-entry pair codes.  A pair of boxes that share a cell is handled only in the cell that is the minimum corner
+// of the boxes' intersection ("min-corner rule": no pair is visited twice, no de-duplication pass).  Both cheap pair
+// tests only need data that is LOCAL to the (cell, primitive) entry:
+//   * min corner:  cell == max(loA, loB) per axis  <=>  per axis, A or B STARTS in this cell (both cover it)  -> 3 bits
+//   * quantised-AABB overlap (FINE_SUB = 16 steps per voxel): with both fine intervals clamped to the cell's own fine
+//     range [16c, 16c+15] the test is unchanged, because each interval reaches into the cell from both sides
+//     (cell(fine lo) <= box lo <= c <= box hi <= cell(fine hi))                                                   -> 6 x 4 bits
+// code.x = lo bytes (x | y<<8 | z<<16) | start bits << 24, code.y = hi bytes.  One coalesced 8-byte load and two
+// byte-wise SIMD compares per pair replace the 24 bytes of gathers of the global test.
+__global__ void k_entry_codes(const u32* __restrict__ keys, const u32* __restrict__ vals, u32 nE, int nBN, int nBE,
+    const u64* __restrict__ boxLo, const ulonglong2* __restrict__ fine, GridDesc G, uint2* __restrict__ codes)
 {
-    const u32 mx = (u32)max(ux(loA), ux(loB)), my = (u32)max(uy(loA), uy(loB)), mz = (u32)max(uz(loA), uz(loB));
-    return cell == mx + (u32)G.gx * (my + (u32)G.gy * mz);
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nE) return;
+    const u32 key = keys[i], cell = key >> 2, kind = key & 3u;
+    const u32 g = vals[i] + (kind == 0 ? 0u : (kind == 1 ? (u32)nBN : (u32)(nBN + nBE)));
+    const u32 cxy = (u32)G.gx * (u32)G.gy;
+    const u32 cz = cell / cxy, rem = cell - cz * cxy, cy = rem / (u32)G.gx, cx = rem - cy * (u32)G.gx;
+    const u64 lo = boxLo[g];
+    const ulonglong2 f = fine[g];
+    const int c[3] = {(int)cx, (int)cy, (int)cz};
+    const int l[3] = {ux(lo), uy(lo), uz(lo)}, fl[3] = {ux(f.x), uy(f.x), uz(f.x)}, fh[3] = {ux(f.y), uy(f.y), uz(f.y)};
+    u32 a = 0, b = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        a |= (u32)clampi(fl[d] - FINE_SUB * c[d], 0, FINE_SUB - 1) << (8 * d);
+        b |= (u32)clampi(fh[d] - FINE_SUB * c[d], 0, FINE_SUB - 1) << (8 * d);
+        if (l[d] == c[d]) a |= 1u << (24 + d);
+    }
+    codes[i] = make_uint2(a, b);
+}
+__device__ __forceinline__ bool code_pair_ok(const uint2 a, const uint2 b)
+{
+    const u32 ov = __vcmpleu4(a.x, b.y) & __vcmpleu4(b.x, a.y); // per byte: loA <= hiB and loB <= hiA
+    return (ov & 0x00ffffffu) == 0x00ffffffu && (((a.x | b.x) >> 24) & 7u) == 7u;
 }
 
-// quantised AABBs overlap in all three axes
-__device__ __forceinline__ bool fine_overlap(const ulonglong2 a, const ulonglong2 b)
-{
-    return ux(a.x) <= ux(b.y) && ux(b.x) <= ux(a.y) && uy(a.x) <= uy(b.y) && uy(b.x) <= uy(a.y) && uz(a.x) <= uz(b.y) && uz(b.x) <= uz(a.y);
-}
-// One WARP per voxel cell in [c0, c1): the queries of the cell (points, then edges) are walked in order and the 32
-// lanes test 32 targets of the run at a time, so the id / box / topology loads of a warp instruction are contiguous
-// or broadcast.  Per pair, cheapest test first: quantised AABB (16 B gather), min-corner rule (8 B gather), topology
-// filters, then the coordinates and the reference's exact AABB test.
+// One WARP per voxel cell in [c0, c1).  Phase 1 (cheap, all lanes busy): the queries of the cell (points, then edges)
+// are walked in order and the 32 lanes test 32 targets of the run at a time on the entry codes; survivors (~1 in 8)
+// are appended to a per-warp ring buffer in shared memory.  Phase 2 (expensive, all lanes busy): whenever the buffer
+// holds 32 pairs, each lane takes one: topology filters, coordinate gathers and the reference's exact AABB test.
+// Without the queue the expensive path ran for every chunk with ~4 of 32 lanes active.
 // CCD=false: constraint-set pass (gap test with dist = dHat).  CCD=true: step-size pass (swept AABB test with
 // dist = thickness, full search direction).
+constexpr int PAIRS_WARPS = 8;
 template <bool CCD>
-__global__ void __launch_bounds__(256) k_pairs(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double dist_,
-    const u32* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ ks, u32 c0, u32 c1,
-    const u64* __restrict__ boxLo, const ulonglong2* __restrict__ fine, GridDesc G, CandOut out)
+__global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double dist_,
+    const u32* __restrict__ vals, const u32* __restrict__ ks, const uint2* __restrict__ codes, u32 c0, u32 c1, CandOut out)
 {
-    const u32 cellIdx = c0 + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
-    if (cellIdx >= c1) return;
-    const u32 lane = threadIdx.x & 31;
+    __shared__ uint2 sq[PAIRS_WARPS][64];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 cellIdx = c0 + blockIdx.x * PAIRS_WARPS + warp;
+    if (cellIdx >= c1) return; // whole warp leaves; no block-level barrier below
+    uint2* q = sq[warp];
+    u32 head = 0, tail = 0; // warp-uniform ring indices
     const u32 p0 = ks[cellIdx * 4], e0 = ks[cellIdx * 4 + 1], t0 = ks[cellIdx * 4 + 2], end = ks[cellIdx * 4 + 3];
-    const u32 cell = keys[p0] >> 2;
     const xd dist(dist_);
-    const int eOff = T.nBN, tOff = T.nBN + T.nBE;
-    // ---- point queries
+    const u32 ltmask = (1u << lane) - 1u;
+    auto push = [&](bool pass, u32 a, u32 b) { // called by all 32 lanes
+        const u32 m = __ballot_sync(0xffffffffu, pass);
+        if (pass) q[(tail + __popc(m & ltmask)) & 63u] = make_uint2(a, b);
+        tail += __popc(m);
+    };
+    // (a, b) = sorted-entry indices of a point and a triangle
+    auto do_pt = [&](u32 a, u32 b) {
+        const int svI = (int)vals[a], t = (int)vals[b];
+        const int vI = T.BN[svI];
+        const int4 tri = T.BT[t];
+        if (!pt_pair_ok(T, vI, tri)) return;
+        const xv3 p = ldx(X, vI), q0 = ldx(X, tri.x), q1 = ldx(X, tri.y), q2 = ldx(X, tri.z);
+        bool ok;
+        if (CCD) ok = pt_ccd_broadphase(p, q0, q1, q2, ldx(P, vI), ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
+        else ok = pt_cd_broadphase(p, q0, q1, q2, dist);
+        if (ok) cand_push(out, 0, svI, t);
+    };
+    auto do_ee = [&](u32 a, u32 b) {
+        const int eI = (int)vals[a], eJ = (int)vals[b];
+        const int2 ea = T.BE[eI], eb = T.BE[eJ];
+        if (!ee_pair_ok(T, ea, eb)) return;
+        const xv3 a0 = ldx(X, ea.x), a1 = ldx(X, ea.y), b0 = ldx(X, eb.x), b1 = ldx(X, eb.y);
+        bool ok;
+        if (CCD) ok = ee_ccd_broadphase(a0, a1, b0, b1, ldx(P, ea.x), ldx(P, ea.y), ldx(P, eb.x), ldx(P, eb.y), dist);
+        else ok = ee_cd_broadphase(a0, a1, b0, b1, dist);
+        if (ok) cand_push(out, 1, eI, eJ);
+    };
+    auto drain = [&](auto process, bool all) {
+        while (tail - head >= 32u || (all && tail != head)) {
+            const u32 n = min(32u, tail - head);
+            __syncwarp();
+            if (lane < n) { const uint2 e = q[(head + lane) & 63u]; process(e.x, e.y); }
+            head += n;
+            __syncwarp();
+        }
+    };
+    // ---- point queries against the triangle run
     for (u32 i = p0; i < e0; ++i) {
-        const int svI = (int)vals[i], vI = T.BN[svI];
-        const u64 loA = boxLo[svI];
-        const ulonglong2 fA = fine[svI];
-        const xv3 p = ldx(X, vI);
-        xv3 dp;
-        if (CCD) dp = ldx(P, vI);
-        for (u32 j = t0 + lane; j < end; j += 32) {
-            const int t = (int)vals[j];
-            if (!fine_overlap(fA, fine[tOff + t])) continue;
-            if (!min_corner(cell, loA, boxLo[tOff + t], G)) continue;
-            const int4 tri = T.BT[t];
-            if (!pt_pair_ok(T, vI, tri)) continue;
-            const xv3 t0_ = ldx(X, tri.x), t1 = ldx(X, tri.y), t2 = ldx(X, tri.z);
-            bool ok;
-            if (CCD) ok = pt_ccd_broadphase(p, t0_, t1, t2, dp, ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
-            else ok = pt_cd_broadphase(p, t0_, t1, t2, dist);
-            if (ok) cand_push(out, 0, svI, t);
+        const uint2 cA = codes[i];
+        for (u32 jb = t0; jb < end; jb += 32) {
+            const u32 j = jb + lane;
+            push(j < end && code_pair_ok(cA, codes[j]), i, j);
+            drain(do_pt, false);
         }
-        // rod / particle points against rod edges (IPC.h:271-326; step size: particles only, :2098-2135)
-        if (T.nRod > 0 && svI >= (CCD ? T.codim1 : T.codim0)) {
-            for (u32 j = e0 + lane; j < t0; j += 32) {
-                const int e = (int)vals[j];
-                if (e < T.nBE - T.nRod) continue;
-                if (!fine_overlap(fA, fine[eOff + e])) continue;
-                if (!min_corner(cell, loA, boxLo[eOff + e], G)) continue;
-                const int2 ed = T.BE[e];
-                if (vI == ed.x || vI == ed.y) continue;
-                if ((T.flags[vI] & 1) && (T.flags[ed.x] & 1) && (T.flags[ed.y] & 1)) continue;
-                const xv3 q0 = ldx(X, ed.x), q1 = ldx(X, ed.y);
-                bool ok;
-                if (CCD) ok = pe_ccd_broadphase(p, q0, q1, dp, ldx(P, ed.x), ldx(P, ed.y), dist);
-                else ok = pe_cd_broadphase(p, q0, q1, dist);
-                if (ok) cand_push(out, 2, svI, e);
+    }
+    drain(do_pt, true);
+    // ---- codimensional extras (rare): rod / particle points against rod edges (IPC.h:271-326; step size: particles
+    //      only, :2098-2135) and particles against later boundary-node slots (IPC.h:328-352, :2137-2163)
+    if (T.nRod > 0 || T.codim1 < T.nBN) {
+        for (u32 i = p0; i < e0; ++i) {
+            const int svI = (int)vals[i];
+            if (svI < min(T.codim0, T.codim1)) continue; // warp-uniform
+            const int vI = T.BN[svI];
+            const uint2 cA = codes[i];
+            const xv3 p = ldx(X, vI);
+            xv3 dp;
+            if (CCD) dp = ldx(P, vI);
+            if (T.nRod > 0 && svI >= (CCD ? T.codim1 : T.codim0)) {
+                for (u32 j = e0 + lane; j < t0; j += 32) {
+                    const int e = (int)vals[j];
+                    if (e < T.nBE - T.nRod) continue;
+                    if (!code_pair_ok(cA, codes[j])) continue;
+                    const int2 ed = T.BE[e];
+                    if (vI == ed.x || vI == ed.y) continue;
+                    if ((T.flags[vI] & 1) && (T.flags[ed.x] & 1) && (T.flags[ed.y] & 1)) continue;
+                    const xv3 q0 = ldx(X, ed.x), q1 = ldx(X, ed.y);
+                    bool ok;
+                    if (CCD) ok = pe_ccd_broadphase(p, q0, q1, dp, ldx(P, ed.x), ldx(P, ed.y), dist);
+                    else ok = pe_cd_broadphase(p, q0, q1, dist);
+                    if (ok) cand_push(out, 2, svI, e);
+                }
             }
-        }
-        // particle against later boundary-node slots (IPC.h:328-352, :2137-2163); slots ascend inside a run
-        if (svI >= T.codim1) {
-            for (u32 j = i + 1 + lane; j < e0; j += 32) {
-                const int svJ = (int)vals[j];
-                if (!fine_overlap(fA, fine[svJ])) continue;
-                if (!min_corner(cell, loA, boxLo[svJ], G)) continue;
-                const int vJ = T.BN[svJ];
-                if ((T.flags[vI] & 1) && (T.flags[vJ] & 1)) continue;
-                bool ok = true;
-                if (CCD) ok = pp_ccd_broadphase(p, ldx(X, vJ), dp, ldx(P, vJ), dist);
-                if (ok) cand_push(out, 3, svI, svJ);
+            if (svI >= T.codim1) { // slots ascend inside a run
+                for (u32 j = i + 1 + lane; j < e0; j += 32) {
+                    if (!code_pair_ok(cA, codes[j])) continue;
+                    const int svJ = (int)vals[j];
+                    const int vJ = T.BN[svJ];
+                    if ((T.flags[vI] & 1) && (T.flags[vJ] & 1)) continue;
+                    bool ok = true;
+                    if (CCD) ok = pp_ccd_broadphase(p, ldx(X, vJ), dp, ldx(P, vJ), dist);
+                    if (ok) cand_push(out, 3, svI, svJ);
+                }
             }
         }
     }
     // ---- edge queries: edge ids ascend inside a run, so j > i <=> eJ > eI
     for (u32 i = e0; i + 1 < t0; ++i) {
-        const int eI = (int)vals[i];
-        const int2 a = T.BE[eI];
-        const u64 loA = boxLo[eOff + eI];
-        const ulonglong2 fA = fine[eOff + eI];
-        const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y);
-        xv3 da0, da1;
-        if (CCD) { da0 = ldx(P, a.x); da1 = ldx(P, a.y); }
-        for (u32 j = i + 1 + lane; j < t0; j += 32) {
-            const int eJ = (int)vals[j];
-            if (!fine_overlap(fA, fine[eOff + eJ])) continue;
-            if (!min_corner(cell, loA, boxLo[eOff + eJ], G)) continue;
-            const int2 b = T.BE[eJ];
-            if (!ee_pair_ok(T, a, b)) continue;
-            const xv3 b0 = ldx(X, b.x), b1 = ldx(X, b.y);
-            bool ok;
-            if (CCD) ok = ee_ccd_broadphase(a0, a1, b0, b1, da0, da1, ldx(P, b.x), ldx(P, b.y), dist);
-            else ok = ee_cd_broadphase(a0, a1, b0, b1, dist);
-            if (ok) cand_push(out, 1, eI, eJ);
+        const uint2 cA = codes[i];
+        for (u32 jb = i + 1; jb < t0; jb += 32) {
+            const u32 j = jb + lane;
+            push(j < t0 && code_pair_ok(cA, codes[j]), i, j);
+            drain(do_ee, false);
         }
     }
+    drain(do_ee, true);
 }
 
 // ===================================================================== constraint-set narrow phase
@@ -1158,6 +1207,7 @@ struct cipc_ctx {
     DevBuf<ulonglong2> fine, nodeFine;
     DevBuf<u32> slabHist;
     DevBuf<u32> cnt, keys, vals, heads, headScan, ks;
+    DevBuf<uint2> codes; // per sorted entry: cell-local pair code (k_entry_codes)
     SortWork sortwk;
     ScanWork scanwk;
     DevBuf<double> partial, scal;  // scal: [0] E partial, [1] alpha, [2] min dist2, [3..] scratch
@@ -1372,6 +1422,8 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
     H.nCells = nCells;
     c->ks.reserve((size_t)nCells * 4, c->st);
     CIPC_LAUNCH(k_kind_starts, div_up((size_t)nE + 1, TB), TB, 0, c->st, c->keys.p, c->headScan.p, c->heads.p, nE, c->ks.p);
+    c->codes.reserve(nE, c->st);
+    CIPC_LAUNCH(k_entry_codes, div_up(nE, TB), TB, 0, c->st, c->keys.p, c->vals.p, nE, T.nBN, T.nBE, c->boxLo.p, c->fine.p, H.G, c->codes.p);
     c->ctr["hash_entries"] = nE;
     c->ctr["hash_cells"] = nCells;
 }
@@ -1414,8 +1466,8 @@ void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
         }
         out.count = c->counters.p;
         CIPC_CUDA(cudaMemsetAsync(c->counters.p, 0, 16 * sizeof(u32), c->st));
-        CIPC_LAUNCH(k_pairs<CCD>, div_up((size_t)(e1 - e0) * 32, 256), 256, 0, c->st, c->T, c->X.p, c->P.p, dist, c->keys.p, c->vals.p,
-            c->ks.p, e0, e1, c->boxLo.p, c->fine.p, H.G, out);
+        CIPC_LAUNCH(k_pairs<CCD>, div_up(e1 - e0, PAIRS_WARPS), PAIRS_WARPS * 32, 0, c->st, c->T, c->X.p, c->P.p, dist, c->vals.p, c->ks.p,
+            c->codes.p, e0, e1, out);
         CIPC_CUDA(cudaMemcpyAsync(counts, c->counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         bool ok = true;
