@@ -293,6 +293,18 @@ class ContactContext:
     def friction_gradient_dev(self, epsvh2, mu, accumulate=True):
         self._ck(self.L.cipc_friction_gradient_dev(self.h, C.c_double(epsvh2), C.c_double(mu), int(accumulate)))
 
+    # ---- device-resident line search
+    def save_positions(self):
+        self._ck(self.L.cipc_save_positions(self.h))
+
+    def step_positions(self, alpha):
+        self._ck(self.L.cipc_step_positions(self.h, C.c_double(alpha)))
+
+    def get_positions(self):
+        X = np.zeros((self.nV, 3))
+        self._ck(self.L.cipc_get_positions(self.h, _p(X, C.c_double), 24))
+        return X
+
     # ---- device-resident variants (results stay in HBM)
     def barrier_energy_dev(self, dHat2, kappa, thickness, elasticIPC=False):
         k = (C.c_double * 3)(*[float(x) for x in kappa])
@@ -301,6 +313,19 @@ class ContactContext:
     def barrier_gradient_dev(self, dHat2, kappa, thickness, elasticIPC=False):
         k = (C.c_double * 3)(*[float(x) for x in kappa])
         self._ck(self.L.cipc_barrier_gradient_dev(self.h, int(elasticIPC), C.c_double(dHat2), k, C.c_double(thickness)))
+
+    def barrier_hessian_dev(self, dHat2, kappa, thickness, projectSPD=True, elasticIPC=False):
+        """blocks computed and expanded on the device in one fused pass; the stream stays in HBM (dev_triplets)"""
+        k = (C.c_double * 3)(*[float(x) for x in kappa])
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_barrier_hessian_dev(self.h, int(elasticIPC), C.c_double(dHat2), k, C.c_double(thickness), int(projectSPD), C.byref(n)))
+        return n.value
+
+    def get_triplets(self, n):
+        trip = np.zeros(n, TRIPLET_DTYPE)
+        if n:
+            self._ck(self.L.cipc_get_triplets(self.h, trip.ctypes.data_as(C.c_void_p)))
+        return trip
 
     def step_size_dev(self, thickness, stepSize=1.0, elasticIPC=False):
         self._ck(self.L.cipc_step_size_dev(self.h, int(elasticIPC), C.c_double(thickness), C.c_double(stepSize)))

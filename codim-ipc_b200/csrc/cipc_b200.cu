@@ -243,15 +243,33 @@ struct Slab {
     int axis, s0, s1;
 };
 __device__ __forceinline__ int uax(u64 p, int axis) { return axis == 0 ? ux(p) : (axis == 1 ? uy(p) : uz(p)); }
-// entries per voxel layer along the slab axis (summed over all primitives): the host balances slabs on it
-__global__ void k_slab_hist(int nP, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, int axis, u32* hist)
+// entries per voxel layer along the slab axis (summed over all primitives): the host balances slabs on it.
+// The few hundred bins would serialise millions of global atomics on a handful of L2 lines, so each CTA first
+// accumulates in shared memory (consecutive primitives are spatial neighbours: a CTA touches a few bins) and flushes
+// only its non-zero bins.
+constexpr int SLAB_SMEM_BINS = 8192;
+__global__ void __launch_bounds__(256) k_slab_hist(int nP, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, int axis, int nl, u32* hist)
 {
+    __shared__ u32 sh[SLAB_SMEM_BINS];
+    const bool priv = nl <= SLAB_SMEM_BINS;
+    if (priv) {
+        for (int i = threadIdx.x; i < nl; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+    }
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nP) return;
-    const u64 a = boxLo[g], b = boxHi[g];
-    const u32 ex[3] = {(u32)(ux(b) - ux(a) + 1), (u32)(uy(b) - uy(a) + 1), (u32)(uz(b) - uz(a) + 1)};
-    const u32 per = (axis == 0) ? ex[1] * ex[2] : (axis == 1 ? ex[0] * ex[2] : ex[0] * ex[1]);
-    for (int i = uax(a, axis); i <= uax(b, axis); ++i) atomicAdd(&hist[i], per);
+    if (g < nP) {
+        const u64 a = boxLo[g], b = boxHi[g];
+        const u32 ex[3] = {(u32)(ux(b) - ux(a) + 1), (u32)(uy(b) - uy(a) + 1), (u32)(uz(b) - uz(a) + 1)};
+        const u32 per = (axis == 0) ? ex[1] * ex[2] : (axis == 1 ? ex[0] * ex[2] : ex[0] * ex[1]);
+        for (int i = uax(a, axis); i <= uax(b, axis); ++i) atomicAdd(priv ? &sh[i] : &hist[i], per);
+    }
+    if (priv) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+            const u32 v = sh[i];
+            if (v) atomicAdd(&hist[i], v);
+        }
+    }
 }
 __global__ void k_clip_counts(int nP, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, Slab sl, u32* cnt)
 {
@@ -501,7 +519,8 @@ __device__ __forceinline__ void push4(int4* buf, u32* ctr, int4 v)
     base = g.shfl(base, 0);
     buf[base + g.thread_rank()] = v;
 }
-// IPC.h:189-257
+// IPC.h:189-257.  The closest-feature type selects the operands first, so a warp runs at most three distance bodies
+// (point-point, point-edge, point-triangle) instead of one per type; the arithmetic of each body is unchanged.
 __global__ void k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,25 +530,37 @@ __global__ void k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* _
     const int4 t = T.BT[c.y];
     const xv3 p = ldx(X, vI), t0 = ldx(X, t.x), t1 = ldx(X, t.y), t2 = ldx(X, t.z);
     const xd dHat2(dHat2_);
+    const int ty = pt_type(p, t0, t1, t2);
     int4 r;
     xd d;
-    bool isPass = false;
-    switch (pt_type(p, t0, t1, t2)) {
-    case 0: d = pp_dist2(p, t0); r = make_int4(-vI - 1, t.x, -1, -1); break;
-    case 1: d = pp_dist2(p, t1); r = make_int4(-vI - 1, t.y, -1, -1); break;
-    case 2: d = pp_dist2(p, t2); r = make_int4(-vI - 1, t.z, -1, -1); break;
-    case 3: d = pe_dist2(p, t0, t1); r = make_int4(-vI - 1, t.x, t.y, -1); break;
-    case 4: d = pe_dist2(p, t1, t2); r = make_int4(-vI - 1, t.y, t.z, -1); break;
-    case 5: d = pe_dist2(p, t2, t0); r = make_int4(-vI - 1, t.z, t.x, -1); break;
-    default: d = pt_dist2(p, t0, t1, t2); r = make_int4(-vI - 1, t.x, t.y, t.z); isPass = true; break;
+    if (ty == 6) { d = pt_dist2(p, t0, t1, t2); r = make_int4(-vI - 1, t.x, t.y, t.z); }
+    else if (ty >= 3) {
+        const bool e3 = ty == 3, e4 = ty == 4;
+        const xv3 e0 = e3 ? t0 : (e4 ? t1 : t2), e1 = e3 ? t1 : (e4 ? t2 : t0);
+        d = pe_dist2(p, e0, e1);
+        r = make_int4(-vI - 1, e3 ? t.x : (e4 ? t.y : t.z), e3 ? t.y : (e4 ? t.z : t.x), -1);
+    }
+    else {
+        const xv3 q = ty == 0 ? t0 : (ty == 1 ? t1 : t2);
+        d = pp_dist2(p, q);
+        r = make_int4(-vI - 1, ty == 0 ? t.x : (ty == 1 ? t.y : t.z), -1, -1);
     }
     if (d < dHat2) {
-        if (isPass) push4(out.pass, &out.count[0], r);
+        if (ty == 6) push4(out.pass, &out.count[0], r);
         else push4(out.raw, &out.count[1], r);
     }
 }
+// rest length^2 per boundary edge: the mollifier threshold 1e-3 |ea|^2 |eb|^2 (EDGE_EDGE_MOLLIFIER.h:582-592) only
+// depends on it, which saves the four rest-position gathers per edge-edge candidate
+__global__ void k_rest_len2(const double4* __restrict__ X0, const int2* __restrict__ BE, int nBE, double* __restrict__ out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nBE) return;
+    const int2 ed = BE[e];
+    out[e] = norm2(ldx(X0, ed.x) - ldx(X0, ed.y)).v;
+}
 // IPC.h:414-564
-__global__ void k_narrow_ee(Topo T, const double4* __restrict__ X, const double4* __restrict__ X0, const int2* __restrict__ cand, u32 n,
+__global__ void k_narrow_ee(Topo T, const double4* __restrict__ X, const double* __restrict__ restLen2, const int2* __restrict__ cand, u32 n,
     double dHat2_, NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,20 +570,29 @@ __global__ void k_narrow_ee(Topo T, const double4* __restrict__ X, const double4
     const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y), b0 = ldx(X, b.x), b1 = ldx(X, b.y);
     const xd dHat2(dHat2_);
     const xd cn2 = ee_cross_norm2(a0, a1, b0, b1);
-    const xd eps_x = ee_mollifier_threshold(ldx(X0, a.x), ldx(X0, a.y), ldx(X0, b.x), ldx(X0, b.y));
+    const xd eps_x = xd(1.0e-3) * xd(restLen2[c.x]) * xd(restLen2[c.y]);
     const bool mol = cn2 < eps_x;
+    const int ty = ee_type(a0, a1, b0, b1);
     int4 r;
     xd d;
-    switch (ee_type(a0, a1, b0, b1)) {
-    case 0: d = pp_dist2(a0, b0); r = mol ? make_int4(a.x, b.x, -a.y - 1, -b.y - 1) : make_int4(-a.x - 1, b.x, -1, -1); break;
-    case 1: d = pp_dist2(a0, b1); r = mol ? make_int4(a.x, b.y, -a.y - 1, -b.x - 1) : make_int4(-a.x - 1, b.y, -1, -1); break;
-    case 2: d = pe_dist2(a0, b0, b1); r = mol ? make_int4(a.x, b.x, b.y, -a.y - 1) : make_int4(-a.x - 1, b.x, b.y, -1); break;
-    case 3: d = pp_dist2(a1, b0); r = mol ? make_int4(a.y, b.x, -a.x - 1, -b.y - 1) : make_int4(-a.y - 1, b.x, -1, -1); break;
-    case 4: d = pp_dist2(a1, b1); r = mol ? make_int4(a.y, b.y, -a.x - 1, -b.x - 1) : make_int4(-a.y - 1, b.y, -1, -1); break;
-    case 5: d = pe_dist2(a1, b0, b1); r = mol ? make_int4(a.y, b.x, b.y, -a.x - 1) : make_int4(-a.y - 1, b.x, b.y, -1); break;
-    case 6: d = pe_dist2(b0, a0, a1); r = mol ? make_int4(b.x, a.x, a.y, -b.y - 1) : make_int4(-b.x - 1, a.x, a.y, -1); break;
-    case 7: d = pe_dist2(b1, a0, a1); r = mol ? make_int4(b.y, a.x, a.y, -b.x - 1) : make_int4(-b.y - 1, a.x, a.y, -1); break;
-    default: d = ee_dist2(a0, a1, b0, b1); r = mol ? make_int4(a.x, a.y, -b.x - 1, b.y) : make_int4(a.x, a.y, b.x, b.y); break;
+    if (ty == 8) {
+        d = ee_dist2(a0, a1, b0, b1);
+        r = mol ? make_int4(a.x, a.y, -b.x - 1, b.y) : make_int4(a.x, a.y, b.x, b.y);
+    }
+    else if (ty == 2 || ty >= 5) { // point-edge: 2 (a0; b), 5 (a1; b), 6 (b0; a), 7 (b1; a)
+        const bool onB = ty <= 5;   // the edge is b
+        const xv3 p = ty == 2 ? a0 : (ty == 5 ? a1 : (ty == 6 ? b0 : b1));
+        const int pv = ty == 2 ? a.x : (ty == 5 ? a.y : (ty == 6 ? b.x : b.y));
+        const int po = ty == 2 ? a.y : (ty == 5 ? a.x : (ty == 6 ? b.y : b.x)); // the other end of the point's edge
+        d = pe_dist2(p, onB ? b0 : a0, onB ? b1 : a1);
+        const int e0 = onB ? b.x : a.x, e1 = onB ? b.y : a.y;
+        r = mol ? make_int4(pv, e0, e1, -po - 1) : make_int4(-pv - 1, e0, e1, -1);
+    }
+    else { // point-point: 0 (a0,b0), 1 (a0,b1), 3 (a1,b0), 4 (a1,b1)
+        const bool fa = ty < 3, fb = (ty == 0 || ty == 3);
+        d = pp_dist2(fa ? a0 : a1, fb ? b0 : b1);
+        const int pa = fa ? a.x : a.y, oa = fa ? a.y : a.x, pb = fb ? b.x : b.y, ob = fb ? b.y : b.x;
+        r = mol ? make_int4(pa, pb, -oa - 1, -ob - 1) : make_int4(-pa - 1, pb, -1, -1);
     }
     if (d < dHat2) {
         if (r.x >= 0) push4(out.pass, &out.count[0], r);
@@ -1024,6 +1064,93 @@ __global__ void __launch_bounds__(256) k_hessian_expand_tiled(const double* __re
         if (STREAM) __stcs(dst, o); else *dst = o;
     }
 }
+// Fused factor + expansion for the device-resident triplet stream: a CTA of 128 threads factors 128 stencils (FP64
+// pipe, one stencil per thread), parks the factors in shared memory, and then all threads turn them into triplets with
+// coalesced streaming 16-byte stores (HBM).  CTAs resident on one SM are in different phases, so the FP64 work of one
+// overlaps the store stream of another, and the factors never travel through HBM (-3.3 GB per launch at 1M triangles).
+// The factor-only kernel above stays in use when the triplets are delivered to the HOST (compact factors cross PCIe).
+constexpr int FUSED_BD = 128;
+template <int CLS> struct FusedShape {
+    static constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, YD = NY * NN;
+    static constexpr int YS = (YD % 2 == 0) ? YD + 1 : YD; // odd stride: conflict-free 8-byte accesses, one stencil per lane
+    static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
+};
+template <int CLS>
+__global__ void __launch_bounds__(FUSED_BD, 3) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
+    const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
+    cipc_triplet* __restrict__ trip, u32* denseList, u32* denseCount)
+{
+    constexpr int NN = FusedShape<CLS>::NN, NY = FusedShape<CLS>::NY, YS = FusedShape<CLS>::YS, PER = NN * NN;
+    extern __shared__ __align__(16) unsigned char fused_sm[];
+    double* sY = reinterpret_cast<double*>(fused_sm);
+    int* sH = reinterpret_cast<int*>(fused_sm + FUSED_BD * YS * 8);
+    const u32 q0 = blockIdx.x * FUSED_BD;
+    const u32 g = min((u32)FUSED_BD, n - q0);
+    if (threadIdx.x < g) {
+        const u32 i = idx[q0 + threadIdx.x];
+        const Stencil s = decode(cs[i]);
+        const double wm = info[i].x * (double)s.mult;
+        const double d = stencil_dist2(X, s) - bp.thickness2;
+        const double alpha = wm * barrier_H(bp.elastic, d, bp.dHat2, bp.k0);
+        const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
+        int* h = sH + threadIdx.x * 8;
+        h[1] = s.v[0]; h[2] = s.v[1]; h[3] = s.v[2]; h[4] = s.v[3];
+        if (!(beta < 0.0) || !(alpha > 0.0)) { // outside the barrier's support: dense path (see k_hessian_factor)
+            h[0] = (int)0xffffffffu;
+            denseList[atomicAdd(denseCount, 1u)] = i;
+        }
+        else {
+            h[0] = (int)off[i];
+            double Y[NY * NN];
+            if (CLS == 0) {
+                const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+                hess4_factor(s.kind == K_EE, x, alpha, beta, Y);
+            }
+            else if (CLS == 1) hess_pe_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), alpha, beta, Y);
+            else hess_pp_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), alpha, beta, Y);
+            double* y = sY + threadIdx.x * YS;
+#pragma unroll
+            for (int k = 0; k < NY * NN; ++k) y[k] = Y[k];
+        }
+    }
+    // Expansion, warp by warp: every warp expands the 32 stencils its own lanes just factored (no CTA barrier: warps
+    // stay decoupled, so one warp's store stream overlaps the others' FP64 work).  Lane l owns the fixed block entries
+    // e = l + 32 j of every stencil; (row, col) decoding is hoisted out of the stencil loop and a warp writes 512
+    // contiguous bytes per store instruction.
+    __syncwarp();
+    const u32 lane = threadIdx.x & 31u, wq0 = threadIdx.x & ~31u;
+    constexpr int NJ = (PER + 31) / 32;
+    int rI[NJ], cI[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int e = (int)lane + 32 * j;
+        rI[j] = e / NN; cI[j] = e - rI[j] * NN;
+    }
+    const u32 wn = (wq0 < g) ? min(32u, g - wq0) : 0u;
+    for (u32 qq = 0; qq < wn; ++qq) {
+        const int* h = sH + (wq0 + qq) * 8;
+        const u32 o = (u32)h[0];
+        if (o == 0xffffffffu) continue;
+        const double* y = sY + (wq0 + qq) * YS;
+        cipc_triplet* dst = trip + (size_t)o * 9;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int e = (int)lane + 32 * j;
+            if (NJ * 32 == PER || e < PER) {
+                const int r = rI[j], c = cI[j];
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
+                const int ri = r / 3, ci = c / 3;
+                int4 w;
+                w.x = h[1 + ri] * 3 + (r - 3 * ri); w.y = h[1 + ci] * 3 + (c - 3 * ci);
+                const long long bb = __double_as_longlong(v);
+                w.z = (int)(bb & 0xffffffffLL); w.w = (int)(bb >> 32);
+                __stcs(reinterpret_cast<int4*>(dst + e), w);
+            }
+        }
+    }
+}
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 constexpr int DENSE_BD = 64;                              // threads per block of the dense path
 constexpr int DENSE_SMEM = 2 * 81 * DENSE_BD * 8;         // 9x9 matrix + eigenvectors per thread
@@ -1166,6 +1293,14 @@ __global__ void k_pack_tris(const int* __restrict__ src, int stride, int n, int4
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = make_int4(src[(size_t)i * stride], src[(size_t)i * stride + 1], src[(size_t)i * stride + 2], 0);
 }
+// line-search trial positions x = xprev + alpha p (Shell/IMPLICIT_EULER.h:102-109), rounded like the unfused host expression
+__global__ void k_step_positions(const double4* __restrict__ Xprev, const double4* __restrict__ P, double alpha, int n, double4* __restrict__ X)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 a = Xprev[i], p = P[i];
+    X[i] = make_double4(__dadd_rn(a.x, __dmul_rn(alpha, p.x)), __dadd_rn(a.y, __dmul_rn(alpha, p.y)), __dadd_rn(a.z, __dmul_rn(alpha, p.z)), 0.0);
+}
 __global__ void k_fill_u32(u32* p, size_t n, u32 v)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1199,9 +1334,9 @@ struct cipc_ctx {
     DevBuf<u64> nnx;
     DevBuf<double> BNArea, BEArea, BTArea;
     // state
-    DevBuf<double4> X, X0, P;
-    bool haveX = false, haveX0 = false, haveP = false;
-    DevBuf<double> stageD;
+    DevBuf<double4> X, X0, P, Xprev;
+    bool haveX = false, haveX0 = false, haveP = false, haveXprev = false;
+    DevBuf<double> stageD, restLen2;
     // hash
     DevBuf<u64> boxLo, boxHi, nodeLo, nodeHi;
     DevBuf<ulonglong2> fine, nodeFine;
@@ -1233,7 +1368,7 @@ struct cipc_ctx {
     int ny[3] = {3, 2, 1};  // factor vectors per stencil of class 0/1/2: barrier {3,2,1}, friction {2,2,2}
     DevBuf<cipc_triplet> denseBuf;
     DevBuf<uint2> denseMeta;
-    PinnedBuf pinY, pinH, pinD, pinM;
+    PinnedBuf pinY, pinH, pinD, pinM, pinSmall;
     DevBuf<double4> yhdr; // YHdr records (32 B each)
     int64_t nTrip = 0;
     PinnedBuf pin;
@@ -1384,12 +1519,12 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
         const int nl = gd[sl.axis];
         c->slabHist.reserve(nl, c->st);
         CIPC_CUDA(cudaMemsetAsync(c->slabHist.p, 0, (size_t)nl * 4, c->st));
-        CIPC_LAUNCH(k_slab_hist, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl.axis, c->slabHist.p);
-        std::vector<u32> hist(nl);
-        CIPC_CUDA(cudaMemcpyAsync(hist.data(), c->slabHist.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, c->st));
+        CIPC_LAUNCH(k_slab_hist, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl.axis, nl, c->slabHist.p);
+        const u32* hist = (const u32*)c->pinSmall.reserve((size_t)nl * 4);
+        CIPC_CUDA(cudaMemcpyAsync((void*)hist, c->slabHist.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         double total = 0;
-        for (u32 v : hist) total += v;
+        for (int i = 0; i < nl; ++i) total += hist[i];
         auto bound = [&](int r) { // first layer whose prefix reaches total * r / world
             if (r <= 0) return 0;
             if (r >= c->world) return nl;
@@ -1859,6 +1994,9 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
         c->errFlag.reserve(1, c->st);
         CIPC_CUDA(cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->st));
         CIPC_CUDA(cudaFuncSetAttribute(k_barrier_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<0>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<1>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<2>::SMEM));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
     }
     catch (const std::exception& e) {
@@ -1972,7 +2110,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         CIPC_CUDA(cudaStreamSynchronize(c->st)); // host vectors above go out of scope
         T.BN = c->BN.p; T.BE = c->BE.p; T.BT = c->BT.p; T.flags = c->flags.p; T.v2sv = c->v2sv.p; T.nnx = c->nnx.p; T.nNnx = nNnx;
         c->topoHash = h;
-        c->haveX = c->haveX0 = c->haveP = c->haveXn = false;
+        c->haveX = c->haveX0 = c->haveP = c->haveXn = c->haveXprev = false;
         c->nC = 0;
         c->nF = 0;
         return (int)CIPC_OK;
@@ -1992,6 +2130,8 @@ int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes)
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
         upload_vec3(ctx, ctx->X0, X0, stride_bytes);
+        ctx->restLen2.reserve(std::max(ctx->T.nBE, 1), ctx->st);
+        if (ctx->T.nBE) CIPC_LAUNCH(k_rest_len2, div_up(ctx->T.nBE, TB), TB, 0, ctx->st, ctx->X0.p, ctx->BE.p, ctx->T.nBE, ctx->restLen2.p);
         ctx->haveX0 = true;
         return (int)CIPC_OK;
     });
@@ -2052,7 +2192,7 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             CIPC_CUDA(cudaMemsetAsync(c->counters.p + 8, 0, 4 * sizeof(u32), c->st));
             NarrowOut out{c->cs.p, c->raw.p, c->counters.p + 8};
             if (counts[0]) CIPC_LAUNCH(k_narrow_pt, div_up(counts[0], 128), 128, 0, c->st, T, c->X.p, c->cand[0].p, counts[0], dHat2o, out);
-            if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->X0.p, c->cand[1].p, counts[1], dHat2o, out);
+            if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->restLen2.p, c->cand[1].p, counts[1], dHat2o, out);
             if (counts[2]) CIPC_LAUNCH(k_narrow_pe, div_up(counts[2], 128), 128, 0, c->st, T, c->X.p, c->cand[2].p, counts[2], dHat2o, out);
             if (counts[3]) CIPC_LAUNCH(k_narrow_pp, div_up(counts[3], 128), 128, 0, c->st, T, c->X.p, c->cand[3].p, counts[3], dHat2o, out);
             CIPC_CUDA(cudaMemcpyAsync(hc, c->counters.p + 8, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
@@ -2150,8 +2290,8 @@ int cipc_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double
         return (int)CIPC_OK;
     });
 }
-int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
-    int64_t* nTrip)
+static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
+    int64_t* nTrip, bool devTriplets)
 {
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
@@ -2184,7 +2324,26 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
                 u32 nk[4];
                 CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
                 CIPC_CUDA(cudaStreamSynchronize(c->st));
-                if (projectSPD) {
+                if (projectSPD && devTriplets) {
+                    // device-resident triplets: fused factor + expansion, the factors never leave the SM
+                    u32* dl = c->clsIdx[3].p; u32* dn = c->counters.p + 15;
+                    {
+                        cipc_ctx::Scope sk(c, "k_hessian_fused0"); // the longest launch of the stage: PT/EE blocks
+                        if (nk[0]) CIPC_LAUNCH(k_hessian_fused<0>, div_up(nk[0], FUSED_BD), FUSED_BD, FusedShape<0>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
+                            c->tripOff.p, c->clsIdx[0].p, nk[0], bp, c->trip.p, dl, dn);
+                    }
+                    {
+                        cipc_ctx::Scope sk(c, "k_hessian_fused12");
+                        if (nk[1]) CIPC_LAUNCH(k_hessian_fused<1>, div_up(nk[1], FUSED_BD), FUSED_BD, FusedShape<1>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
+                            c->tripOff.p, c->clsIdx[1].p, nk[1], bp, c->trip.p, dl, dn);
+                        if (nk[2]) CIPC_LAUNCH(k_hessian_fused<2>, div_up(nk[2], FUSED_BD), FUSED_BD, FusedShape<2>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
+                            c->tripOff.p, c->clsIdx[2].p, nk[2], bp, c->trip.p, dl, dn);
+                    }
+                    for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
+                    CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
+                        (const u32*)dn, bp, projectSPD, c->trip.p);
+                }
+                else if (projectSPD) {
                     // (A) factor, (B) expand; stencils the factor kernels reject are appended to the dense list
                     const size_t ydoubles = (size_t)nk[0] * 36 + (size_t)nk[1] * 18 + (size_t)nk[2] * 6;
                     c->Y.reserve(ydoubles + 4, c->st);
@@ -2227,6 +2386,16 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double 
         if (nTrip) *nTrip = c->nTrip;
         return (int)CIPC_OK;
     });
+}
+int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
+    int64_t* nTrip)
+{
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, false);
+}
+int cipc_barrier_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
+    int64_t* nTrip)
+{
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, true);
 }
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 {
@@ -2409,6 +2578,48 @@ int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSP
         int r = do_friction_hessian(ctx, epsvh2, mu);
         if (nTrip) *nTrip = ctx->nTrip;
         return r;
+    });
+}
+
+// ---- device-resident line search: Shell/IMPLICIT_EULER.h:102-131 without a position upload per trial
+int cipc_save_positions(cipc_ctx* ctx)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->haveX, "positions not set");
+        c->Xprev.reserve(c->T.nV, c->st);
+        CIPC_CUDA(cudaMemcpyAsync(c->Xprev.p, c->X.p, (size_t)c->T.nV * 32, cudaMemcpyDeviceToDevice, c->st));
+        c->haveXprev = true;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_step_positions(cipc_ctx* ctx, double alpha)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->haveXprev && c->haveP, "saved positions / search direction not set");
+        CIPC_LAUNCH(k_step_positions, div_up(c->T.nV, TB), TB, 0, c->st, c->Xprev.p, c->P.p, alpha, c->T.nV, c->X.p);
+        c->haveX = true;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_get_positions(cipc_ctx* ctx, double* X, int stride_bytes)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->haveX, "positions not set");
+        if (stride_bytes != 32 && stride_bytes != 24) return (int)CIPC_ERR_ARG;
+        const size_t n = (size_t)c->T.nV;
+        if (stride_bytes == 32) {
+            CIPC_CUDA(cudaMemcpyAsync(X, c->X.p, n * 32, cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+            return (int)CIPC_OK;
+        }
+        double* h = (double*)c->pin.reserve(n * 32);
+        CIPC_CUDA(cudaMemcpyAsync(h, c->X.p, n * 32, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        for (size_t v = 0; v < n; ++v) { X[3 * v] = h[4 * v]; X[3 * v + 1] = h[4 * v + 1]; X[3 * v + 2] = h[4 * v + 2]; }
+        return (int)CIPC_OK;
     });
 }
 

@@ -347,7 +347,13 @@ CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, doub
 #pragma unroll
         for (int j = i; j < 5; ++j) fro += (i == j ? 1.0 : 2.0) * A[i][j] * A[i][j];
     const double tol = 1e-26 * fro; // off-diagonal norm <= 1e-13 ||M||: eigenvector error far below the 1e-9 gate
-    for (int sweep = 0; sweep < 10; ++sweep) {
+    // Rotation angles are formed in fp32 (MUFU reciprocal / rsqrt on entries scaled by 1/||M||): an fp64 division and
+    // square root cost more instructions than applying the rotation.  The rotation itself stays orthogonal to fp64
+    // rounding (c = rsqrt(1 + t^2), s = t c in fp64) and is applied as an exact similarity transform (a_pq is updated,
+    // not zeroed), so an angle error of 1e-7 only leaves a_pq' ~ 1e-7 a_pq: the sweeps still converge quadratically
+    // down to the fp64 tolerance above, which is what bounds the result's accuracy.
+    const double iscale = cipc_rsqrt(fro);
+    for (int sweep = 0; sweep < 12; ++sweep) {
         double off = 0.0;
 #pragma unroll
         for (int p = 0; p < 4; ++p)
@@ -360,12 +366,20 @@ CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, doub
             for (int q = p + 1; q < 5; ++q) {
                 const double apq = A[p][q];
                 if (apq * apq > 1e-34 * fro) {
-                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double app = A[p][p], aqq = A[q][q];
+                    const float df = (float)((aqq - app) * iscale), af = (float)(apq * iscale) * 2.0f;
+#if defined(__CUDA_ARCH__)
+                    const float h2 = fmaf(df, df, af * af);
+                    const float tf = __fdividef(df >= 0.0f ? af : -af, fabsf(df) + h2 * rsqrtf(h2));
+#else
+                    const float tf = (df >= 0.0f ? af : -af) / (fabsf(df) + sqrtf(df * df + af * af));
+#endif
+                    const double t = (double)tf;
                     const double c = cipc_rsqrt(t * t + 1.0), sn = t * c;
-                    A[p][p] -= t * apq;
-                    A[q][q] += t * apq;
-                    A[p][q] = 0.0;
+                    const double cc = c * c, ss = sn * sn, cs = c * sn;
+                    A[p][p] = cc * app - 2.0 * cs * apq + ss * aqq;
+                    A[q][q] = ss * app + 2.0 * cs * apq + cc * aqq;
+                    A[p][q] = cs * (app - aqq) + (cc - ss) * apq;
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         if (k != p && k != q) { // upper-triangle accessors with compile-time indices

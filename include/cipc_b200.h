@@ -127,6 +127,16 @@ int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSP
 int cipc_friction_energy_dev(cipc_ctx* ctx, double epsvh2, double mu);
 int cipc_friction_gradient_dev(cipc_ctx* ctx, double epsvh2, double mu, int accumulate);
 
+/* ---- device-resident line search ------------------------------------------------------------
+ * Shell/IMPLICIT_EULER.h:102-131 evaluates X = Xprev + alpha p, Compute_Constraint_Set and Compute_Min_Dist2 per
+ * trial step; with these three calls the trial positions never cross PCIe:
+ *   cipc_save_positions  : Xprev <- the resident positions (call once per line search, after cipc_set_positions)
+ *   cipc_step_positions  : resident X <- Xprev + alpha * (resident search direction), unfused multiply-add
+ *   cipc_get_positions   : copies the resident positions out (stride 32 or 24) once a step has been accepted */
+int cipc_save_positions(cipc_ctx* ctx);
+int cipc_step_positions(cipc_ctx* ctx, double alpha);
+int cipc_get_positions(cipc_ctx* ctx, double* X, int stride_bytes);
+
 /* ---- device-resident access (multi-GPU reductions, benchmarking) ----------------------------- */
 double* cipc_dev_positions(cipc_ctx* ctx);      /* nV x 4 doubles (x,y,z,pad) */
 double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient_dev */
@@ -134,6 +144,11 @@ double* cipc_dev_scalars(cipc_ctx* ctx);        /* [0]=barrier energy, [1]=step 
 /* same stages with every result left on the device (no D2H): */
 int cipc_barrier_energy_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
 int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
+/* Compute_Barrier_Hessian with the (row, col, value) stream left in HBM (cipc_dev_triplets): factoring and expansion
+ * run fused in one kernel per stencil class, the factors never travel through HBM.  cipc_get_triplets afterwards copies
+ * the expanded stream over PCIe. */
+int cipc_barrier_hessian_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
+                             int projectSPD, int64_t* nTriplets_out);
 int cipc_step_size_dev(cipc_ctx* ctx, int elasticIPC, double thickness, double stepSize_in);
 int cipc_min_dist2_dev(cipc_ctx* ctx, double thickness);
 int cipc_sync(cipc_ctx* ctx);

@@ -96,3 +96,36 @@ def test_triplet_delivery_paths_agree(ctx, monkeypatch):
     from helpers import max_block_rel_err
     cs, _ = ctx.get_constraints()
     assert max_block_rel_err(cs, a["val"], c["val"]) <= 1e-10
+
+
+def test_device_resident_line_search(ctx):
+    """X = Xprev + alpha p formed on the device gives the same constraint set / min distance as uploading
+    the host-formed trial positions (Shell/IMPLICIT_EULER.h:102-131), bit for bit"""
+    from codim_ipc_b200 import scenes
+    sc = scenes.cloth_stack(24, 4)
+    ctx.set_scene(sc)
+    ctx.save_positions()
+    for alpha in (0.5, 0.125):
+        ctx.step_positions(alpha)
+        Xt = sc["X"] + alpha * sc["p"]
+        assert np.array_equal(ctx.get_positions(), Xt)
+        cs_d = sort_cs(ctx.constraint_set(sc["dHat2"], sc["xi"])[0])
+        d_d, m_d = ctx.min_dist2(sc["xi"])
+        ctx.set_positions(Xt)
+        cs_h = sort_cs(ctx.constraint_set(sc["dHat2"], sc["xi"])[0])
+        d_h, m_h = ctx.min_dist2(sc["xi"])
+        assert np.array_equal(cs_d, cs_h) and m_d == m_h and len(cs_d) > 0
+
+
+def test_fused_device_hessian_equals_factor_path(ctx):
+    """cipc_barrier_hessian_dev (fused factor + expansion, stream left in HBM) == factor kernel + host expansion"""
+    from codim_ipc_b200 import scenes
+    for sc in (scenes.mixed_small(), scenes.cloth_stack(20, 4)):
+        ctx.set_scene(sc)
+        ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+        a = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True).copy()
+        n = ctx.barrier_hessian_dev(sc["dHat2"], sc["kappa"], sc["xi"], True)
+        assert ctx.dev_triplets()
+        b = ctx.get_triplets(n)
+        assert n == len(a) > 0 and np.array_equal(a["row"], b["row"]) and np.array_equal(a["col"], b["col"])
+        assert np.abs(a["val"] - b["val"]).max() <= 1e-13 * np.abs(a["val"]).max()
