@@ -387,8 +387,29 @@ __device__ __forceinline__ bool code_pair_ok(const uint2 a, const uint2 b)
     return (ov & 0x00ffffffu) == 0x00ffffffu && (((a.x | b.x) >> 24) & 7u) == 7u;
 }
 
-// One WARP per voxel cell in [c0, c1).  Phase 1 (cheap, all lanes busy): the queries of the cell (points, then edges)
-// are walked in order and the 32 lanes test 32 targets of the run at a time on the entry codes; survivors (~1 in 8)
+// Work items of the pair enumeration: a cell's point queries and edge queries are cut into tasks of PAIRS_QCH queries,
+// one warp per task, so a crowded cell (hundreds of particles in one voxel of a granular pile) is spread over many
+// warps instead of serialising on one.  cnt[c] = tasks of cell c; desc[] = (cell, task index within the cell).
+constexpr u32 PAIRS_QCH = 16;
+__device__ __forceinline__ u32 cell_point_tasks(u32 p0, u32 e0) { return (e0 - p0 + PAIRS_QCH - 1) / PAIRS_QCH; }
+__device__ __forceinline__ u32 cell_edge_tasks(u32 e0, u32 t0) { return t0 > e0 + 1 ? (t0 - e0 - 1 + PAIRS_QCH - 1) / PAIRS_QCH : 0u; }
+__global__ void k_task_counts(const u32* __restrict__ ks, u32 nCells, u32* __restrict__ cnt)
+{
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    const u32 p0 = ks[c * 4], e0 = ks[c * 4 + 1], t0 = ks[c * 4 + 2];
+    cnt[c] = cell_point_tasks(p0, e0) + cell_edge_tasks(e0, t0);
+}
+__global__ void k_task_desc(const u32* __restrict__ ks, u32 nCells, const u32* __restrict__ off, uint2* __restrict__ desc)
+{
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    const u32 p0 = ks[c * 4], e0 = ks[c * 4 + 1], t0 = ks[c * 4 + 2];
+    const u32 n = cell_point_tasks(p0, e0) + cell_edge_tasks(e0, t0), o = off[c];
+    for (u32 k = 0; k < n; ++k) desc[o + k] = make_uint2(c, k);
+}
+// One WARP per task (<= PAIRS_QCH point queries or edge queries of one voxel cell).  Phase 1 (cheap, all lanes busy): the
+// queries are walked in order and the 32 lanes test 32 targets of the run at a time on the entry codes; survivors
 // are appended to a per-warp ring buffer in shared memory.  Phase 2 (expensive, all lanes busy): whenever the buffer
 // holds 32 pairs, each lane takes one: topology filters, coordinate gathers and the reference's exact AABB test.
 // Without the queue the expensive path ran for every chunk with ~4 of 32 lanes active.
@@ -397,15 +418,23 @@ __device__ __forceinline__ bool code_pair_ok(const uint2 a, const uint2 b)
 constexpr int PAIRS_WARPS = 8;
 template <bool CCD>
 __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double dist_,
-    const u32* __restrict__ vals, const u32* __restrict__ ks, const uint2* __restrict__ codes, u32 c0, u32 c1, CandOut out)
+    const u32* __restrict__ vals, const u32* __restrict__ ks, const uint2* __restrict__ codes, const uint2* __restrict__ desc,
+    const u32* __restrict__ nTasks, CandOut out)
 {
     __shared__ uint2 sq[PAIRS_WARPS][64];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u32 cellIdx = c0 + blockIdx.x * PAIRS_WARPS + warp;
-    if (cellIdx >= c1) return; // whole warp leaves; no block-level barrier below
+    const u32 task = blockIdx.x * PAIRS_WARPS + warp;
+    if (task >= *nTasks) return; // whole warp leaves; no block-level barrier below
+    const uint2 td = desc[task];
+    const u32 cellIdx = td.x;
     uint2* q = sq[warp];
     u32 head = 0, tail = 0; // warp-uniform ring indices
     const u32 p0 = ks[cellIdx * 4], e0 = ks[cellIdx * 4 + 1], t0 = ks[cellIdx * 4 + 2], end = ks[cellIdx * 4 + 3];
+    const u32 nPT = cell_point_tasks(p0, e0);
+    const bool pointTask = td.y < nPT;
+    // this task's query range [qa, qb): point entries of the cell, or edge entries (the last edge has no later partner)
+    const u32 qa = pointTask ? p0 + td.y * PAIRS_QCH : e0 + (td.y - nPT) * PAIRS_QCH;
+    const u32 qb = pointTask ? min(qa + PAIRS_QCH, e0) : min(qa + PAIRS_QCH, t0 - 1);
     const xd dist(dist_);
     const u32 ltmask = (1u << lane) - 1u;
     auto push = [&](bool pass, u32 a, u32 b) { // called by all 32 lanes
@@ -444,8 +473,9 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
             __syncwarp();
         }
     };
+    if (pointTask) {
     // ---- point queries against the triangle run
-    for (u32 i = p0; i < e0; ++i) {
+    for (u32 i = qa; i < qb; ++i) {
         const uint2 cA = codes[i];
         for (u32 jb = t0; jb < end; jb += 32) {
             const u32 j = jb + lane;
@@ -457,7 +487,7 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
     // ---- codimensional extras (rare): rod / particle points against rod edges (IPC.h:271-326; step size: particles
     //      only, :2098-2135) and particles against later boundary-node slots (IPC.h:328-352, :2137-2163)
     if (T.nRod > 0 || T.codim1 < T.nBN) {
-        for (u32 i = p0; i < e0; ++i) {
+        for (u32 i = qa; i < qb; ++i) {
             const int svI = (int)vals[i];
             if (svI < min(T.codim0, T.codim1)) continue; // warp-uniform
             const int vI = T.BN[svI];
@@ -493,8 +523,10 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
             }
         }
     }
+    return;
+    }
     // ---- edge queries: edge ids ascend inside a run, so j > i <=> eJ > eI
-    for (u32 i = e0; i + 1 < t0; ++i) {
+    for (u32 i = qa; i < qb; ++i) {
         const uint2 cA = codes[i];
         for (u32 jb = i + 1; jb < t0; jb += 32) {
             const u32 j = jb + lane;
@@ -1336,6 +1368,9 @@ struct cipc_ctx {
     // state
     DevBuf<double4> X, X0, P, Xprev;
     bool haveX = false, haveX0 = false, haveP = false, haveXprev = false;
+    u64 xVersion = 1, edgeLenVersion = 0; // bumped whenever the resident positions or the topology change
+    double edgeLenCached = 0.0;
+    bool edgeLenPending = false;
     DevBuf<double> stageD, restLen2;
     // hash
     DevBuf<u64> boxLo, boxHi, nodeLo, nodeHi;
@@ -1343,6 +1378,8 @@ struct cipc_ctx {
     DevBuf<u32> slabHist;
     DevBuf<u32> cnt, keys, vals, heads, headScan, ks;
     DevBuf<uint2> codes; // per sorted entry: cell-local pair code (k_entry_codes)
+    DevBuf<u32> taskCnt, nTasksDev;
+    DevBuf<uint2> taskDesc; // pair-enumeration tasks: (cell, task index within the cell)
     SortWork sortwk;
     ScanWork scanwk;
     DevBuf<double> partial, scal;  // scal: [0] E partial, [1] alpha, [2] min dist2, [3..] scratch
@@ -1368,7 +1405,7 @@ struct cipc_ctx {
     int ny[3] = {3, 2, 1};  // factor vectors per stencil of class 0/1/2: barrier {3,2,1}, friction {2,2,2}
     DevBuf<cipc_triplet> denseBuf;
     DevBuf<uint2> denseMeta;
-    PinnedBuf pinY, pinH, pinD, pinM, pinSmall;
+    PinnedBuf pinY, pinH, pinD, pinM, pinSmall, pinScal;
     DevBuf<double4> yhdr; // YHdr records (32 B each)
     int64_t nTrip = 0;
     PinnedBuf pin;
@@ -1472,7 +1509,7 @@ void upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int strid
 // ---- spatial hash (shared by the constraint-set and the step-size passes)
 struct HashInfo {
     GridDesc G;
-    u32 nEntries = 0, nCells = 0;
+    u32 nEntries = 0, nCells = 0, maxTasks = 0;
 };
 
 // sum of partials helper: returns value on host
@@ -1484,10 +1521,26 @@ double reduce_to_host(cipc_ctx* c, double scale)
     CIPC_CUDA(cudaStreamSynchronize(c->st));
     return v;
 }
-double mean_edge_len(cipc_ctx* c)
+// mean boundary-edge length of the resident positions; cached until the positions (or the topology) change, so the
+// step-size pass that follows a constraint-set pass on the same X saves the reduction and its host round trip.
+// edge_len_begin launches the reduction and its copy without waiting; the value is valid after the next stream sync.
+void edge_len_begin(cipc_ctx* c)
 {
+    if (c->edgeLenVersion == c->xVersion || !c->T.nBE) return;
+    double* h = (double*)c->pinScal.reserve(64);
     CIPC_LAUNCH(k_edge_len_partial, RED_GRID, RED_BT, 0, c->st, c->X.p, c->BE.p, c->T.nBE, c->partial.p);
-    return reduce_to_host(c, 1.0 / (double)c->T.nBE);
+    CIPC_LAUNCH(k_final_sum, 1, RED_BT, 0, c->st, c->partial.p, RED_GRID, c->scal.p + 5, 1.0 / (double)c->T.nBE);
+    CIPC_CUDA(cudaMemcpyAsync(h, c->scal.p + 5, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    c->edgeLenPending = true;
+}
+double edge_len_end(cipc_ctx* c) // after a stream synchronisation
+{
+    if (c->edgeLenPending) {
+        c->edgeLenCached = *(const double*)c->pinScal.p;
+        c->edgeLenVersion = c->xVersion;
+        c->edgeLenPending = false;
+    }
+    return c->edgeLenCached;
 }
 void bbox_to_host(cipc_ctx* c, const double4* P, double alpha, double* mn, double* mx)
 {
@@ -1495,8 +1548,8 @@ void bbox_to_host(cipc_ctx* c, const double4* P, double alpha, double* mn, doubl
     for (int d = 0; d < 3; ++d) { init[d] = dbl_ordered_h(1e300); init[3 + d] = dbl_ordered_h(-1e300); }
     CIPC_CUDA(cudaMemcpyAsync(c->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, c->st));
     CIPC_LAUNCH(k_bbox, RED_GRID, RED_BT, 0, c->st, c->X.p, P, alpha, c->BN.p, c->T.nBN, c->bbox.p);
-    long long out[6];
-    CIPC_CUDA(cudaMemcpyAsync(out, c->bbox.p, sizeof(out), cudaMemcpyDeviceToHost, c->st));
+    long long* out = (long long*)((char*)c->pinScal.reserve(64) + 8);
+    CIPC_CUDA(cudaMemcpyAsync(out, c->bbox.p, 6 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
     CIPC_CUDA(cudaStreamSynchronize(c->st));
     for (int d = 0; d < 3; ++d) {
         long long a = out[d], b = out[3 + d];
@@ -1557,6 +1610,13 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
     H.nCells = nCells;
     c->ks.reserve((size_t)nCells * 4, c->st);
     CIPC_LAUNCH(k_kind_starts, div_up((size_t)nE + 1, TB), TB, 0, c->st, c->keys.p, c->headScan.p, c->heads.p, nE, c->ks.p);
+    // pair-enumeration tasks (count -> scan -> descriptors); the exact total stays on the device, the launch uses a bound
+    H.maxTasks = nCells + nE / PAIRS_QCH + 1;
+    c->taskCnt.reserve(nCells, c->st); c->taskDesc.reserve(H.maxTasks, c->st);
+    CIPC_LAUNCH(k_task_counts, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, c->taskCnt.p);
+    device_excl_scan(c->taskCnt.p, c->taskCnt.p, nCells, c->scanwk, c->st);
+    CIPC_CUDA(cudaMemcpyAsync(c->nTasksDev.p, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToDevice, c->st));
+    CIPC_LAUNCH(k_task_desc, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, c->taskCnt.p, c->taskDesc.p);
     c->codes.reserve(nE, c->st);
     CIPC_LAUNCH(k_entry_codes, div_up(nE, TB), TB, 0, c->st, c->keys.p, c->vals.p, nE, T.nBN, T.nBE, c->boxLo.p, c->fine.p, H.G, c->codes.p);
     c->ctr["hash_entries"] = nE;
@@ -1601,8 +1661,8 @@ void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
         }
         out.count = c->counters.p;
         CIPC_CUDA(cudaMemsetAsync(c->counters.p, 0, 16 * sizeof(u32), c->st));
-        CIPC_LAUNCH(k_pairs<CCD>, div_up(e1 - e0, PAIRS_WARPS), PAIRS_WARPS * 32, 0, c->st, c->T, c->X.p, c->P.p, dist, c->vals.p, c->ks.p,
-            c->codes.p, e0, e1, out);
+        CIPC_LAUNCH(k_pairs<CCD>, div_up(H.maxTasks, PAIRS_WARPS), PAIRS_WARPS * 32, 0, c->st, c->T, c->X.p, c->P.p, dist, c->vals.p, c->ks.p,
+            c->codes.p, c->taskDesc.p, c->nTasksDev.p, out);
         CIPC_CUDA(cudaMemcpyAsync(counts, c->counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         bool ok = true;
@@ -1668,13 +1728,14 @@ int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
     double alpha = stepIn;
     {
         cipc_ctx::Scope sc(c, "ccd_hash_build");
-        double voxelSize = 1.0;
-        if (T.nBE) voxelSize *= mean_edge_len(c);
+        edge_len_begin(c); // rides on the search-direction reduction's round trip
         // span rule (SPATIAL_HASH.h:466-482).  The sum is a fixed-tree reduction; when the rule
         // fires the step is biased down by 4e-13 relative so that it never exceeds the sequential
         // CPU sum's result.
         CIPC_LAUNCH(k_psize_partial, RED_GRID, RED_BT, 0, c->st, c->P.p, c->BN.p, T.nBN, c->partial.p);
         const double pSize = reduce_to_host(c, 1.0 / ((double)T.nBN * 3.0));
+        double voxelSize = 1.0;
+        if (T.nBE) voxelSize *= edge_len_end(c);
         const double spanSize = alpha * pSize / voxelSize;
         if (spanSize > 1) alpha = (alpha / spanSize) * (1.0 - 4e-13);
         double mn[3], mx[3];
@@ -1992,6 +2053,7 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
         c->bbox.reserve(6, c->st);
         c->counters.reserve(16, c->st);
         c->errFlag.reserve(1, c->st);
+        c->nTasksDev.reserve(1, c->st);
         CIPC_CUDA(cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->st));
         CIPC_CUDA(cudaFuncSetAttribute(k_barrier_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM));
         CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<0>::SMEM));
@@ -2111,6 +2173,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         T.BN = c->BN.p; T.BE = c->BE.p; T.BT = c->BT.p; T.flags = c->flags.p; T.v2sv = c->v2sv.p; T.nnx = c->nnx.p; T.nNnx = nNnx;
         c->topoHash = h;
         c->haveX = c->haveX0 = c->haveP = c->haveXn = c->haveXprev = false;
+        ++c->xVersion;
         c->nC = 0;
         c->nF = 0;
         return (int)CIPC_OK;
@@ -2122,6 +2185,7 @@ int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes)
         need(ctx->T.nV > 0, "topology not set");
         upload_vec3(ctx, ctx->X, X, stride_bytes);
         ctx->haveX = true;
+        ++ctx->xVersion;
         return (int)CIPC_OK;
     });
 }
@@ -2159,11 +2223,12 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
         HashInfo H;
         {
             cipc_ctx::Scope sc(c, "ccs_hash_build");
-            double voxelSize = 1.0;
-            if (T.nBE) voxelSize *= mean_edge_len(c);
-            else voxelSize = 4.0 * dHat;
+            edge_len_begin(c); // rides on the bounding-box round trip
             double mn[3], mx[3];
             bbox_to_host(c, nullptr, 0.0, mn, mx);
+            double voxelSize = 1.0;
+            if (T.nBE) voxelSize *= edge_len_end(c);
+            else voxelSize = 4.0 * dHat;
             double mag = 0;
             for (int d = 0; d < 3; ++d) mag = std::max(mag, std::max(std::fabs(mn[d]), std::fabs(mx[d])));
             // inflation radius: half the activation distance plus a rounding guard, so that any pair
@@ -2305,9 +2370,14 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
             c->tripOff.reserve(c->nC, c->st);
             CIPC_LAUNCH(k_block_sizes, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->tripOff.p);
             device_excl_scan(c->tripOff.p, c->tripOff.p, c->nC, c->scanwk, c->st);
-            u32 tot;
+            u32 tot, nk[4];
             CIPC_CUDA(cudaMemcpyAsync(&tot, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
-            CIPC_CUDA(cudaStreamSynchronize(c->st));
+            for (int k = 0; k < 4; ++k) c->clsIdx[k].reserve(c->nC, c->st);
+            CIPC_CUDA(cudaMemsetAsync(c->counters.p + 12, 0, 4 * sizeof(u32), c->st));
+            CIPC_LAUNCH(k_classify, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->clsIdx[0].p, c->clsIdx[1].p, c->clsIdx[2].p,
+                c->clsIdx[3].p, c->counters.p + 12);
+            CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st)); // one host round trip for the triplet total and the class counts
             c->nTrip = (int64_t)tot * 9;
             c->trip.reserve((size_t)c->nTrip, c->st);
             const char* dense = getenv("CIPC_HESSIAN_DENSE"); // cross-check switch: force the dense eigen path for every stencil
@@ -2317,13 +2387,6 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     (const u32*)nullptr, c->nC, (const u32*)nullptr, bp, projectSPD, c->trip.p);
             }
             else {
-                for (int k = 0; k < 4; ++k) c->clsIdx[k].reserve(c->nC, c->st);
-                CIPC_CUDA(cudaMemsetAsync(c->counters.p + 12, 0, 4 * sizeof(u32), c->st));
-                CIPC_LAUNCH(k_classify, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->clsIdx[0].p, c->clsIdx[1].p, c->clsIdx[2].p,
-                    c->clsIdx[3].p, c->counters.p + 12);
-                u32 nk[4];
-                CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
-                CIPC_CUDA(cudaStreamSynchronize(c->st));
                 if (projectSPD && devTriplets) {
                     // device-resident triplets: fused factor + expansion, the factors never leave the SM
                     u32* dl = c->clsIdx[3].p; u32* dn = c->counters.p + 15;
@@ -2414,7 +2477,12 @@ int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx)
 {
     if (!ctx) return nullptr;
-    int r = guarded(ctx, [&]() { ctx->begin_call(); expand_on_device(ctx); return (int)CIPC_OK; });
+    int r = guarded(ctx, [&]() {
+        ctx->begin_call();
+        ctx->trip.reserve(1, ctx->st); // an empty stream (no constraints) still has a valid address
+        expand_on_device(ctx);
+        return (int)CIPC_OK;
+    });
     return r == CIPC_OK ? ctx->trip.p : nullptr;
 }
 int cipc_step_size_dev(cipc_ctx* ctx, int elastic, double thickness, double stepIn)
@@ -2600,6 +2668,7 @@ int cipc_step_positions(cipc_ctx* ctx, double alpha)
         need(c->haveXprev && c->haveP, "saved positions / search direction not set");
         CIPC_LAUNCH(k_step_positions, div_up(c->T.nV, TB), TB, 0, c->st, c->Xprev.p, c->P.p, alpha, c->T.nV, c->X.p);
         c->haveX = true;
+        ++c->xVersion;
         return (int)CIPC_OK;
     });
 }

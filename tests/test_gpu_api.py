@@ -129,3 +129,26 @@ def test_fused_device_hessian_equals_factor_path(ctx):
         b = ctx.get_triplets(n)
         assert n == len(a) > 0 and np.array_equal(a["row"], b["row"]) and np.array_equal(a["col"], b["col"])
         assert np.abs(a["val"] - b["val"]).max() <= 1e-13 * np.abs(a["val"]).max()
+
+
+def test_empty_constraint_set_through_every_stage(ctx):
+    """a scene with nothing in contact (cloth 1.5 dHat above the sphere): every stage returns an empty / neutral result"""
+    from codim_ipc_b200 import scenes
+    sc = scenes.cloth_on_sphere(24, draped=False)
+    ctx.set_scene(sc)
+    cs, info = ctx.constraint_set(sc["dHat2"], sc["xi"])
+    assert cs.shape == (0, 4) and info.shape == (0, 2)
+    assert ctx.barrier_energy(sc["dHat2"], sc["kappa"], sc["xi"], E=0.75) == 0.75
+    assert not ctx.barrier_gradient(sc["dHat2"], sc["kappa"], sc["xi"]).any()
+    assert len(ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True)) == 0
+    assert ctx.barrier_hessian_dev(sc["dHat2"], sc["kappa"], sc["xi"], True) == 0 and ctx.dev_triplets()
+    fcs, cp, B, nf = ctx.friction_basis(sc["dHat2"], sc["kappa"], sc["xi"])
+    assert len(fcs) == len(cp) == len(B) == len(nf) == 0
+    ctx.set_prev_positions(sc["X"])
+    assert ctx.friction_energy(1e-10, 0.4, E=0.5) == 0.5
+    assert not ctx.friction_gradient(1e-10, 0.4).any()
+    assert len(ctx.friction_hessian(1e-10, 0.4, True)) == 0
+    a = ctx.step_size(sc["xi"], 1.0)
+    assert 0.0 < a <= 1.0
+    with pytest.raises(Exception):  # the reference dereferences min_element of an empty vector; the C ABI reports it
+        ctx.min_dist2(sc["xi"])
