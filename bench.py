@@ -267,6 +267,19 @@ def main():
         friction = {k: round(v, 4) for k, v in friction.items()}
         friction["stencils"] = int(nF); friction["triplets"] = int(nFT)
 
+    # triplets -> CSR assembly on the device, barrier Hessian only: reported beside the metric
+    csr = {}
+    if not args.no_friction:
+        for _ in range(2):
+            ctx.csr_begin()
+            ctx.barrier_hessian_dev(dHat2, kappa, xi, True)
+            ctx.csr_add(); csr["blocks"] = ctx.stage_ms("csr_add")
+            nnz = ctx.csr_finish(fetch=False)
+            for k in ("csr_sort", "csr_pattern", "csr_emit"):
+                csr[k[4:]] = ctx.stage_ms(k)
+        csr = {k: round(v, 4) for k, v in csr.items()}
+        csr["nnz"] = int(nnz); csr["blocks_in"] = ctx.counter("csr_blocks_in"); csr["blocks_unique"] = ctx.counter("csr_blocks_unique")
+
     # ---- end-to-end through the host API (pinned host buffers; copies inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -397,7 +410,7 @@ def main():
                        "parallelism": "pairs partitioned by hash-cell ranges x%d" % world},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters,
-            "friction_stages_ms": friction}
+            "friction_stages_ms": friction, "csr_stages_ms": csr}
     if args.stage_report:
         print(json.dumps(line["stages_ms"], indent=1), file=sys.stderr)
     print(json.dumps(line))

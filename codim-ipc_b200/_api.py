@@ -293,6 +293,24 @@ class ContactContext:
     def friction_gradient_dev(self, epsvh2, mu, accumulate=True):
         self._ck(self.L.cipc_friction_gradient_dev(self.h, C.c_double(epsvh2), C.c_double(mu), int(accumulate)))
 
+    # ---- Hessian triplets -> CSR on the device
+    def csr_begin(self):
+        self._ck(self.L.cipc_csr_begin(self.h))
+
+    def csr_add(self):
+        """append the blocks of the Hessian computed last (barrier or friction)"""
+        self._ck(self.L.cipc_csr_add(self.h))
+
+    def csr_finish(self, fetch=True):
+        """-> (rowPtr (3nV+1,), colIdx (nnz,), val (nnz,)) like Eigen's row-major SparseMatrix after setFromTriplets"""
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_csr_finish(self.h, C.byref(n)))
+        if not fetch:
+            return n.value
+        rp = np.zeros(3 * self.nV + 1, np.int32); ci = np.zeros(n.value, np.int32); v = np.zeros(n.value)
+        self._ck(self.L.cipc_get_csr(self.h, _p(rp, C.c_int32), _p(ci, C.c_int32), _p(v, C.c_double)))
+        return rp, ci, v
+
     # ---- device-resident line search (SURVEY 8(f)-4)
     def save_positions(self):
         self._ck(self.L.cipc_save_positions(self.h))

@@ -44,6 +44,7 @@ struct Topo {
 struct GridDesc {
     double ox, oy, oz, inv; // cell = floor((x - o) * inv)
     int gx, gy, gz;         // cells per axis (linear index = ix + gx*(iy + gy*iz))
+    int fsh;                // log2 of the fine steps per voxel (quantised-AABB pre-test)
 };
 
 __device__ __forceinline__ xv3 ldx(const double4* __restrict__ A, int v)
@@ -94,7 +95,8 @@ __device__ __forceinline__ int ux(u64 p) { return (int)(p & 0x1fffffu); }
 __device__ __forceinline__ int uy(u64 p) { return (int)((p >> 21) & 0x1fffffu); }
 __device__ __forceinline__ int uz(u64 p) { return (int)((p >> 42) & 0x1fffffu); }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-constexpr int FINE_SUB = 16; // quantised-AABB pre-test resolution: FINE_SUB steps per voxel
+// quantised-AABB pre-test resolution: GridDesc::fs = 2^fsh steps per voxel, 256 unless the grid is so elongated that
+// fs x finer coordinates would not fit the 21 bits per axis of the packed boxes (size_grid)
 
 // ===================================================================== reductions for the grids
 __global__ void k_edge_len_partial(const double4* __restrict__ X, const int2* __restrict__ BE, int nBE, double* partial)
@@ -171,11 +173,12 @@ __global__ void k_boxes_ccs(Topo T, const double4* __restrict__ X, GridDesc G, d
     const int gd[3] = {G.gx, G.gy, G.gz};
     int l[3], h[3], fl[3], fh[3];
     for (int d = 0; d < 3; ++d) {
-        // FINE_SUB-times finer coordinates of the same inflated box; the voxel index is the fine index / FINE_SUB
-        fl[d] = clampi((int)floor((lo[d] - r - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
-        fh[d] = clampi((int)floor((hi[d] + r - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
-        l[d] = fl[d] / FINE_SUB;
-        h[d] = fh[d] / FINE_SUB;
+        // fs-times finer coordinates of the same inflated box; the voxel index is the fine index / fs
+        const double fs = (double)(1 << G.fsh);
+        fl[d] = clampi((int)floor((lo[d] - r - o[d]) * G.inv * fs), 0, (gd[d] << G.fsh) - 1);
+        fh[d] = clampi((int)floor((hi[d] + r - o[d]) * G.inv * fs), 0, (gd[d] << G.fsh) - 1);
+        l[d] = fl[d] >> G.fsh;
+        h[d] = fh[d] >> G.fsh;
     }
     boxLo[g] = pack3(l[0], l[1], l[2]);
     boxHi[g] = pack3(h[0], h[1], h[2]);
@@ -202,8 +205,9 @@ __global__ void k_node_boxes_ccd(Topo T, const double4* __restrict__ X, const do
         l[d] = clampi((int)floor(__dmul_rn(__dsub_rn(mn, o[d]), G.inv)), 0, gd[d] - 1);
         h[d] = clampi((int)floor(__dmul_rn(__dsub_rn(mx, o[d]), G.inv)), 0, gd[d] - 1);
         // conservative quantised full-step box (any pair passing the swept AABB test with gap xi overlaps here)
-        fl[d] = clampi((int)floor((fmin(c[d], f[d]) - halfXi - guard - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
-        fh[d] = clampi((int)floor((fmax(c[d], f[d]) + halfXi + guard - o[d]) * G.inv * FINE_SUB), 0, gd[d] * FINE_SUB - 1);
+        const double fs = (double)(1 << G.fsh);
+        fl[d] = clampi((int)floor((fmin(c[d], f[d]) - halfXi - guard - o[d]) * G.inv * fs), 0, (gd[d] << G.fsh) - 1);
+        fh[d] = clampi((int)floor((fmax(c[d], f[d]) + halfXi + guard - o[d]) * G.inv * fs), 0, (gd[d] << G.fsh) - 1);
     }
     nodeLo[i] = pack3(l[0], l[1], l[2]);
     nodeHi[i] = pack3(h[0], h[1], h[2]);
@@ -354,9 +358,9 @@ __device__ __forceinline__ void cand_push(const CandOut& o, int which, int a, in
 // of the boxes' intersection ("min-corner rule": no pair is visited twice, no de-duplication pass).  Both cheap pair
 // tests only need data that is LOCAL to the (cell, primitive) entry:
 //   * min corner:  cell == max(loA, loB) per axis  <=>  per axis, A or B STARTS in this cell (both cover it)  -> 3 bits
-//   * quantised-AABB overlap (FINE_SUB = 16 steps per voxel): with both fine intervals clamped to the cell's own fine
-//     range [16c, 16c+15] the test is unchanged, because each interval reaches into the cell from both sides
-//     (cell(fine lo) <= box lo <= c <= box hi <= cell(fine hi))                                                   -> 6 x 4 bits
+//   * quantised-AABB overlap (fs <= 256 steps per voxel): with both fine intervals clamped to the cell's own fine
+//     range [fs c, fs c + fs-1] the test is unchanged, because each interval reaches into the cell from both sides
+//     (cell(fine lo) <= box lo <= c <= box hi <= cell(fine hi))                                                   -> 6 x 8 bits
 // code.x = lo bytes (x | y<<8 | z<<16) | start bits << 24, code.y = hi bytes.  One coalesced 8-byte load and two
 // byte-wise SIMD compares per pair replace the 24 bytes of gathers of the global test.
 __global__ void k_entry_codes(const u32* __restrict__ keys, const u32* __restrict__ vals, u32 nE, int nBN, int nBE,
@@ -375,8 +379,8 @@ __global__ void k_entry_codes(const u32* __restrict__ keys, const u32* __restric
     u32 a = 0, b = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        a |= (u32)clampi(fl[d] - FINE_SUB * c[d], 0, FINE_SUB - 1) << (8 * d);
-        b |= (u32)clampi(fh[d] - FINE_SUB * c[d], 0, FINE_SUB - 1) << (8 * d);
+        a |= (u32)clampi(fl[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (8 * d);
+        b |= (u32)clampi(fh[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (8 * d);
         if (l[d] == c[d]) a |= 1u << (24 + d);
     }
     codes[i] = make_uint2(a, b);
@@ -387,28 +391,34 @@ __device__ __forceinline__ bool code_pair_ok(const uint2 a, const uint2 b)
     return (ov & 0x00ffffffu) == 0x00ffffffu && (((a.x | b.x) >> 24) & 7u) == 7u;
 }
 
-// Work items of the pair enumeration: a cell's point queries and edge queries are cut into tasks of PAIRS_QCH queries,
+// Work items of the pair enumeration: a cell's point queries and edge queries are cut into tasks of `qch` queries,
 // one warp per task, so a crowded cell (hundreds of particles in one voxel of a granular pile) is spread over many
 // warps instead of serialising on one.  cnt[c] = tasks of cell c; desc[] = (cell, task index within the cell).
-constexpr u32 PAIRS_QCH = 16;
-__device__ __forceinline__ u32 cell_point_tasks(u32 p0, u32 e0) { return (e0 - p0 + PAIRS_QCH - 1) / PAIRS_QCH; }
-__device__ __forceinline__ u32 cell_edge_tasks(u32 e0, u32 t0) { return t0 > e0 + 1 ? (t0 - e0 - 1 + PAIRS_QCH - 1) / PAIRS_QCH : 0u; }
-__global__ void k_task_counts(const u32* __restrict__ ks, u32 nCells, u32* __restrict__ cnt)
+// qch is chosen per hash build (pairs_qch): few, crowded cells are cut finely; with many cells a task is a whole cell
+// side, because every task ends with a partially filled batch of the expensive filters.
+__device__ __forceinline__ u32 cell_point_tasks(u32 p0, u32 e0, u32 qch) { return (e0 - p0 + qch - 1) / qch; }
+__device__ __forceinline__ u32 cell_edge_tasks(u32 e0, u32 t0, u32 qch) { return t0 > e0 + 1 ? (t0 - e0 - 1 + qch - 1) / qch : 0u; }
+// Point tasks of all cells come first, then the edge tasks (cnt has 2 nCells entries, one scan): the warps of a CTA then
+// work on tasks of one kind and similar length.
+__global__ void k_task_counts(const u32* __restrict__ ks, u32 nCells, u32 qch, u32* __restrict__ cnt)
 {
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const u32 p0 = ks[c * 4], e0 = ks[c * 4 + 1], t0 = ks[c * 4 + 2];
-    cnt[c] = cell_point_tasks(p0, e0) + cell_edge_tasks(e0, t0);
+    cnt[c] = cell_point_tasks(p0, e0, qch);
+    cnt[nCells + c] = cell_edge_tasks(e0, t0, qch);
 }
-__global__ void k_task_desc(const u32* __restrict__ ks, u32 nCells, const u32* __restrict__ off, uint2* __restrict__ desc)
+__global__ void k_task_desc(const u32* __restrict__ ks, u32 nCells, u32 qch, const u32* __restrict__ off, uint2* __restrict__ desc)
 {
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const u32 p0 = ks[c * 4], e0 = ks[c * 4 + 1], t0 = ks[c * 4 + 2];
-    const u32 n = cell_point_tasks(p0, e0) + cell_edge_tasks(e0, t0), o = off[c];
-    for (u32 k = 0; k < n; ++k) desc[o + k] = make_uint2(c, k);
+    const u32 np = cell_point_tasks(p0, e0, qch), ne = cell_edge_tasks(e0, t0, qch);
+    const u32 op = off[c], oe = off[nCells + c];
+    for (u32 k = 0; k < np; ++k) desc[op + k] = make_uint2(c, k);
+    for (u32 k = 0; k < ne; ++k) desc[oe + k] = make_uint2(c, k | 0x80000000u);
 }
-// One WARP per task (<= PAIRS_QCH point queries or edge queries of one voxel cell).  Phase 1 (cheap, all lanes busy): the
+// One WARP per task (<= qch point queries or edge queries of one voxel cell).  Phase 1 (cheap, all lanes busy): the
 // queries are walked in order and the 32 lanes test 32 targets of the run at a time on the entry codes; survivors
 // are appended to a per-warp ring buffer in shared memory.  Phase 2 (expensive, all lanes busy): whenever the buffer
 // holds 32 pairs, each lane takes one: topology filters, coordinate gathers and the reference's exact AABB test.
@@ -419,7 +429,7 @@ constexpr int PAIRS_WARPS = 8;
 template <bool CCD>
 __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double4* __restrict__ X, const double4* __restrict__ P, double dist_,
     const u32* __restrict__ vals, const u32* __restrict__ ks, const uint2* __restrict__ codes, const uint2* __restrict__ desc,
-    const u32* __restrict__ nTasks, CandOut out)
+    const u32* __restrict__ nTasks, u32 qch, CandOut out)
 {
     __shared__ uint2 sq[PAIRS_WARPS][64];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -430,11 +440,11 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
     uint2* q = sq[warp];
     u32 head = 0, tail = 0; // warp-uniform ring indices
     const u32 p0 = ks[cellIdx * 4], e0 = ks[cellIdx * 4 + 1], t0 = ks[cellIdx * 4 + 2], end = ks[cellIdx * 4 + 3];
-    const u32 nPT = cell_point_tasks(p0, e0);
-    const bool pointTask = td.y < nPT;
+    const bool pointTask = (td.y & 0x80000000u) == 0u;
+    const u32 tk = td.y & 0x7fffffffu;
     // this task's query range [qa, qb): point entries of the cell, or edge entries (the last edge has no later partner)
-    const u32 qa = pointTask ? p0 + td.y * PAIRS_QCH : e0 + (td.y - nPT) * PAIRS_QCH;
-    const u32 qb = pointTask ? min(qa + PAIRS_QCH, e0) : min(qa + PAIRS_QCH, t0 - 1);
+    const u32 qa = (pointTask ? p0 : e0) + tk * qch;
+    const u32 qb = pointTask ? min(qa + qch, e0) : min(qa + qch, t0 - 1);
     const xd dist(dist_);
     const u32 ltmask = (1u << lane) - 1u;
     auto push = [&](bool pass, u32 a, u32 b) { // called by all 32 lanes
@@ -1342,6 +1352,7 @@ __global__ void k_fill_u32(u32* p, size_t n, u32 v)
 } // namespace cipc
 
 #include "friction.cuh"
+#include "csr.cuh"
 
 // ========================================================================================= context
 using namespace cipc;
@@ -1409,6 +1420,15 @@ struct cipc_ctx {
     DevBuf<double4> yhdr; // YHdr records (32 B each)
     int64_t nTrip = 0;
     PinnedBuf pin;
+    // triplets -> CSR assembly (csr.cuh)
+    const int4* hessStencils = nullptr; // stencil array (cs or fcs) and count of the Hessian whose triplets are resident
+    u32 hessN = 0;
+    DevBuf<double> blkVal, csrVal;
+    DevBuf<u32> keyI, keyJ, csrKey, csrIds, csrColS, csrHeads, csrScan, urow, ucol, ustart, browCnt;
+    DevBuf<int> csrRowPtr, csrColIdx;
+    size_t nBlk = 0;
+    u32 nU = 0;
+    bool csrValid = false;
     // lagged friction (FEM/FRICTION.h): the friction set lives on the device between calls
     DevBuf<double4> Xn;
     bool haveXn = false;
@@ -1509,7 +1529,7 @@ void upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int strid
 // ---- spatial hash (shared by the constraint-set and the step-size passes)
 struct HashInfo {
     GridDesc G;
-    u32 nEntries = 0, nCells = 0, maxTasks = 0;
+    u32 nEntries = 0, nCells = 0, maxTasks = 0, qch = 16;
 };
 
 // sum of partials helper: returns value on host
@@ -1611,12 +1631,13 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
     c->ks.reserve((size_t)nCells * 4, c->st);
     CIPC_LAUNCH(k_kind_starts, div_up((size_t)nE + 1, TB), TB, 0, c->st, c->keys.p, c->headScan.p, c->heads.p, nE, c->ks.p);
     // pair-enumeration tasks (count -> scan -> descriptors); the exact total stays on the device, the launch uses a bound
-    H.maxTasks = nCells + nE / PAIRS_QCH + 1;
-    c->taskCnt.reserve(nCells, c->st); c->taskDesc.reserve(H.maxTasks, c->st);
-    CIPC_LAUNCH(k_task_counts, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, c->taskCnt.p);
-    device_excl_scan(c->taskCnt.p, c->taskCnt.p, nCells, c->scanwk, c->st);
+    H.qch = std::min(256u, std::max(8u, nE / 50000u)); // aim at >= ~50K tasks (5 per resident warp slot), whole cell sides beyond that
+    H.maxTasks = 2 * nCells + nE / H.qch + 1;
+    c->taskCnt.reserve((size_t)2 * nCells, c->st); c->taskDesc.reserve(H.maxTasks, c->st);
+    CIPC_LAUNCH(k_task_counts, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, H.qch, c->taskCnt.p);
+    device_excl_scan(c->taskCnt.p, c->taskCnt.p, (size_t)2 * nCells, c->scanwk, c->st);
     CIPC_CUDA(cudaMemcpyAsync(c->nTasksDev.p, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToDevice, c->st));
-    CIPC_LAUNCH(k_task_desc, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, c->taskCnt.p, c->taskDesc.p);
+    CIPC_LAUNCH(k_task_desc, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, H.qch, c->taskCnt.p, c->taskDesc.p);
     c->codes.reserve(nE, c->st);
     CIPC_LAUNCH(k_entry_codes, div_up(nE, TB), TB, 0, c->st, c->keys.p, c->vals.p, nE, T.nBN, T.nBE, c->boxLo.p, c->fine.p, H.G, c->codes.p);
     c->ctr["hash_entries"] = nE;
@@ -1634,11 +1655,13 @@ bool size_grid(const double* mn, const double* mx, double voxelSize, GridDesc& G
         inv = 1.0 / voxelSize;
     }
     long g[3];
-    for (int d = 0; d < 3; ++d) {
-        g[d] = std::max(1L, (long)std::ceil(range[d] * inv)) + (plusOne ? 1 : 0);
-        if (g[d] > (1L << 17) - 1) return false; // FINE_SUB x finer coordinates must fit 21 bits
-    }
+    for (int d = 0; d < 3; ++d) g[d] = std::max(1L, (long)std::ceil(range[d] * inv)) + (plusOne ? 1 : 0);
     if ((double)g[0] * g[1] * g[2] >= (double)(1L << 30)) return false;
+    const long gmax = std::max(g[0], std::max(g[1], g[2]));
+    int fsh = 8; // 256 fine steps per voxel when they fit the 21 bits per axis of the packed boxes
+    while (fsh > 0 && (gmax << fsh) > (1L << 21) - 1) --fsh;
+    if ((gmax << fsh) > (1L << 21) - 1) return false;
+    G.fsh = fsh;
     G.ox = mn[0]; G.oy = mn[1]; G.oz = mn[2]; G.inv = inv;
     G.gx = (int)g[0]; G.gy = (int)g[1]; G.gz = (int)g[2];
     return true;
@@ -1662,7 +1685,7 @@ void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
         out.count = c->counters.p;
         CIPC_CUDA(cudaMemsetAsync(c->counters.p, 0, 16 * sizeof(u32), c->st));
         CIPC_LAUNCH(k_pairs<CCD>, div_up(H.maxTasks, PAIRS_WARPS), PAIRS_WARPS * 32, 0, c->st, c->T, c->X.p, c->P.p, dist, c->vals.p, c->ks.p,
-            c->codes.p, c->taskDesc.p, c->nTasksDev.p, out);
+            c->codes.p, c->taskDesc.p, c->nTasksDev.p, H.qch, out);
         CIPC_CUDA(cudaMemcpyAsync(counts, c->counters.p, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         bool ok = true;
@@ -1831,6 +1854,7 @@ int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu)
     need(c->haveX && c->haveXn, "positions / previous positions not set");
     c->nTrip = 0;
     c->factorValid = false;
+    c->hessStencils = c->fcs.p; c->hessN = c->nF;
     if (!c->nF) return CIPC_OK;
     cipc_ctx::Scope sc(c, "friction_H");
     const u32 nF = c->nF;
@@ -2365,6 +2389,7 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
         const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
         c->nTrip = 0;
         c->factorValid = false;
+        c->hessStencils = c->cs.p; c->hessN = c->nC;
         if (c->nC) {
             cipc_ctx::Scope sc(c, "barrier_H");
             c->tripOff.reserve(c->nC, c->st);
@@ -2688,6 +2713,98 @@ int cipc_get_positions(cipc_ctx* ctx, double* X, int stride_bytes)
         CIPC_CUDA(cudaMemcpyAsync(h, c->X.p, n * 32, cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         for (size_t v = 0; v < n; ++v) { X[3 * v] = h[4 * v]; X[3 * v + 1] = h[4 * v + 1]; X[3 * v + 2] = h[4 * v + 2]; }
+        return (int)CIPC_OK;
+    });
+}
+
+// ---- triplets -> CSR (Math/CSR_MATRIX.h:49-56)
+int cipc_csr_begin(cipc_ctx* ctx)
+{
+    return guarded(ctx, [&]() { ctx->nBlk = 0; ctx->nU = 0; ctx->csrValid = false; return (int)CIPC_OK; });
+}
+int cipc_csr_add(cipc_ctx* ctx)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        c->begin_call();
+        if (!c->nTrip || !c->hessN) return (int)CIPC_OK;
+        expand_on_device(c); // the blocks are read from the device-resident triplet stream
+        cipc_ctx::Scope sc(c, "csr_add");
+        const size_t add = (size_t)(c->nTrip / 9), tot = c->nBlk + add;
+        if (tot >= 0xfffffff0ull) throw std::runtime_error("CSR assembly: more than 2^32 blocks");
+        c->blkVal.reserve(tot * 9, c->st, true); c->keyI.reserve(tot, c->st, true); c->keyJ.reserve(tot, c->st, true);
+        CIPC_LAUNCH(k_trip_to_blocks, div_up((size_t)c->hessN * 32, 256), 256, 0, c->st, c->trip.p, c->hessStencils, c->tripOff.p, c->hessN,
+            c->nBlk, c->blkVal.p, c->keyI.p, c->keyJ.p);
+        c->nBlk = tot;
+        c->csrValid = false;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_csr_finish(cipc_ctx* ctx, int64_t* nnz_out)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->T.nV > 0, "topology not set");
+        c->begin_call();
+        const size_t n = c->nBlk;
+        const int nV = c->T.nV;
+        c->csrRowPtr.reserve((size_t)3 * nV + 1, c->st);
+        c->nU = 0;
+        if (n == 0) {
+            CIPC_CUDA(cudaMemsetAsync(c->csrRowPtr.p, 0, ((size_t)3 * nV + 1) * sizeof(int), c->st));
+            c->csrValid = true;
+            if (nnz_out) *nnz_out = 0;
+            return (int)CIPC_OK;
+        }
+        int bits = 1;
+        while ((1ll << bits) < (long long)nV) ++bits;
+        u32 nU = 0;
+        {
+            cipc_ctx::Scope sc(c, "csr_sort");
+            c->csrKey.reserve(n, c->st); c->csrIds.reserve(n, c->st);
+            CIPC_LAUNCH(k_iota_copy, div_up(n, TB), TB, 0, c->st, c->keyJ.p, c->csrKey.p, c->csrIds.p, n);
+            device_radix_sort(c->csrKey.p, c->csrIds.p, n, bits, c->sortwk, c->st);                      // by column vertex
+            CIPC_LAUNCH(k_gather_u32, div_up(n, TB), TB, 0, c->st, c->keyI.p, c->csrIds.p, c->csrKey.p, n);
+            device_radix_sort(c->csrKey.p, c->csrIds.p, n, bits, c->sortwk, c->st);                      // then (stable) by row vertex
+        }
+        {
+            cipc_ctx::Scope sc(c, "csr_pattern");
+            c->csrColS.reserve(n, c->st); c->csrHeads.reserve(n, c->st); c->csrScan.reserve(n, c->st);
+            CIPC_LAUNCH(k_csr_heads, div_up(n, TB), TB, 0, c->st, c->csrKey.p, c->keyJ.p, c->csrIds.p, n, c->csrColS.p, c->csrHeads.p);
+            device_excl_scan(c->csrHeads.p, c->csrScan.p, n, c->scanwk, c->st);
+            CIPC_CUDA(cudaMemcpyAsync(&nU, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+            if ((uint64_t)nU * 9 > 0x7fffffffull) throw std::runtime_error("CSR assembly: nnz exceeds the reference's 32-bit index type");
+            c->urow.reserve(nU, c->st); c->ucol.reserve(nU, c->st); c->ustart.reserve(nU, c->st); c->browCnt.reserve((size_t)nV + 1, c->st);
+            CIPC_CUDA(cudaMemsetAsync(c->browCnt.p, 0, ((size_t)nV + 1) * 4, c->st));
+            CIPC_LAUNCH(k_csr_unique, div_up(n, TB), TB, 0, c->st, c->csrKey.p, c->csrColS.p, c->csrHeads.p, c->csrScan.p, n, c->urow.p, c->ucol.p,
+                c->ustart.p, c->browCnt.p);
+            device_excl_scan(c->browCnt.p, c->browCnt.p, (size_t)nV + 1, c->scanwk, c->st);
+        }
+        {
+            cipc_ctx::Scope sc(c, "csr_emit");
+            c->csrColIdx.reserve((size_t)nU * 9, c->st); c->csrVal.reserve((size_t)nU * 9, c->st);
+            CIPC_LAUNCH(k_csr_rowptr, div_up((size_t)nV + 1, TB), TB, 0, c->st, c->browCnt.p, nV, nU, c->csrRowPtr.p);
+            CIPC_LAUNCH(k_csr_emit, div_up(nU, 128), 128, 0, c->st, c->blkVal.p, c->csrIds.p, c->urow.p, c->ucol.p, c->ustart.p, nU, n, c->browCnt.p,
+                c->csrColIdx.p, c->csrVal.p);
+        }
+        c->nU = nU;
+        c->csrValid = true;
+        c->ctr["csr_blocks_in"] = (int64_t)n; c->ctr["csr_blocks_unique"] = nU;
+        if (nnz_out) *nnz_out = (int64_t)nU * 9;
+        return (int)CIPC_OK;
+    });
+}
+int cipc_get_csr(cipc_ctx* ctx, int32_t* rowPtr, int32_t* colIdx, double* val)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        need(c->csrValid, "no assembled CSR matrix (call cipc_csr_finish)");
+        const size_t nnz = (size_t)c->nU * 9;
+        if (rowPtr) CIPC_CUDA(cudaMemcpyAsync(rowPtr, c->csrRowPtr.p, ((size_t)3 * c->T.nV + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        if (colIdx && nnz) CIPC_CUDA(cudaMemcpyAsync(colIdx, c->csrColIdx.p, nnz * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        if (val && nnz) CIPC_CUDA(cudaMemcpyAsync(val, c->csrVal.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
         return (int)CIPC_OK;
     });
 }

@@ -188,13 +188,12 @@ struct SortWork {
     ScanWork scan;
 };
 // Sorts (keys, vals) by the low `bits` bits of the key, ascending, stable.  Result is left in
-// (keys, vals) (an even number of passes is always run).
+// (keys, vals): after an odd number of passes it is copied back (two D2D copies cost less than a fourth pass).
 static inline void device_radix_sort(u32* keys, u32* vals, size_t n, int bits, SortWork& wk, cudaStream_t s)
 {
     if (n <= 1) return;
     int passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
-    if (passes & 1) ++passes;
     const int nb = div_up(n, RS_TILE);
     wk.k2.reserve(n, s); wk.v2.reserve(n, s); wk.hist.reserve((size_t)256 * nb, s);
     u32 *ki = keys, *vi = vals, *ko = wk.k2.p, *vo = wk.v2.p;
@@ -205,6 +204,10 @@ static inline void device_radix_sort(u32* keys, u32* vals, size_t n, int bits, S
         CIPC_LAUNCH(k_radix_scatter, nb, RS_BT, 0, s, ki, vi, ko, vo, wk.hist.p, n, shift, nb);
         u32* t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
+    }
+    if (ki != keys) {
+        CIPC_CUDA(cudaMemcpyAsync(keys, ki, n * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+        CIPC_CUDA(cudaMemcpyAsync(vals, vi, n * sizeof(u32), cudaMemcpyDeviceToDevice, s));
     }
 }
 

@@ -137,6 +137,21 @@ int cipc_save_positions(cipc_ctx* ctx);
 int cipc_step_positions(cipc_ctx* ctx, double alpha);
 int cipc_get_positions(cipc_ctx* ctx, double* X, int stride_bytes);
 
+/* ---- Hessian triplets -> CSR on the device ---------------------------------------------------
+ * What Math/CSR_MATRIX.h:49-56 Construct_From_Triplet (Eigen setFromTriplets; Shell/INC_POTENTIAL.h:382-394) does with
+ * the contact / friction triplets, done in HBM at 3x3-block granularity: duplicates summed (in a reproducible order),
+ * column indices sorted inside every row, explicit zeros kept.  The matrix is 3nV x 3nV.
+ *   cipc_csr_begin  : start a new matrix
+ *   cipc_csr_add    : append the blocks of the Hessian computed last (cipc_barrier_hessian[_dev] / cipc_friction_hessian);
+ *                     call it after each Hessian that should be part of the matrix (the triplet stream is reused)
+ *   cipc_csr_finish : sort, merge and emit; nnz_out = stored entries
+ *   cipc_get_csr    : rowPtr (3nV+1), colIdx (nnz), val (nnz) -> host (Eigen outerIndexPtr / innerIndexPtr / valuePtr of
+ *                     a row-major SparseMatrix<double,RowMajor,int>); any pointer may be NULL */
+int cipc_csr_begin(cipc_ctx* ctx);
+int cipc_csr_add(cipc_ctx* ctx);
+int cipc_csr_finish(cipc_ctx* ctx, int64_t* nnz_out);
+int cipc_get_csr(cipc_ctx* ctx, int32_t* rowPtr, int32_t* colIdx, double* val);
+
 /* ---- device-resident access (multi-GPU reductions, benchmarking) ----------------------------- */
 double* cipc_dev_positions(cipc_ctx* ctx);      /* nV x 4 doubles (x,y,z,pad) */
 double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient_dev */

@@ -19,6 +19,7 @@ for rep in range(2):
     ctx.barrier_gradient_dev(sc["dHat2"], sc["kappa"], sc["xi"]); out["g"] = ctx.stage_ms("barrier_g")
     nT = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True, fetch=False); out["H_factor"] = ctx.stage_ms("barrier_H")
     t0 = time.perf_counter(); ctx.dev_triplets(); ctx.sync(); out["H_expand_wall"] = 1e3 * (time.perf_counter() - t0)
+    ctx.barrier_hessian_dev(sc["dHat2"], sc["kappa"], sc["xi"], True); out["H_fused"] = ctx.stage_ms("barrier_H")
     cnt.update({k: ctx.counter(k) for k in ("hessian_4pt", "hessian_pe", "hessian_pp", "hessian_mollified")})
     ctx.step_size_dev(sc["xi"], 1.0)
     for s in ("ccd_hash_build", "ccd_pairs", "ccd_accd"):
