@@ -357,6 +357,21 @@ def main():
                "note": "d2h = bytes delivered into host buffers; the Hessian triplets (%d B) cross PCIe as %d B of factors and are expanded "
                        "by the host cores inside cipc_get_triplets" % (len(trip_h[:nTrip]) * 16, pcie[0]),
                "calls_ms": {k: round(1e3 * v / args.steps, 3) for k, v in calls.items()}}
+        # the same Hessian delivered as CSR assembled on the device instead of 16-byte triplets: what an
+        # integration that feeds the solver's A->p/i/x directly would pay (reported beside e2e, not part of it)
+        if csr:
+            rp_h = pin((3 * nV + 1,), torch.int32); ci_h = pin((csr["nnz"] + 1024,), torch.int32); cv_h = pin((csr["nnz"] + 1024,), torch.float64)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ctx.set_positions(X4)
+                ctx.csr_begin(); ctx.barrier_hessian_dev(dHat2, kappa, xi, True); ctx.csr_add()
+                nnz = ctx.csr_finish(fetch=False)
+                ctx._ck(ctx.L.cipc_get_csr(ctx.h, rp_h.ctypes.data_as(C.POINTER(C.c_int32)), ci_h.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           cv_h.ctypes.data_as(C.POINTER(C.c_double))))
+                ts.append(1e3 * (time.perf_counter() - t0))
+            e2e["hessian_as_csr_ms"] = round(min(ts), 3)
+            e2e["hessian_as_csr_bytes"] = int(nnz * 12 + (3 * nV + 1) * 4)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

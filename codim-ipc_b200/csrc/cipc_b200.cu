@@ -432,13 +432,16 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
     const u32* __restrict__ nTasks, u32 qch, CandOut out)
 {
     __shared__ uint2 sq[PAIRS_WARPS][64];
+    __shared__ int2 so[PAIRS_WARPS][96];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u32 task = blockIdx.x * PAIRS_WARPS + warp;
     if (task >= *nTasks) return; // whole warp leaves; no block-level barrier below
     const uint2 td = desc[task];
     const u32 cellIdx = td.x;
     uint2* q = sq[warp];
-    u32 head = 0, tail = 0; // warp-uniform ring indices
+    int2* ob = so[warp];
+    u32 head = 0, tail = 0; // warp-uniform ring indices of the pair queue
+    u32 on = 0;             // warp-uniform fill of the output buffer
     const u32 p0 = ks[cellIdx * 4], e0 = ks[cellIdx * 4 + 1], t0 = ks[cellIdx * 4 + 2], end = ks[cellIdx * 4 + 3];
     const bool pointTask = (td.y & 0x80000000u) == 0u;
     const u32 tk = td.y & 0x7fffffffu;
@@ -452,88 +455,120 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
         if (pass) q[(tail + __popc(m & ltmask)) & 63u] = make_uint2(a, b);
         tail += __popc(m);
     };
+    // Candidates are collected per warp in shared memory and handed to the global list 64 or more at a time: one
+    // atomic on the list counter per flush instead of one per batch (millions of same-address atomics serialise in L2).
+    auto flush = [&](int which) { // called by all 32 lanes
+        if (on == 0) return;
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(&out.count[which], on);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (u32 k = lane; k < on; k += 32)
+            if (base + k < out.cap[which]) out.buf[which][base + k] = ob[k];
+        __syncwarp();
+        on = 0;
+    };
+    auto emit = [&](bool ok, int a, int b, int which) { // called by all 32 lanes
+        const u32 m = __ballot_sync(0xffffffffu, ok);
+        if (ok) ob[on + __popc(m & ltmask)] = make_int2(a, b);
+        on += __popc(m);
+        if (on >= 64u) flush(which);
+    };
     // (a, b) = sorted-entry indices of a point and a triangle
-    auto do_pt = [&](u32 a, u32 b) {
+    auto do_pt = [&](u32 a, u32 b, int& ra, int& rb) -> bool {
         const int svI = (int)vals[a], t = (int)vals[b];
         const int vI = T.BN[svI];
         const int4 tri = T.BT[t];
-        if (!pt_pair_ok(T, vI, tri)) return;
+        ra = svI; rb = t;
+        if (!pt_pair_ok(T, vI, tri)) return false;
         const xv3 p = ldx(X, vI), q0 = ldx(X, tri.x), q1 = ldx(X, tri.y), q2 = ldx(X, tri.z);
-        bool ok;
-        if (CCD) ok = pt_ccd_broadphase(p, q0, q1, q2, ldx(P, vI), ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
-        else ok = pt_cd_broadphase(p, q0, q1, q2, dist);
-        if (ok) cand_push(out, 0, svI, t);
+        if (CCD) return pt_ccd_broadphase(p, q0, q1, q2, ldx(P, vI), ldx(P, tri.x), ldx(P, tri.y), ldx(P, tri.z), dist);
+        return pt_cd_broadphase(p, q0, q1, q2, dist);
     };
-    auto do_ee = [&](u32 a, u32 b) {
+    auto do_ee = [&](u32 a, u32 b, int& ra, int& rb) -> bool {
         const int eI = (int)vals[a], eJ = (int)vals[b];
         const int2 ea = T.BE[eI], eb = T.BE[eJ];
-        if (!ee_pair_ok(T, ea, eb)) return;
+        ra = eI; rb = eJ;
+        if (!ee_pair_ok(T, ea, eb)) return false;
         const xv3 a0 = ldx(X, ea.x), a1 = ldx(X, ea.y), b0 = ldx(X, eb.x), b1 = ldx(X, eb.y);
-        bool ok;
-        if (CCD) ok = ee_ccd_broadphase(a0, a1, b0, b1, ldx(P, ea.x), ldx(P, ea.y), ldx(P, eb.x), ldx(P, eb.y), dist);
-        else ok = ee_cd_broadphase(a0, a1, b0, b1, dist);
-        if (ok) cand_push(out, 1, eI, eJ);
+        if (CCD) return ee_ccd_broadphase(a0, a1, b0, b1, ldx(P, ea.x), ldx(P, ea.y), ldx(P, eb.x), ldx(P, eb.y), dist);
+        return ee_cd_broadphase(a0, a1, b0, b1, dist);
     };
-    auto drain = [&](auto process, bool all) {
+    auto drain = [&](auto process, int which, bool all) {
         while (tail - head >= 32u || (all && tail != head)) {
             const u32 n = min(32u, tail - head);
             __syncwarp();
-            if (lane < n) { const uint2 e = q[(head + lane) & 63u]; process(e.x, e.y); }
+            bool ok = false;
+            int ra = 0, rb = 0;
+            if (lane < n) { const uint2 e = q[(head + lane) & 63u]; ok = process(e.x, e.y, ra, rb); }
             head += n;
-            __syncwarp();
+            emit(ok, ra, rb, which);
         }
     };
     if (pointTask) {
-    // ---- point queries against the triangle run
-    for (u32 i = qa; i < qb; ++i) {
-        const uint2 cA = codes[i];
-        for (u32 jb = t0; jb < end; jb += 32) {
-            const u32 j = jb + lane;
-            push(j < end && code_pair_ok(cA, codes[j]), i, j);
-            drain(do_pt, false);
-        }
-    }
-    drain(do_pt, true);
-    // ---- codimensional extras (rare): rod / particle points against rod edges (IPC.h:271-326; step size: particles
-    //      only, :2098-2135) and particles against later boundary-node slots (IPC.h:328-352, :2137-2163)
-    if (T.nRod > 0 || T.codim1 < T.nBN) {
+        // ---- point queries against the triangle run
         for (u32 i = qa; i < qb; ++i) {
-            const int svI = (int)vals[i];
-            if (svI < min(T.codim0, T.codim1)) continue; // warp-uniform
-            const int vI = T.BN[svI];
             const uint2 cA = codes[i];
-            const xv3 p = ldx(X, vI);
-            xv3 dp;
-            if (CCD) dp = ldx(P, vI);
-            if (T.nRod > 0 && svI >= (CCD ? T.codim1 : T.codim0)) {
-                for (u32 j = e0 + lane; j < t0; j += 32) {
-                    const int e = (int)vals[j];
-                    if (e < T.nBE - T.nRod) continue;
-                    if (!code_pair_ok(cA, codes[j])) continue;
-                    const int2 ed = T.BE[e];
-                    if (vI == ed.x || vI == ed.y) continue;
-                    if ((T.flags[vI] & 1) && (T.flags[ed.x] & 1) && (T.flags[ed.y] & 1)) continue;
-                    const xv3 q0 = ldx(X, ed.x), q1 = ldx(X, ed.y);
-                    bool ok;
-                    if (CCD) ok = pe_ccd_broadphase(p, q0, q1, dp, ldx(P, ed.x), ldx(P, ed.y), dist);
-                    else ok = pe_cd_broadphase(p, q0, q1, dist);
-                    if (ok) cand_push(out, 2, svI, e);
-                }
-            }
-            if (svI >= T.codim1) { // slots ascend inside a run
-                for (u32 j = i + 1 + lane; j < e0; j += 32) {
-                    if (!code_pair_ok(cA, codes[j])) continue;
-                    const int svJ = (int)vals[j];
-                    const int vJ = T.BN[svJ];
-                    if ((T.flags[vI] & 1) && (T.flags[vJ] & 1)) continue;
-                    bool ok = true;
-                    if (CCD) ok = pp_ccd_broadphase(p, ldx(X, vJ), dp, ldx(P, vJ), dist);
-                    if (ok) cand_push(out, 3, svI, svJ);
-                }
+            for (u32 jb = t0; jb < end; jb += 32) {
+                const u32 j = jb + lane;
+                push(j < end && code_pair_ok(cA, codes[j]), i, j);
+                drain(do_pt, 0, false);
             }
         }
-    }
-    return;
+        drain(do_pt, 0, true);
+        flush(0);
+        // ---- codimensional extras: rod / particle points against rod edges (IPC.h:271-326; step size: particles only,
+        //      :2098-2135) and particles against later boundary-node slots (IPC.h:328-352, :2137-2163)
+        if (T.nRod > 0 || T.codim1 < T.nBN) {
+            for (u32 i = qa; i < qb; ++i) {
+                const int svI = (int)vals[i];
+                if (svI < min(T.codim0, T.codim1)) continue; // warp-uniform
+                const int vI = T.BN[svI];
+                const uint2 cA = codes[i];
+                const xv3 p = ldx(X, vI);
+                xv3 dp;
+                if (CCD) dp = ldx(P, vI);
+                if (T.nRod > 0 && svI >= (CCD ? T.codim1 : T.codim0)) {
+                    for (u32 jb = e0; jb < t0; jb += 32) {
+                        const u32 j = jb + lane;
+                        bool ok = j < t0 && code_pair_ok(cA, codes[j]);
+                        int e = 0;
+                        if (ok) {
+                            e = (int)vals[j];
+                            ok = e >= T.nBE - T.nRod;
+                        }
+                        if (ok) {
+                            const int2 ed = T.BE[e];
+                            ok = !(vI == ed.x || vI == ed.y) && !((T.flags[vI] & 1) && (T.flags[ed.x] & 1) && (T.flags[ed.y] & 1));
+                            if (ok) {
+                                const xv3 q0 = ldx(X, ed.x), q1 = ldx(X, ed.y);
+                                if (CCD) ok = pe_ccd_broadphase(p, q0, q1, dp, ldx(P, ed.x), ldx(P, ed.y), dist);
+                                else ok = pe_cd_broadphase(p, q0, q1, dist);
+                            }
+                        }
+                        emit(ok, svI, e, 2);
+                    }
+                    flush(2);
+                }
+                if (svI >= T.codim1) { // slots ascend inside a run
+                    for (u32 jb = i + 1; jb < e0; jb += 32) {
+                        const u32 j = jb + lane;
+                        bool ok = j < e0 && code_pair_ok(cA, codes[j]);
+                        int svJ = 0;
+                        if (ok) {
+                            svJ = (int)vals[j];
+                            const int vJ = T.BN[svJ];
+                            ok = !((T.flags[vI] & 1) && (T.flags[vJ] & 1));
+                            if (CCD && ok) ok = pp_ccd_broadphase(p, ldx(X, vJ), dp, ldx(P, vJ), dist);
+                        }
+                        emit(ok, svI, svJ, 3);
+                    }
+                    if (T.nRod > 0) flush(3); // the buffer holds one candidate kind at a time
+                }
+            }
+            flush(3);
+        }
+        return;
     }
     // ---- edge queries: edge ids ascend inside a run, so j > i <=> eJ > eI
     for (u32 i = qa; i < qb; ++i) {
@@ -541,10 +576,11 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
         for (u32 jb = i + 1; jb < t0; jb += 32) {
             const u32 j = jb + lane;
             push(j < t0 && code_pair_ok(cA, codes[j]), i, j);
-            drain(do_ee, false);
+            drain(do_ee, 1, false);
         }
     }
-    drain(do_ee, true);
+    drain(do_ee, 1, true);
+    flush(1);
 }
 
 // ===================================================================== constraint-set narrow phase
@@ -561,36 +597,72 @@ __device__ __forceinline__ void push4(int4* buf, u32* ctr, int4 v)
     base = g.shfl(base, 0);
     buf[base + g.thread_rank()] = v;
 }
+// Block-wide slot reservation in one of NL append-only lists: which in [0, NL) or -1 (nothing to append).  One atomic
+// per list and CTA instead of one per warp -- the list counters are single addresses, and same-address atomics retire at
+// about one per clock in L2, which bounded the narrow phase (a million warps, two counters).  EVERY thread of the CTA
+// must call it.  Returns the element index in list `which`.
+template <int NL, int BT>
+__device__ __forceinline__ u32 block_slot(int which, u32* counters)
+{
+    __shared__ u32 wcnt[NL][BT / 32];
+    __shared__ u32 sbase[NL];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    u32 myRank = 0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const u32 m = __ballot_sync(0xffffffffu, which == l);
+        if (which == l) myRank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) wcnt[l][warp] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x < NL) {
+        u32 tot = 0;
+        for (int w = 0; w < BT / 32; ++w) { const u32 t = wcnt[threadIdx.x][w]; wcnt[threadIdx.x][w] = tot; tot += t; }
+        sbase[threadIdx.x] = tot ? atomicAdd(&counters[threadIdx.x], tot) : 0u;
+    }
+    __syncthreads();
+    const u32 r = which >= 0 ? sbase[which] + wcnt[which][warp] + myRank : 0u;
+    __syncthreads();
+    return r;
+}
+constexpr int NARROW_BT = 256;
+__device__ __forceinline__ void narrow_append(const NarrowOut& out, int which, const int4 r)
+{
+    const u32 slot = block_slot<2, NARROW_BT>(which, out.count);
+    if (which == 0) out.pass[slot] = r;
+    else if (which == 1) out.raw[slot] = r;
+}
 // IPC.h:189-257.  The closest-feature type selects the operands first, so a warp runs at most three distance bodies
 // (point-point, point-edge, point-triangle) instead of one per type; the arithmetic of each body is unchanged.
-__global__ void k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
+__global__ void __launch_bounds__(NARROW_BT) k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_,
+    NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int2 c = cand[i];
-    const int vI = T.BN[c.x];
-    const int4 t = T.BT[c.y];
-    const xv3 p = ldx(X, vI), t0 = ldx(X, t.x), t1 = ldx(X, t.y), t2 = ldx(X, t.z);
-    const xd dHat2(dHat2_);
-    const int ty = pt_type(p, t0, t1, t2);
-    int4 r;
-    xd d;
-    if (ty == 6) { d = pt_dist2(p, t0, t1, t2); r = make_int4(-vI - 1, t.x, t.y, t.z); }
-    else if (ty >= 3) {
-        const bool e3 = ty == 3, e4 = ty == 4;
-        const xv3 e0 = e3 ? t0 : (e4 ? t1 : t2), e1 = e3 ? t1 : (e4 ? t2 : t0);
-        d = pe_dist2(p, e0, e1);
-        r = make_int4(-vI - 1, e3 ? t.x : (e4 ? t.y : t.z), e3 ? t.y : (e4 ? t.z : t.x), -1);
+    int which = -1;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (i < n) {
+        const int2 c = cand[i];
+        const int vI = T.BN[c.x];
+        const int4 t = T.BT[c.y];
+        const xv3 p = ldx(X, vI), t0 = ldx(X, t.x), t1 = ldx(X, t.y), t2 = ldx(X, t.z);
+        const xd dHat2(dHat2_);
+        const int ty = pt_type(p, t0, t1, t2);
+        xd d;
+        if (ty == 6) { d = pt_dist2(p, t0, t1, t2); r = make_int4(-vI - 1, t.x, t.y, t.z); }
+        else if (ty >= 3) {
+            const bool e3 = ty == 3, e4 = ty == 4;
+            const xv3 e0 = e3 ? t0 : (e4 ? t1 : t2), e1 = e3 ? t1 : (e4 ? t2 : t0);
+            d = pe_dist2(p, e0, e1);
+            r = make_int4(-vI - 1, e3 ? t.x : (e4 ? t.y : t.z), e3 ? t.y : (e4 ? t.z : t.x), -1);
+        }
+        else {
+            const xv3 q = ty == 0 ? t0 : (ty == 1 ? t1 : t2);
+            d = pp_dist2(p, q);
+            r = make_int4(-vI - 1, ty == 0 ? t.x : (ty == 1 ? t.y : t.z), -1, -1);
+        }
+        if (d < dHat2) which = (ty == 6) ? 0 : 1;
     }
-    else {
-        const xv3 q = ty == 0 ? t0 : (ty == 1 ? t1 : t2);
-        d = pp_dist2(p, q);
-        r = make_int4(-vI - 1, ty == 0 ? t.x : (ty == 1 ? t.y : t.z), -1, -1);
-    }
-    if (d < dHat2) {
-        if (ty == 6) push4(out.pass, &out.count[0], r);
-        else push4(out.raw, &out.count[1], r);
-    }
+    narrow_append(out, which, r);
 }
 // rest length^2 per boundary edge: the mollifier threshold 1e-3 |ea|^2 |eb|^2 (EDGE_EDGE_MOLLIFIER.h:582-592) only
 // depends on it, which saves the four rest-position gathers per edge-edge candidate
@@ -602,73 +674,82 @@ __global__ void k_rest_len2(const double4* __restrict__ X0, const int2* __restri
     out[e] = norm2(ldx(X0, ed.x) - ldx(X0, ed.y)).v;
 }
 // IPC.h:414-564
-__global__ void k_narrow_ee(Topo T, const double4* __restrict__ X, const double* __restrict__ restLen2, const int2* __restrict__ cand, u32 n,
-    double dHat2_, NarrowOut out)
+__global__ void __launch_bounds__(NARROW_BT) k_narrow_ee(Topo T, const double4* __restrict__ X, const double* __restrict__ restLen2,
+    const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int2 c = cand[i];
-    const int2 a = T.BE[c.x], b = T.BE[c.y];
-    const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y), b0 = ldx(X, b.x), b1 = ldx(X, b.y);
-    const xd dHat2(dHat2_);
-    const xd cn2 = ee_cross_norm2(a0, a1, b0, b1);
-    const xd eps_x = xd(1.0e-3) * xd(restLen2[c.x]) * xd(restLen2[c.y]);
-    const bool mol = cn2 < eps_x;
-    const int ty = ee_type(a0, a1, b0, b1);
-    int4 r;
-    xd d;
-    if (ty == 8) {
-        d = ee_dist2(a0, a1, b0, b1);
-        r = mol ? make_int4(a.x, a.y, -b.x - 1, b.y) : make_int4(a.x, a.y, b.x, b.y);
+    int which = -1;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (i < n) {
+        const int2 c = cand[i];
+        const int2 a = T.BE[c.x], b = T.BE[c.y];
+        const xv3 a0 = ldx(X, a.x), a1 = ldx(X, a.y), b0 = ldx(X, b.x), b1 = ldx(X, b.y);
+        const xd dHat2(dHat2_);
+        const xd cn2 = ee_cross_norm2(a0, a1, b0, b1);
+        const xd eps_x = xd(1.0e-3) * xd(restLen2[c.x]) * xd(restLen2[c.y]);
+        const bool mol = cn2 < eps_x;
+        const int ty = ee_type(a0, a1, b0, b1);
+        xd d;
+        if (ty == 8) {
+            d = ee_dist2(a0, a1, b0, b1);
+            r = mol ? make_int4(a.x, a.y, -b.x - 1, b.y) : make_int4(a.x, a.y, b.x, b.y);
+        }
+        else if (ty == 2 || ty >= 5) { // point-edge: 2 (a0; b), 5 (a1; b), 6 (b0; a), 7 (b1; a)
+            const bool onB = ty <= 5;   // the edge is b
+            const xv3 p = ty == 2 ? a0 : (ty == 5 ? a1 : (ty == 6 ? b0 : b1));
+            const int pv = ty == 2 ? a.x : (ty == 5 ? a.y : (ty == 6 ? b.x : b.y));
+            const int po = ty == 2 ? a.y : (ty == 5 ? a.x : (ty == 6 ? b.y : b.x)); // the other end of the point's edge
+            d = pe_dist2(p, onB ? b0 : a0, onB ? b1 : a1);
+            const int e0 = onB ? b.x : a.x, e1 = onB ? b.y : a.y;
+            r = mol ? make_int4(pv, e0, e1, -po - 1) : make_int4(-pv - 1, e0, e1, -1);
+        }
+        else { // point-point: 0 (a0,b0), 1 (a0,b1), 3 (a1,b0), 4 (a1,b1)
+            const bool fa = ty < 3, fb = (ty == 0 || ty == 3);
+            d = pp_dist2(fa ? a0 : a1, fb ? b0 : b1);
+            const int pa = fa ? a.x : a.y, oa = fa ? a.y : a.x, pb = fb ? b.x : b.y, ob = fb ? b.y : b.x;
+            r = mol ? make_int4(pa, pb, -oa - 1, -ob - 1) : make_int4(-pa - 1, pb, -1, -1);
+        }
+        if (d < dHat2) which = (r.x >= 0) ? 0 : 1;
     }
-    else if (ty == 2 || ty >= 5) { // point-edge: 2 (a0; b), 5 (a1; b), 6 (b0; a), 7 (b1; a)
-        const bool onB = ty <= 5;   // the edge is b
-        const xv3 p = ty == 2 ? a0 : (ty == 5 ? a1 : (ty == 6 ? b0 : b1));
-        const int pv = ty == 2 ? a.x : (ty == 5 ? a.y : (ty == 6 ? b.x : b.y));
-        const int po = ty == 2 ? a.y : (ty == 5 ? a.x : (ty == 6 ? b.y : b.x)); // the other end of the point's edge
-        d = pe_dist2(p, onB ? b0 : a0, onB ? b1 : a1);
-        const int e0 = onB ? b.x : a.x, e1 = onB ? b.y : a.y;
-        r = mol ? make_int4(pv, e0, e1, -po - 1) : make_int4(-pv - 1, e0, e1, -1);
-    }
-    else { // point-point: 0 (a0,b0), 1 (a0,b1), 3 (a1,b0), 4 (a1,b1)
-        const bool fa = ty < 3, fb = (ty == 0 || ty == 3);
-        d = pp_dist2(fa ? a0 : a1, fb ? b0 : b1);
-        const int pa = fa ? a.x : a.y, oa = fa ? a.y : a.x, pb = fb ? b.x : b.y, ob = fb ? b.y : b.x;
-        r = mol ? make_int4(pa, pb, -oa - 1, -ob - 1) : make_int4(-pa - 1, pb, -1, -1);
-    }
-    if (d < dHat2) {
-        if (r.x >= 0) push4(out.pass, &out.count[0], r);
-        else push4(out.raw, &out.count[1], r);
-    }
+    narrow_append(out, which, r);
 }
 // IPC.h:281-322
-__global__ void k_narrow_pe(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
+__global__ void __launch_bounds__(NARROW_BT) k_narrow_pe(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_,
+    NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int2 c = cand[i];
-    const int vI = T.BN[c.x];
-    const int2 e = T.BE[c.y];
-    const xv3 p = ldx(X, vI), e0 = ldx(X, e.x), e1 = ldx(X, e.y);
-    const xd dHat2(dHat2_);
-    int4 r;
-    xd d;
-    switch (pe_type(p, e0, e1)) {
-    case 0: d = pp_dist2(p, e0); r = make_int4(-vI - 1, e.x, -1, -1); break;
-    case 1: d = pp_dist2(p, e1); r = make_int4(-vI - 1, e.y, -1, -1); break;
-    default: d = pe_dist2(p, e0, e1); r = make_int4(-vI - 1, e.x, e.y, -1); break;
+    int which = -1;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (i < n) {
+        const int2 c = cand[i];
+        const int vI = T.BN[c.x];
+        const int2 e = T.BE[c.y];
+        const xv3 p = ldx(X, vI), e0 = ldx(X, e.x), e1 = ldx(X, e.y);
+        xd d;
+        switch (pe_type(p, e0, e1)) {
+        case 0: d = pp_dist2(p, e0); r = make_int4(-vI - 1, e.x, -1, -1); break;
+        case 1: d = pp_dist2(p, e1); r = make_int4(-vI - 1, e.y, -1, -1); break;
+        default: d = pe_dist2(p, e0, e1); r = make_int4(-vI - 1, e.x, e.y, -1); break;
+        }
+        if (d < xd(dHat2_)) which = 1;
     }
-    if (d < dHat2) push4(out.raw, &out.count[1], r);
+    narrow_append(out, which, r);
 }
 // IPC.h:336-349
-__global__ void k_narrow_pp(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
+__global__ void __launch_bounds__(NARROW_BT) k_narrow_pp(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_,
+    NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int2 c = cand[i];
-    const int vI = T.BN[c.x], vJ = T.BN[c.y];
-    const xd d = pp_dist2(ldx(X, vI), ldx(X, vJ));
-    if (d < xd(dHat2_)) push4(out.raw, &out.count[1], make_int4(-vI - 1, vJ, -1, -1));
+    int which = -1;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (i < n) {
+        const int2 c = cand[i];
+        const int vI = T.BN[c.x], vJ = T.BN[c.y];
+        const xd d = pp_dist2(ldx(X, vI), ldx(X, vJ));
+        r = make_int4(-vI - 1, vJ, -1, -1);
+        if (d < xd(dHat2_)) which = 1;
+    }
+    narrow_append(out, which, r);
 }
 
 // PP/PE de-duplication (IPC.h:599-654): same raw 4-tuple => one stencil with multiplicity.
@@ -695,15 +776,15 @@ __global__ void k_dedup_insert(const int4* __restrict__ raw, u32 n, u32* slots, 
         h = (h + 1) & mask;
     }
 }
-__global__ void k_dedup_emit(const int4* __restrict__ raw, const u32* __restrict__ slots, const u32* __restrict__ slotCnt, u32 nSlots,
+__global__ void __launch_bounds__(256) k_dedup_emit(const int4* __restrict__ raw, const u32* __restrict__ slots, const u32* __restrict__ slotCnt, u32 nSlots,
     int4* out, u32* outCount)
 {
     const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nSlots) return;
-    const u32 r = slots[s];
+    const u32 r = s < nSlots ? slots[s] : 0xffffffffu;
+    const u32 o = block_slot<1, 256>(r != 0xffffffffu ? 0 : -1, outCount);
     if (r == 0xffffffffu) return;
     const int4 k = raw[r];
-    push4(out, outCount, make_int4(k.x, k.y, k.z, -(int)slotCnt[s]));
+    out[o] = make_int4(k.x, k.y, k.z, -(int)slotCnt[s]);
 }
 __global__ void k_fill_info(double2* info, u32 n, double w, double dHat2)
 {
@@ -928,24 +1009,20 @@ __device__ void stencil_hessian(const double4* __restrict__ X, const double4* __
             H[i * 12 + j] += w * (bG * (G[i] * eg[j] + eg[i] * G[j]) + (e * bH) * G[i] * G[j]);
 }
 // class of a stencil for the Hessian pass: 0 = PT / EE, 1 = PE, 2 = PP (low-rank fast paths), 3 = mollified (dense path)
-__global__ void k_classify(const int4* __restrict__ cs, u32 n, u32* idx0, u32* idx1, u32* idx2, u32* idx3, u32* counts)
+__global__ void __launch_bounds__(256) k_classify(const int4* __restrict__ cs, u32 n, u32* idx0, u32* idx1, u32* idx2, u32* idx3, u32* counts)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int4 c = cs[i];
-    int cls;
-    if (c.x >= 0) cls = (c.w >= 0 && c.z >= 0) ? 0 : 3;
-    else cls = (c.w >= 0) ? 0 : (c.z >= 0 ? 1 : 2);
+    int cls = -1;
+    if (i < n) {
+        const int4 c = cs[i];
+        if (c.x >= 0) cls = (c.w >= 0 && c.z >= 0) ? 0 : 3;
+        else cls = (c.w >= 0) ? 0 : (c.z >= 0 ? 1 : 2);
+    }
+    const u32 slot = block_slot<4, 256>(cls, counts);
     u32* lists[4] = {idx0, idx1, idx2, idx3};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (cls == k) {
-            cg::coalesced_group g = cg::coalesced_threads();
-            u32 base = 0;
-            if (g.thread_rank() == 0) base = atomicAdd(&counts[k], g.size());
-            base = g.shfl(base, 0);
-            lists[k][base + g.thread_rank()] = i;
-        }
+        if (cls == k) lists[k][slot] = i;
 }
 __device__ __forceinline__ void put_triplet(cipc_triplet* o, int row, int col, double val)
 {
@@ -2146,10 +2223,28 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         u64 h = 0xcbf29ce484222325ULL;
         const int hdr[8] = {nV, nBN, nBE, nBT, nRod, codim[0], codim[1], nNnx};
         h = fnv(hdr, sizeof(hdr), h);
-        h = fnv(BN, (size_t)nBN * 4, h);
-        h = fnv(BE, (size_t)nBE * be_stride * 4, h);
-        h = fnv(BT, (size_t)nBT * bt_stride * 4, h);
-        h = fnv(dbc, nV, h);
+        {
+            // the three index arrays (tens of MB at 1M triangles) are hashed in 1 MiB pieces by a few host threads and the
+            // piece hashes are chained in order: the check costs ~1 ms instead of ~5 ms per call
+            struct Seg { const unsigned char* p; size_t n; };
+            const Seg segs[4] = {{(const unsigned char*)BN, (size_t)nBN * 4}, {(const unsigned char*)BE, (size_t)nBE * be_stride * 4},
+                {(const unsigned char*)BT, (size_t)nBT * bt_stride * 4}, {(const unsigned char*)dbc, (size_t)nV}};
+            const size_t PIECE = (size_t)1 << 20;
+            std::vector<Seg> pieces;
+            for (const Seg& sg : segs)
+                for (size_t o = 0; o < sg.n; o += PIECE) pieces.push_back({sg.p + o, std::min(PIECE, sg.n - o)});
+            std::vector<u64> ph(pieces.size());
+            const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, pieces.size() / 4));
+            std::atomic<size_t> next(0);
+            auto work = [&]() {
+                for (size_t k; (k = next.fetch_add(1)) < pieces.size();) ph[k] = fnv(pieces[k].p, pieces[k].n, 0x9E3779B97F4A7C15ULL + k);
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work);
+            work();
+            for (auto& t : th) t.join();
+            h = fnv(ph.data(), ph.size() * sizeof(u64), h);
+        }
         if (nNnx) h = fnv(nnxPairs, (size_t)nNnx * 8, h);
         if (BNArea) h = fnv(BNArea, (size_t)nBN * 8, h ^ 1);
         if (h == c->topoHash && c->T.nV == nV) return (int)CIPC_OK; // unchanged: keep the resident copy
@@ -2250,9 +2345,14 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             edge_len_begin(c); // rides on the bounding-box round trip
             double mn[3], mx[3];
             bbox_to_host(c, nullptr, 0.0, mn, mx);
-            double voxelSize = 1.0;
-            if (T.nBE) voxelSize *= edge_len_end(c);
-            else voxelSize = 4.0 * dHat;
+            // Voxel size of the constraint-set grid (our own choice: any grid gives the same set).  The reference uses the
+            // mean edge length, which puts hundreds of particles into one voxel of a granular pile whose only edges belong
+            // to a coarse obstacle mesh.  Here: the mean extent over ALL primitives (points count as 0; edges and triangles
+            // ~ one edge length) plus the activation distance every box is inflated by -- for a cloth mesh that is the
+            // reference's choice within a few percent, for point clouds it drops to a few dHat.
+            const double nPrim = (double)T.nBN + T.nBE + T.nBT;
+            double voxelSize = (T.nBE ? edge_len_end(c) * ((double)T.nBE + T.nBT) / nPrim : 0.0) + dHat;
+            voxelSize = std::max(voxelSize, 2.0 * dHat);
             double mag = 0;
             for (int d = 0; d < 3; ++d) mag = std::max(mag, std::max(std::fabs(mn[d]), std::fabs(mx[d])));
             // inflation radius: half the activation distance plus a rounding guard, so that any pair
@@ -2280,10 +2380,10 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             cipc_ctx::Scope sc(c, "ccs_narrow");
             CIPC_CUDA(cudaMemsetAsync(c->counters.p + 8, 0, 4 * sizeof(u32), c->st));
             NarrowOut out{c->cs.p, c->raw.p, c->counters.p + 8};
-            if (counts[0]) CIPC_LAUNCH(k_narrow_pt, div_up(counts[0], 128), 128, 0, c->st, T, c->X.p, c->cand[0].p, counts[0], dHat2o, out);
-            if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->restLen2.p, c->cand[1].p, counts[1], dHat2o, out);
-            if (counts[2]) CIPC_LAUNCH(k_narrow_pe, div_up(counts[2], 128), 128, 0, c->st, T, c->X.p, c->cand[2].p, counts[2], dHat2o, out);
-            if (counts[3]) CIPC_LAUNCH(k_narrow_pp, div_up(counts[3], 128), 128, 0, c->st, T, c->X.p, c->cand[3].p, counts[3], dHat2o, out);
+            if (counts[0]) CIPC_LAUNCH(k_narrow_pt, div_up(counts[0], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[0].p, counts[0], dHat2o, out);
+            if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->restLen2.p, c->cand[1].p, counts[1], dHat2o, out);
+            if (counts[2]) CIPC_LAUNCH(k_narrow_pe, div_up(counts[2], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[2].p, counts[2], dHat2o, out);
+            if (counts[3]) CIPC_LAUNCH(k_narrow_pp, div_up(counts[3], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[3].p, counts[3], dHat2o, out);
             CIPC_CUDA(cudaMemcpyAsync(hc, c->counters.p + 8, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
             CIPC_CUDA(cudaStreamSynchronize(c->st));
         }
@@ -2785,7 +2885,7 @@ int cipc_csr_finish(cipc_ctx* ctx, int64_t* nnz_out)
             cipc_ctx::Scope sc(c, "csr_emit");
             c->csrColIdx.reserve((size_t)nU * 9, c->st); c->csrVal.reserve((size_t)nU * 9, c->st);
             CIPC_LAUNCH(k_csr_rowptr, div_up((size_t)nV + 1, TB), TB, 0, c->st, c->browCnt.p, nV, nU, c->csrRowPtr.p);
-            CIPC_LAUNCH(k_csr_emit, div_up(nU, 128), 128, 0, c->st, c->blkVal.p, c->csrIds.p, c->urow.p, c->ucol.p, c->ustart.p, nU, n, c->browCnt.p,
+            CIPC_LAUNCH(k_csr_emit, div_up(nU, 32), 288, 0, c->st, c->blkVal.p, c->csrIds.p, c->urow.p, c->ucol.p, c->ustart.p, nU, n, c->browCnt.p,
                 c->csrColIdx.p, c->csrVal.p);
         }
         c->nU = nU;

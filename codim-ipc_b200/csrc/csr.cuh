@@ -6,7 +6,7 @@
 //                         Hessians (barrier, friction) can be appended before finishing
 //   2. two stable LSD radix sorts (by column vertex, then by row vertex) of (key, block id)
 //   3. head flags + scan -> unique blocks; blocks per block-row -> scan -> block row pointer
-//   4. k_csr_emit       : one thread per unique block sums its run in sorted (= deterministic) order and writes the
+//   4. k_csr_emit       : nine threads per unique block sum its run in sorted (= deterministic) order and write the
 //                         three scalar rows' (col, value) entries; k_csr_rowptr writes the scalar row pointer
 // Included by cipc_b200.cu (block_dim_of / cipc_triplet / u32 live there).
 #pragma once
@@ -68,29 +68,23 @@ __global__ void k_csr_rowptr(const u32* __restrict__ browPtr, int nV, u32 nU, in
     const u32 b0 = browPtr[v], m = browPtr[v + 1] - b0;
     for (int a = 0; a < 3; ++a) rowPtr[3 * v + a] = (int)(9u * b0 + (u32)a * 3u * m);
 }
-__global__ void __launch_bounds__(128) k_csr_emit(const double* __restrict__ blkVal, const u32* __restrict__ ids, const u32* __restrict__ urow,
+// nine threads per unique block (one per entry of the 3x3): the 72-byte blocks of a run are read with contiguous
+// 8-byte loads across the nine threads, the run is walked in sorted order (reproducible sum)
+__global__ void __launch_bounds__(288) k_csr_emit(const double* __restrict__ blkVal, const u32* __restrict__ ids, const u32* __restrict__ urow,
     const u32* __restrict__ ucol, const u32* __restrict__ ustart, u32 nU, size_t nBlk, const u32* __restrict__ browPtr, int* __restrict__ colIdx,
     double* __restrict__ val)
 {
-    const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 u = blockIdx.x * 32u + threadIdx.x / 9u, k = threadIdx.x % 9u;
     if (u >= nU) return;
     const size_t s0 = ustart[u], s1 = (u + 1 < nU) ? (size_t)ustart[u + 1] : nBlk;
-    double acc[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    for (size_t i = s0; i < s1; ++i) { // sorted order: the sum is reproducible
-        const double* b = blkVal + (size_t)ids[i] * 9;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[k] += b[k];
-    }
+    double acc = 0.0;
+    for (size_t i = s0; i < s1; ++i) acc += blkVal[(size_t)ids[i] * 9 + k];
     const u32 vi = urow[u], vj = ucol[u];
     const u32 b0 = browPtr[vi], m = browPtr[vi + 1] - b0, t = u - b0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const size_t base = (size_t)9 * b0 + (size_t)a * 3 * m + (size_t)3 * t;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) { colIdx[base + b] = (int)(3u * vj) + b; val[base + b] = acc[a * 3 + b]; }
-    }
+    const u32 a = k / 3u, b = k - 3u * a;
+    const size_t o = (size_t)9 * b0 + (size_t)a * 3 * m + (size_t)3 * t + b;
+    colIdx[o] = (int)(3u * vj + b);
+    val[o] = acc;
 }
 
 } // namespace cipc
