@@ -361,8 +361,12 @@ __device__ __forceinline__ void cand_push(const CandOut& o, int which, int a, in
 //   * quantised-AABB overlap (fs <= 256 steps per voxel): with both fine intervals clamped to the cell's own fine
 //     range [fs c, fs c + fs-1] the test is unchanged, because each interval reaches into the cell from both sides
 //     (cell(fine lo) <= box lo <= c <= box hi <= cell(fine hi))                                                   -> 6 x 8 bits
-// code.x = lo bytes (x | y<<8 | z<<16) | start bits << 24, code.y = hi bytes.  One coalesced 8-byte load and two
-// byte-wise SIMD compares per pair replace the 24 bytes of gathers of the global test.
+// code.x = lo fields (x at bit 0, y at bit 10, z at bit 20, 8 bits each); code.y = hi fields at the same positions, a
+// guard bit above each field (bits 8, 18, 28) and the start bits at 29..31.  "lo_A <= hi_B on all three axes" is then one
+// subtraction: (hi_B | guards) - lo_A keeps every guard bit exactly when no field borrows.  One coalesced 8-byte load
+// and ~7 integer instructions per pair replace the 24 bytes of gathers of the global test (byte-wise SIMD compares are
+// emulated with a dozen instructions each on this architecture and were 70% of the kernel's instruction count).
+constexpr u32 CODE_GUARDS = (1u << 8) | (1u << 18) | (1u << 28);
 __global__ void k_entry_codes(const u32* __restrict__ keys, const u32* __restrict__ vals, u32 nE, int nBN, int nBE,
     const u64* __restrict__ boxLo, const ulonglong2* __restrict__ fine, GridDesc G, uint2* __restrict__ codes)
 {
@@ -379,16 +383,16 @@ __global__ void k_entry_codes(const u32* __restrict__ keys, const u32* __restric
     u32 a = 0, b = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        a |= (u32)clampi(fl[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (8 * d);
-        b |= (u32)clampi(fh[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (8 * d);
-        if (l[d] == c[d]) a |= 1u << (24 + d);
+        a |= (u32)clampi(fl[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (10 * d);
+        b |= (u32)clampi(fh[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (10 * d);
+        if (l[d] == c[d]) b |= 1u << (29 + d);
     }
-    codes[i] = make_uint2(a, b);
+    codes[i] = make_uint2(a, b | CODE_GUARDS);
 }
 __device__ __forceinline__ bool code_pair_ok(const uint2 a, const uint2 b)
 {
-    const u32 ov = __vcmpleu4(a.x, b.y) & __vcmpleu4(b.x, a.y); // per byte: loA <= hiB and loB <= hiA
-    return (ov & 0x00ffffffu) == 0x00ffffffu && (((a.x | b.x) >> 24) & 7u) == 7u;
+    const u32 t = (b.y - a.x) & (a.y - b.x) & CODE_GUARDS; // guards survive <=> lo_A <= hi_B and lo_B <= hi_A per axis
+    return t == CODE_GUARDS && (a.y | b.y) >= 0xE0000000u; // and on every axis one of the two boxes starts in this cell
 }
 
 // Work items of the pair enumeration: a cell's point queries and edge queries are cut into tasks of `qch` queries,
@@ -634,7 +638,7 @@ __device__ __forceinline__ void narrow_append(const NarrowOut& out, int which, c
 }
 // IPC.h:189-257.  The closest-feature type selects the operands first, so a warp runs at most three distance bodies
 // (point-point, point-edge, point-triangle) instead of one per type; the arithmetic of each body is unchanged.
-__global__ void __launch_bounds__(NARROW_BT) k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_,
+__global__ void __launch_bounds__(NARROW_BT, 4) k_narrow_pt(Topo T, const double4* __restrict__ X, const int2* __restrict__ cand, u32 n, double dHat2_,
     NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -674,7 +678,7 @@ __global__ void k_rest_len2(const double4* __restrict__ X0, const int2* __restri
     out[e] = norm2(ldx(X0, ed.x) - ldx(X0, ed.y)).v;
 }
 // IPC.h:414-564
-__global__ void __launch_bounds__(NARROW_BT) k_narrow_ee(Topo T, const double4* __restrict__ X, const double* __restrict__ restLen2,
+__global__ void __launch_bounds__(NARROW_BT, 4) k_narrow_ee(Topo T, const double4* __restrict__ X, const double* __restrict__ restLen2,
     const int2* __restrict__ cand, u32 n, double dHat2_, NarrowOut out)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1687,23 +1691,36 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
         sl.s1 = bound(c->rank + 1);
         CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
     }
-    device_excl_scan(c->cnt.p, c->cnt.p, nP, c->scanwk, c->st);
     u32 nE;
-    CIPC_CUDA(cudaMemcpyAsync(&nE, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+    {
+        cipc_ctx::Scope s1(c, "hb_count_scan");
+        device_excl_scan(c->cnt.p, c->cnt.p, nP, c->scanwk, c->st);
+        CIPC_CUDA(cudaMemcpyAsync(&nE, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+    }
     CIPC_CUDA(cudaStreamSynchronize(c->st));
     H.nEntries = nE;
     c->keys.reserve(nE, c->st); c->vals.reserve(nE, c->st); c->heads.reserve(nE, c->st); c->headScan.reserve(nE, c->st);
     if (nE == 0) { H.nCells = 0; return; }
-    CIPC_LAUNCH(k_emit_entries, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, c->cnt.p, sl, c->keys.p, c->vals.p);
+    {
+        cipc_ctx::Scope s2(c, "hb_emit");
+        CIPC_LAUNCH(k_emit_entries, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, c->cnt.p, sl, c->keys.p, c->vals.p);
+    }
     const double cells = (double)H.G.gx * H.G.gy * H.G.gz;
     int bits = 2;
     while ((double)(1ULL << (bits - 2)) < cells) ++bits;
-    device_radix_sort(c->keys.p, c->vals.p, nE, bits, c->sortwk, c->st);
-    CIPC_LAUNCH(k_cell_heads, div_up(nE, TB), TB, 0, c->st, c->keys.p, nE, c->heads.p);
-    device_excl_scan(c->heads.p, c->headScan.p, nE, c->scanwk, c->st);
+    {
+        cipc_ctx::Scope s3(c, "hb_sort");
+        device_radix_sort(c->keys.p, c->vals.p, nE, bits, c->sortwk, c->st);
+    }
     u32 nCells;
-    CIPC_CUDA(cudaMemcpyAsync(&nCells, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+    {
+        cipc_ctx::Scope s4(c, "hb_heads");
+        CIPC_LAUNCH(k_cell_heads, div_up(nE, TB), TB, 0, c->st, c->keys.p, nE, c->heads.p);
+        device_excl_scan(c->heads.p, c->headScan.p, nE, c->scanwk, c->st);
+        CIPC_CUDA(cudaMemcpyAsync(&nCells, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+    }
     CIPC_CUDA(cudaStreamSynchronize(c->st));
+    cipc_ctx::Scope s5(c, "hb_tables");
     H.nCells = nCells;
     c->ks.reserve((size_t)nCells * 4, c->st);
     CIPC_LAUNCH(k_kind_starts, div_up((size_t)nE + 1, TB), TB, 0, c->st, c->keys.p, c->headScan.p, c->heads.p, nE, c->ks.p);

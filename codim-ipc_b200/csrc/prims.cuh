@@ -3,6 +3,7 @@
 // Grids are sized from the tile count; all kernels are bandwidth-bound streaming kernels.
 #pragma once
 #include "util.cuh"
+#include <cstdlib>
 
 namespace cipc {
 
@@ -104,9 +105,64 @@ __global__ void k_scan_apply(const u32* __restrict__ in, u32* __restrict__ out, 
     }
 }
 
+// Single-pass scan (decoupled look-back): tiles take a ticket in launch order, publish their aggregate, and resolve
+// their exclusive prefix from the descriptors of the preceding tiles (flag in the high word: 1 = aggregate only,
+// 2 = inclusive prefix).  One kernel and one read of the input instead of three kernels and two reads; the hash build
+// runs a dozen scans per contact stage, most of them launch-latency bound.
+__global__ void __launch_bounds__(SCAN_BT) k_scan_onepass(const u32* __restrict__ in, u32* __restrict__ out, size_t n, u64* desc, u32* ticket,
+    u32* total, u32 nt)
+{
+    __shared__ u32 sTile, sPrefix;
+    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = sTile;
+    const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_IT;
+    u32 v[SCAN_IT], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_IT; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        s += v[i];
+    }
+    u32 tileTotal;
+    u32 ex = block_excl_scan<SCAN_BT>(s, tileTotal);
+    if (threadIdx.x < 32) { // warp 0 publishes the aggregate and looks back 32 descriptors at a time
+        volatile u64* d = desc;
+        const int lane = threadIdx.x;
+        u32 prefix = 0;
+        if (lane == 0) d[tile] = ((u64)(tile == 0 ? 2 : 1) << 32) | tileTotal;
+        if (tile != 0) {
+            for (int j0 = (int)tile - 1;; j0 -= 32) {
+                const int j = j0 - lane;
+                u64 w = (u64)2 << 32; // before the first tile: inclusive prefix 0
+                if (j >= 0) do { w = d[j]; } while ((w >> 32) == 0);
+                const u32 isP = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+                const int firstP = isP ? __ffs(isP) - 1 : 31; // nearest tile that already knows its inclusive prefix
+                u32 c = (lane <= firstP) ? (u32)w : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                prefix += c;
+                if (isP) break;
+            }
+            if (lane == 0) d[tile] = ((u64)2 << 32) | (u32)(prefix + tileTotal);
+        }
+        if (lane == 0) {
+            sPrefix = prefix;
+            if (tile == nt - 1) *total = prefix + tileTotal;
+        }
+    }
+    __syncthreads();
+    ex += sPrefix;
+#pragma unroll
+    for (int i = 0; i < SCAN_IT; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+}
+
 struct ScanWork {
     DevBuf<u32> tileSum;
     DevBuf<u32> total;
+    DevBuf<u64> desc; // [0] = ticket counter (low word), [1..] = tile descriptors
 };
 // out[i] = sum_{j<i} in[j]; *total (device) = sum of all.  in may alias out.
 static inline void device_excl_scan(const u32* in, u32* out, size_t n, ScanWork& wk, cudaStream_t s)
@@ -114,6 +170,15 @@ static inline void device_excl_scan(const u32* in, u32* out, size_t n, ScanWork&
     wk.total.reserve(1, s);
     if (n == 0) { CIPC_CUDA(cudaMemsetAsync(wk.total.p, 0, sizeof(u32), s)); return; }
     const int nt = div_up(n, SCAN_TILE);
+    // default: three streaming kernels; CIPC_SCAN_1PASS=1 selects the decoupled look-back kernel (same speed in the hash build
+    // at 1M triangles: the scans there are not the limiter)
+    static const bool onePass = getenv("CIPC_SCAN_1PASS") != nullptr;
+    if (onePass) {
+        wk.desc.reserve((size_t)nt + 1, s);
+        CIPC_CUDA(cudaMemsetAsync(wk.desc.p, 0, ((size_t)nt + 1) * sizeof(u64), s));
+        CIPC_LAUNCH(k_scan_onepass, nt, SCAN_BT, 0, s, in, out, n, wk.desc.p + 1, (u32*)wk.desc.p, wk.total.p, (u32)nt);
+        return;
+    }
     wk.tileSum.reserve(nt, s);
     CIPC_LAUNCH(k_scan_tile_sums, nt, SCAN_BT, 0, s, in, wk.tileSum.p, n);
     CIPC_LAUNCH(k_scan_tile_offsets, 1, 1024, 0, s, wk.tileSum.p, nt, wk.total.p);

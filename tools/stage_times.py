@@ -14,6 +14,7 @@ for rep in range(2):
     n = ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
     for s in ("ccs_hash_build", "ccs_pairs", "ccs_narrow", "ccs_merge"):
         out[s] = ctx.stage_ms(s)
+    hb = {s: round(ctx.stage_ms(s), 3) for s in ("hb_count_scan", "hb_emit", "hb_sort", "hb_heads", "hb_tables")}
     cnt = {k: ctx.counter(k) for k in ("hash_entries", "hash_cells", "candidates_pt", "candidates_ee", "candidates_pe", "candidates_pp", "constraints")}
     ctx.barrier_energy_dev(sc["dHat2"], sc["kappa"], sc["xi"]); out["E"] = ctx.stage_ms("barrier_E")
     ctx.barrier_gradient_dev(sc["dHat2"], sc["kappa"], sc["xi"]); out["g"] = ctx.stage_ms("barrier_g")
@@ -28,4 +29,5 @@ for rep in range(2):
     ctx.min_dist2_dev(sc["xi"]); out["min_dist"] = ctx.stage_ms("min_dist")
 print(name, "nV", len(sc["X"]), "tris", len(sc["BT"]), "edges", len(sc["BE"]))
 print({k: round(v, 3) for k, v in out.items()}, "total", round(sum(out.values()), 2))
+print("ccs hash build detail", hb)
 print(cnt)
