@@ -262,8 +262,9 @@ def main():
             nF = ctx.friction_basis(dHat2, kappa, xi, fetch=False); friction["basis"] = ctx.stage_ms("friction_basis")
             ctx.friction_energy_dev(1e-10, 0.4); friction["E"] = ctx.stage_ms("friction_E")
             ctx.friction_gradient_dev(1e-10, 0.4, accumulate=False); friction["g"] = ctx.stage_ms("friction_g")
-            nFT = ctx.friction_hessian(1e-10, 0.4, True, fetch=False); friction["H_factor"] = ctx.stage_ms("friction_H")
-            ctx.dev_triplets(); friction["H_expand"] = ctx.stage_ms("k_barrier_hessian")
+            nFT = ctx.friction_hessian(1e-10, 0.4, True, fetch=False); friction["H_factor_only"] = ctx.stage_ms("friction_H")
+            ctx.dev_triplets(); friction["H_expand_only"] = ctx.stage_ms("k_barrier_hessian")
+            ctx.friction_hessian_dev(1e-10, 0.4, True); friction["H_fused"] = ctx.stage_ms("friction_H")
         friction = {k: round(v, 4) for k, v in friction.items()}
         friction["stencils"] = int(nF); friction["triplets"] = int(nFT)
 

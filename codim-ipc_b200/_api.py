@@ -287,6 +287,12 @@ class ContactContext:
             self._ck(self.L.cipc_get_triplets(self.h, trip.ctypes.data_as(C.c_void_p)))
         return trip[:n.value]
 
+    def friction_hessian_dev(self, epsvh2, mu, projectSPD=True):
+        """friction blocks computed and expanded on the device in one fused pass; the stream stays in HBM"""
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_friction_hessian_dev(self.h, C.c_double(epsvh2), C.c_double(mu), int(projectSPD), C.byref(n)))
+        return n.value
+
     def friction_energy_dev(self, epsvh2, mu):
         self._ck(self.L.cipc_friction_energy_dev(self.h, C.c_double(epsvh2), C.c_double(mu)))
 

@@ -1187,6 +1187,48 @@ __global__ void __launch_bounds__(256) k_hessian_expand_tiled(const double* __re
         if (STREAM) __stcs(dst, o); else *dst = o;
     }
 }
+// Expansion, warp by warp: a warp expands the (up to) 32 stencils whose factors its own lanes parked in shared memory
+// (stencil q of the CTA: factors at sY + q*YS, header {offset, v0..v3, sign} at sH + q*8).  No CTA barrier is involved:
+// warps stay decoupled, so one warp's store stream overlaps the others' arithmetic.  Lane l owns the fixed block entries
+// e = l + 32 j of every stencil; (row, col) decoding is hoisted out of the stencil loop and a warp writes 512 contiguous
+// bytes per store instruction.
+template <int NN, int NY, int YS>
+__device__ __forceinline__ void warp_expand_stencils(const double* sY, const int* sH, u32 wq0, u32 g, u32 lane, cipc_triplet* __restrict__ trip)
+{
+    constexpr int PER = NN * NN, NJ = (PER + 31) / 32;
+    int rI[NJ], cI[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int e = (int)lane + 32 * j;
+        rI[j] = e / NN; cI[j] = e - rI[j] * NN;
+    }
+    const u32 wn = (wq0 < g) ? min(32u, g - wq0) : 0u;
+    for (u32 qq = 0; qq < wn; ++qq) {
+        const int* h = sH + (wq0 + qq) * 8;
+        const u32 o = (u32)h[0];
+        if (o == 0xffffffffu) continue;
+        const double* y = sY + (wq0 + qq) * YS;
+        const bool neg = h[5] != 0;
+        cipc_triplet* dst = trip + (size_t)o * 9;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int e = (int)lane + 32 * j;
+            if (NJ * 32 == PER || e < PER) {
+                const int r = rI[j], c = cI[j];
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
+                if (neg) v = -v;
+                const int ri = r / 3, ci = c / 3;
+                int4 w;
+                w.x = h[1 + ri] * 3 + (r - 3 * ri); w.y = h[1 + ci] * 3 + (c - 3 * ci);
+                const long long bb = __double_as_longlong(v);
+                w.z = (int)(bb & 0xffffffffLL); w.w = (int)(bb >> 32);
+                __stcs(reinterpret_cast<int4*>(dst + e), w);
+            }
+        }
+    }
+}
 // Fused factor + expansion for the device-resident triplet stream: a CTA of 128 threads factors 128 stencils (FP64
 // pipe, one stencil per thread), parks the factors in shared memory, and then all threads turn them into triplets with
 // coalesced streaming 16-byte stores (HBM).  CTAs resident on one SM are in different phases, so the FP64 work of one
@@ -1203,7 +1245,7 @@ __global__ void __launch_bounds__(FUSED_BD, 3) k_hessian_fused(const double4* __
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
     cipc_triplet* __restrict__ trip, u32* denseList, u32* denseCount)
 {
-    constexpr int NN = FusedShape<CLS>::NN, NY = FusedShape<CLS>::NY, YS = FusedShape<CLS>::YS, PER = NN * NN;
+    constexpr int NN = FusedShape<CLS>::NN, NY = FusedShape<CLS>::NY, YS = FusedShape<CLS>::YS;
     extern __shared__ __align__(16) unsigned char fused_sm[];
     double* sY = reinterpret_cast<double*>(fused_sm);
     int* sH = reinterpret_cast<int*>(fused_sm + FUSED_BD * YS * 8);
@@ -1217,7 +1259,7 @@ __global__ void __launch_bounds__(FUSED_BD, 3) k_hessian_fused(const double4* __
         const double alpha = wm * barrier_H(bp.elastic, d, bp.dHat2, bp.k0);
         const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
         int* h = sH + threadIdx.x * 8;
-        h[1] = s.v[0]; h[2] = s.v[1]; h[3] = s.v[2]; h[4] = s.v[3];
+        h[1] = s.v[0]; h[2] = s.v[1]; h[3] = s.v[2]; h[4] = s.v[3]; h[5] = 0;
         if (!(beta < 0.0) || !(alpha > 0.0)) { // outside the barrier's support: dense path (see k_hessian_factor)
             h[0] = (int)0xffffffffu;
             denseList[atomicAdd(denseCount, 1u)] = i;
@@ -1236,47 +1278,12 @@ __global__ void __launch_bounds__(FUSED_BD, 3) k_hessian_fused(const double4* __
             for (int k = 0; k < NY * NN; ++k) y[k] = Y[k];
         }
     }
-    // Expansion, warp by warp: every warp expands the 32 stencils its own lanes just factored (no CTA barrier: warps
-    // stay decoupled, so one warp's store stream overlaps the others' FP64 work).  Lane l owns the fixed block entries
-    // e = l + 32 j of every stencil; (row, col) decoding is hoisted out of the stencil loop and a warp writes 512
-    // contiguous bytes per store instruction.
     __syncwarp();
-    const u32 lane = threadIdx.x & 31u, wq0 = threadIdx.x & ~31u;
-    constexpr int NJ = (PER + 31) / 32;
-    int rI[NJ], cI[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int e = (int)lane + 32 * j;
-        rI[j] = e / NN; cI[j] = e - rI[j] * NN;
-    }
-    const u32 wn = (wq0 < g) ? min(32u, g - wq0) : 0u;
-    for (u32 qq = 0; qq < wn; ++qq) {
-        const int* h = sH + (wq0 + qq) * 8;
-        const u32 o = (u32)h[0];
-        if (o == 0xffffffffu) continue;
-        const double* y = sY + (wq0 + qq) * YS;
-        cipc_triplet* dst = trip + (size_t)o * 9;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int e = (int)lane + 32 * j;
-            if (NJ * 32 == PER || e < PER) {
-                const int r = rI[j], c = cI[j];
-                double v = 0.0;
-#pragma unroll
-                for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
-                const int ri = r / 3, ci = c / 3;
-                int4 w;
-                w.x = h[1 + ri] * 3 + (r - 3 * ri); w.y = h[1 + ci] * 3 + (c - 3 * ci);
-                const long long bb = __double_as_longlong(v);
-                w.z = (int)(bb & 0xffffffffLL); w.w = (int)(bb >> 32);
-                __stcs(reinterpret_cast<int4*>(dst + e), w);
-            }
-        }
-    }
+    warp_expand_stencils<NN, NY, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, trip);
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 constexpr int DENSE_BD = 64;                              // threads per block of the dense path
-constexpr int DENSE_SMEM = 2 * 81 * DENSE_BD * 8;         // 9x9 matrix + eigenvectors per thread
+constexpr int DENSE_SMEM = (45 + 81) * DENSE_BD * 8;       // upper triangle of the 9x9 matrix + eigenvectors per thread
 __global__ void __launch_bounds__(DENSE_BD) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
     const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
     const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip)
@@ -1943,7 +1950,7 @@ int do_friction_gradient(cipc_ctx* c, double epsvh2, double mu, bool accumulate)
         std::sqrt(epsvh2), mu, c->g.p);
     return CIPC_OK;
 }
-int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu)
+int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu, bool devTriplets)
 {
     need(c->haveX && c->haveXn, "positions / previous positions not set");
     c->nTrip = 0;
@@ -1966,12 +1973,24 @@ int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu)
     need(nk[3] == 0, "mollified stencil in the friction constraint set");
     c->nTrip = (int64_t)tot * 9;
     c->trip.reserve((size_t)c->nTrip, c->st);
+    const double epsvh = std::sqrt(epsvh2);
+    if (devTriplets) {
+        // device-resident stream: factors go through shared memory only (k_friction_fused)
+        cipc_ctx::Scope sk(c, "k_friction_fused");
+        if (nk[0]) CIPC_LAUNCH(k_friction_fused<0>, div_up(nk[0], FUSED_BD), FUSED_BD, FrFusedShape<0>::SMEM, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p,
+            c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[0].p, nk[0], epsvh, epsvh2, mu, c->trip.p);
+        if (nk[1]) CIPC_LAUNCH(k_friction_fused<1>, div_up(nk[1], FUSED_BD), FUSED_BD, FrFusedShape<1>::SMEM, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p,
+            c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[1].p, nk[1], epsvh, epsvh2, mu, c->trip.p);
+        if (nk[2]) CIPC_LAUNCH(k_friction_fused<2>, div_up(nk[2], FUSED_BD), FUSED_BD, FrFusedShape<2>::SMEM, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p,
+            c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[2].p, nk[2], epsvh, epsvh2, mu, c->trip.p);
+        for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
+    }
+    else {
     const size_t ydoubles = (size_t)nk[0] * 24 + (size_t)nk[1] * 18 + (size_t)nk[2] * 12;
     c->Y.reserve(ydoubles + 4, c->st);
     c->yhdr.reserve((size_t)nk[0] + nk[1] + nk[2] + 1, c->st);
     double* Y0 = c->Y.p; double* Y1 = Y0 + (size_t)nk[0] * 24; double* Y2 = Y1 + (size_t)nk[1] * 18;
     YHdr* h0 = (YHdr*)c->yhdr.p; YHdr* h1 = h0 + nk[0]; YHdr* h2 = h1 + nk[1];
-    const double epsvh = std::sqrt(epsvh2);
     {
         cipc_ctx::Scope sk(c, "k_friction_factor");
         if (nk[0]) CIPC_LAUNCH(k_friction_factor<0>, div_up(nk[0], 128), 128, 0, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p, c->fB.p, c->fnf.p,
@@ -1986,6 +2005,7 @@ int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu)
     c->Y0 = Y0; c->Y1 = Y1; c->Y2 = Y2; c->h0 = h0; c->h1 = h1; c->h2 = h2;
     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
     c->ny[0] = c->ny[1] = c->ny[2] = 2;
+    }
     c->ctr["friction_4pt"] = nk[0]; c->ctr["friction_pe"] = nk[1]; c->ctr["friction_pp"] = nk[2];
     return CIPC_OK;
 }
@@ -2177,6 +2197,9 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
         CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<0>::SMEM));
         CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<1>::SMEM));
         CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<2>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute(k_friction_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<0>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute(k_friction_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<1>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute(k_friction_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<2>::SMEM));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
     }
     catch (const std::exception& e) {
@@ -2785,7 +2808,17 @@ int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSP
     (void)projectSPD; // the inner 2x2 matrix is positive semi-definite in closed form: makePD is the identity (friction.cuh)
     return guarded(ctx, [&]() {
         ctx->begin_call();
-        int r = do_friction_hessian(ctx, epsvh2, mu);
+        int r = do_friction_hessian(ctx, epsvh2, mu, false);
+        if (nTrip) *nTrip = ctx->nTrip;
+        return r;
+    });
+}
+int cipc_friction_hessian_dev(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTrip)
+{
+    (void)projectSPD;
+    return guarded(ctx, [&]() {
+        ctx->begin_call();
+        int r = do_friction_hessian(ctx, epsvh2, mu, true);
         if (nTrip) *nTrip = ctx->nTrip;
         return r;
     });

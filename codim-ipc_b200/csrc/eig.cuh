@@ -74,14 +74,16 @@ CIPC_HD void psd_project_jacobi(double* A)
 // outside the barrier's support).  Every block annihilates rigid translations (H t = 0 for t = (c,c,..,c)), so it
 // is first compressed with an orthonormal Helmert basis Q of the translation-free subspace:  M = Q H Q^T is
 // (N-3) x (N-3), H+ = Q^T M+ Q.  The cyclic Jacobi iteration then runs on M with matrix and eigenvectors held in
-// SHARED memory, element (i,j) of thread t at sm[(i*K+j)*BD + t] (bank-conflict free), instead of thread-local
+// SHARED memory (upper triangle of M + full eigenvector matrix, element e of thread t at sm[e*BD + t]: bank-conflict
+// free, 63 KB per 64 threads -> three CTAs per SM), instead of thread-local
 // arrays that spill to L1/L2.  H: N x N row-major (N = 3*nb) in local memory, replaced by its PSD projection.
 __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, int tid, int BD)
 {
     const int N = 3 * nb, K = N - 3;
-    double* A = sm;                 // K*K
-    double* V = sm + 81 * BD;       // K*K (capacity 81 each)
-#define SA(i, j) A[((i) * K + (j)) * BD + tid]
+    double* A = sm;                 // upper triangle of the symmetric K x K matrix (capacity 45)
+    double* V = sm + 45 * BD;       // K*K eigenvectors (capacity 81)
+    auto tri = [&](int i, int j) { const int a = i < j ? i : j, b = i < j ? j : i; return a * (2 * K - a + 1) / 2 + (b - a); };
+#define SA(i, j) A[tri((i), (j)) * BD + tid]
 #define SV(i, j) V[((i) * K + (j)) * BD + tid]
     // Helmert rows h_k (k = 1..nb-1): k entries 1/sqrt(k(k+1)), then -k/sqrt(k(k+1)), then zeros
     double hc[3], hd[3];
@@ -92,14 +94,16 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
         for (int a = 0; a < 3; ++a)
             for (int l = 0; l < nb - 1; ++l)
                 for (int b = 0; b < 3; ++b) {
+                    const int r = 3 * k + a, c = 3 * l + b;
+                    SV(r, c) = (r == c) ? 1.0 : 0.0;
+                    if (r > c) continue; // symmetric: only the upper triangle is formed and stored
                     double s = 0.0;
                     for (int I = 0; I <= k + 1; ++I) {
                         const double hI = helm(k, I);
                         for (int J = 0; J <= l + 1; ++J) s += hI * helm(l, J) * H[(3 * I + a) * N + 3 * J + b];
                     }
-                    SA(3 * k + a, 3 * l + b) = s;
-                    SV(3 * k + a, 3 * l + b) = (k == l && a == b) ? 1.0 : 0.0;
-                    fro += s * s;
+                    SA(r, c) = s;
+                    fro += (r == c ? 1.0 : 2.0) * s * s;
                 }
     if (fro > 0.0) {
         const double tol = 1e-28 * fro;
@@ -120,8 +124,8 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
                         if (k != p && k != q) {
                             const double akp = SA(k, p), akq = SA(k, q);
                             const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
-                            SA(k, p) = np_; SA(p, k) = np_;
-                            SA(k, q) = nq_; SA(q, k) = nq_;
+                            SA(k, p) = np_;
+                            SA(k, q) = nq_;
                         }
                         const double vkp = SV(k, p), vkq = SV(k, q);
                         SV(k, p) = c * vkp - s * vkq;
@@ -130,7 +134,6 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
                     SA(p, p) = app - t * apq;
                     SA(q, q) = aqq + t * apq;
                     SA(p, q) = 0.0;
-                    SA(q, p) = 0.0;
                 }
         }
     }
@@ -142,7 +145,6 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
             double s = 0.0;
             for (int k = 0; k < K; ++k) s += lam[k] * SV(i, k) * SV(j, k);
             SA(i, j) = s;
-            SA(j, i) = s;
         }
     // H+ = Q^T M+ Q
     for (int I = 0; I < nb; ++I)

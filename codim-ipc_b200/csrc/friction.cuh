@@ -207,15 +207,12 @@ __global__ void __launch_bounds__(128) k_friction_gradient(const double4* __rest
 //   |u| >= eps_v h : l_a = f1/|u|^2 along ubar = (-u1, u0) (unnormalised), l_b = 0          (:440-444)
 //   |u| == 0       : f1 * I                                                                    (:446-449)
 //   otherwise      : f1 + f2 |u| = 2 (eps - |u|) / eps^2 >= 0 along u/|u|,  f1 > 0 along ubar/|u|   (:451-462; makePD is the identity)
+// factors of friction stencil i: Y = [y_a | y_b] (2 x 3nb doubles), vertex ids, sign of the block
 template <int CLS>
-__global__ void __launch_bounds__(128) k_friction_factor(const double4* __restrict__ X, const double4* __restrict__ Xn,
-    const int4* __restrict__ fcs, const double2* __restrict__ fcp, const double* __restrict__ fB, const double* __restrict__ fnf,
-    const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, double epsvh, double epsvh2, double mu, double* __restrict__ Yout,
-    YHdr* __restrict__ hdr)
+__device__ __forceinline__ void friction_factor_one(const double4* __restrict__ X, const double4* __restrict__ Xn, const int4* __restrict__ fcs,
+    const double2* __restrict__ fcp, const double* __restrict__ fB, const double* __restrict__ fnf, u32 i, double epsvh, double epsvh2, double mu,
+    double* Y, int* v, bool& neg)
 {
-    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const u32 i = idx[q];
     const int4 c = fcs[i];
     const double2 cp = fcp[i];
     const FrStencil s = fr_decode(c, cp);
@@ -242,19 +239,65 @@ __global__ void __launch_bounds__(128) k_friction_factor(const double4* __restri
     const double wa[3] = {B.b0.x * qa[0] + B.b1.x * qa[1], B.b0.y * qa[0] + B.b1.y * qa[1], B.b0.z * qa[0] + B.b1.z * qa[1]};
     const double wb[3] = {B.b0.x * qb[0] + B.b1.x * qb[1], B.b0.y * qb[0] + B.b1.y * qb[1], B.b0.z * qb[0] + B.b1.z * qb[1]};
     constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2), NN = 3 * NB;
-    double Y[2 * NN];
 #pragma unroll
     for (int k = 0; k < NB; ++k)
 #pragma unroll
         for (int a = 0; a < 3; ++a) { Y[3 * k + a] = s.coef[k] * wa[a]; Y[NN + 3 * k + a] = s.coef[k] * wb[a]; }
+    v[0] = s.v[0]; v[1] = s.v[1]; v[2] = s.v[2]; v[3] = s.v[3];
+    neg = sc < 0.0;
+}
+template <int CLS>
+__global__ void __launch_bounds__(128) k_friction_factor(const double4* __restrict__ X, const double4* __restrict__ Xn,
+    const int4* __restrict__ fcs, const double2* __restrict__ fcp, const double* __restrict__ fB, const double* __restrict__ fnf,
+    const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, double epsvh, double epsvh2, double mu, double* __restrict__ Yout,
+    YHdr* __restrict__ hdr)
+{
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const u32 i = idx[q];
+    constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2), NN = 3 * NB;
+    double Y[2 * NN];
+    YHdr h;
+    bool neg;
+    friction_factor_one<CLS>(X, Xn, fcs, fcp, fB, fnf, i, epsvh, epsvh2, mu, Y, h.v, neg);
     double2* o = reinterpret_cast<double2*>(Yout + (size_t)q * (2 * NN));
 #pragma unroll
     for (int k = 0; k < NN; ++k) o[k] = make_double2(Y[2 * k], Y[2 * k + 1]);
-    YHdr h;
     h.off = off[i];
-    h.v[0] = s.v[0]; h.v[1] = s.v[1]; h.v[2] = s.v[2]; h.v[3] = s.v[3];
-    h.pad[0] = sc < 0.0 ? 1 : 0; h.pad[1] = h.pad[2] = 0;
+    h.pad[0] = neg ? 1 : 0; h.pad[1] = h.pad[2] = 0;
     hdr[q] = h;
+}
+// Fused factor + expansion (device-resident triplet stream, cipc_friction_hessian_dev): same structure as k_hessian_fused.
+// The friction factors are cheap (no eigenproblem), so this kernel is a pure store stream.
+template <int CLS> struct FrFusedShape {
+    static constexpr int NN = 3 * ((CLS == 0) ? 4 : (CLS == 1 ? 3 : 2)), YD = 2 * NN, YS = YD + 1;
+    static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
+};
+template <int CLS>
+__global__ void __launch_bounds__(FUSED_BD) k_friction_fused(const double4* __restrict__ X, const double4* __restrict__ Xn,
+    const int4* __restrict__ fcs, const double2* __restrict__ fcp, const double* __restrict__ fB, const double* __restrict__ fnf,
+    const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, double epsvh, double epsvh2, double mu, cipc_triplet* __restrict__ trip)
+{
+    constexpr int NN = FrFusedShape<CLS>::NN, YS = FrFusedShape<CLS>::YS;
+    extern __shared__ __align__(16) unsigned char fr_fused_sm[];
+    double* sY = reinterpret_cast<double*>(fr_fused_sm);
+    int* sH = reinterpret_cast<int*>(fr_fused_sm + FUSED_BD * YS * 8);
+    const u32 q0 = blockIdx.x * FUSED_BD;
+    const u32 g = min((u32)FUSED_BD, n - q0);
+    if (threadIdx.x < g) {
+        const u32 i = idx[q0 + threadIdx.x];
+        double Y[2 * NN];
+        int* h = sH + threadIdx.x * 8;
+        bool neg;
+        friction_factor_one<CLS>(X, Xn, fcs, fcp, fB, fnf, i, epsvh, epsvh2, mu, Y, h + 1, neg);
+        h[0] = (int)off[i];
+        h[5] = neg ? 1 : 0;
+        double* y = sY + threadIdx.x * YS;
+#pragma unroll
+        for (int k = 0; k < 2 * NN; ++k) y[k] = Y[k];
+    }
+    __syncwarp();
+    warp_expand_stencils<NN, 2, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, trip);
 }
 
 } // namespace cipc

@@ -42,8 +42,11 @@ CIPC_HD void jacobi_psd_small(double (&A)[K][K])
 #pragma unroll
         for (int j = 0; j < K; ++j) fro += A[i][j] * A[i][j];
     if (fro == 0.0) return;
-    const double tol = 1e-32 * fro;
-    for (int sweep = 0; sweep < 12; ++sweep) {
+    const double tol = 1e-30 * fro;
+    // rotation angles in fp32 on entries scaled by 1/||A||, rotations orthogonal to fp64 rounding and applied as exact
+    // similarity transforms (see hess4_factor): the sweeps converge to the fp64 tolerance above
+    const double iscale = cipc_rsqrt(fro);
+    for (int sweep = 0; sweep < 14; ++sweep) {
         double off = 0.0;
 #pragma unroll
         for (int p = 0; p < K - 1; ++p)
@@ -56,13 +59,22 @@ CIPC_HD void jacobi_psd_small(double (&A)[K][K])
             for (int q = p + 1; q < K; ++q) {
                 const double apq = A[p][q];
                 if (apq * apq > 1e-36 * fro) {
-                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                    A[p][p] -= t * apq;
-                    A[q][q] += t * apq;
-                    A[p][q] = 0.0;
-                    A[q][p] = 0.0;
+                    const double app = A[p][p], aqq = A[q][q];
+                    const float df = (float)((aqq - app) * iscale), af = (float)(apq * iscale) * 2.0f;
+#if defined(__CUDA_ARCH__)
+                    const float h2 = fmaf(df, df, af * af);
+                    const float tf = __fdividef(df >= 0.0f ? af : -af, fabsf(df) + h2 * rsqrtf(h2));
+#else
+                    const float tf = (df >= 0.0f ? af : -af) / (fabsf(df) + sqrtf(df * df + af * af));
+#endif
+                    const double t = (double)tf;
+                    const double c = cipc_rsqrt(t * t + 1.0), s = t * c;
+                    const double cc = c * c, ss = s * s, cs = c * s;
+                    A[p][p] = cc * app - 2.0 * cs * apq + ss * aqq;
+                    A[q][q] = ss * app + 2.0 * cs * apq + cc * aqq;
+                    const double npq = cs * (app - aqq) + (cc - ss) * apq;
+                    A[p][q] = npq;
+                    A[q][p] = npq;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         if (k != p && k != q) {

@@ -126,6 +126,8 @@ int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSP
  * when accumulate != 0 (e.g. after cipc_barrier_gradient_dev) */
 int cipc_friction_energy_dev(cipc_ctx* ctx, double epsvh2, double mu);
 int cipc_friction_gradient_dev(cipc_ctx* ctx, double epsvh2, double mu, int accumulate);
+/* Compute_Friction_Hessian with the triplet stream left in HBM (cipc_dev_triplets), fused like cipc_barrier_hessian_dev */
+int cipc_friction_hessian_dev(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTriplets_out);
 
 /* ---- device-resident line search ------------------------------------------------------------
  * Shell/IMPLICIT_EULER.h:102-131 evaluates X = Xprev + alpha p, Compute_Constraint_Set and Compute_Min_Dist2 per

@@ -52,3 +52,12 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "").lower() or f == "hess.cuh" or True
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("tests/", ""), f
+
+
+def test_shim_headers_compile_with_reference_signatures():
+    """the drop-in shims (codim-ipc_b200/shim/FEM/IPC.h, FRICTION.h) compile against stand-ins of the reference's
+    container types when driven with the reference's call signatures (no GPU needed: syntax / overload check only)"""
+    import subprocess
+    for src in ("main.cpp", "friction_main.cpp"):
+        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "codim-ipc_b200", "shim"), "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.join(ROOT, "tests", "shim_harness", "stub"), os.path.join(ROOT, "tests", "shim_harness", src)])

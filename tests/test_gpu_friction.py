@@ -196,3 +196,21 @@ def test_friction_device_resident_accumulates(ctx):
     scal = multi.wrap_device_f64(ctx.dev_ptrs()["scalars"], 16, 0).cpu().numpy()
     assert np.abs(g - (gb + gf)).max() <= 1e-12 * np.abs(gb + gf).max()
     assert scal[4] == Ef
+
+
+def test_fused_friction_hessian_equals_factor_path(ctx):
+    """cipc_friction_hessian_dev (fused factor + expansion, stream left in HBM) == factor kernel + host expansion"""
+    from codim_ipc_b200 import scenes
+    sc = scenes.mixed_small()
+    ctx.set_scene(sc)
+    ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+    fcs, cp, B, nf = ctx.friction_basis(sc["dHat2"], sc["kappa"], sc["xi"])
+    nf = nf.copy(); nf[::4] *= -1.0  # include negated blocks
+    ctx.set_friction_basis(fcs, cp, B, nf)
+    rng = np.random.default_rng(13)
+    ctx.set_prev_positions(sc["X"] - rng.normal(size=sc["X"].shape) * np.where(rng.random(len(sc["X"])) < 0.5, 1e-7, 1e-4)[:, None])
+    a = ctx.friction_hessian(1e-10, 0.4, True).copy()
+    n = ctx.friction_hessian_dev(1e-10, 0.4, True)
+    b = ctx.get_triplets(n)
+    assert n == len(a) > 0 and np.array_equal(a["row"], b["row"]) and np.array_equal(a["col"], b["col"])
+    assert np.abs(a["val"] - b["val"]).max() <= 1e-13 * np.abs(a["val"]).max()
