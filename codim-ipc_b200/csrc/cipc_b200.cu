@@ -504,7 +504,10 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
             __syncwarp();
             bool ok = false;
             int ra = 0, rb = 0;
-            if (lane < n) { const uint2 e = q[(head + lane) & 63u]; ok = process(e.x, e.y, ra, rb); }
+            uint2 e = make_uint2(0u, 0u);
+            if (lane < n) e = q[(head + lane) & 63u];
+            __syncwarp(); // the slots may be overwritten by the next push
+            if (lane < n) ok = process(e.x, e.y, ra, rb);
             head += n;
             emit(ok, ra, rb, which);
         }

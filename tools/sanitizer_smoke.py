@@ -1,0 +1,22 @@
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np
+import codim_ipc_b200 as cipc
+from codim_ipc_b200 import scenes
+ctx = cipc.ContactContext(0)
+for sc in (scenes.mixed_small(), scenes.cloth_stack(12, 3), scenes.granules(800, cloth_n=9)):
+    ctx.set_scene(sc)
+    n = ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+    ctx.barrier_energy_dev(sc["dHat2"], sc["kappa"], sc["xi"]); ctx.barrier_gradient_dev(sc["dHat2"], sc["kappa"], sc["xi"])
+    nt = ctx.barrier_hessian_dev(sc["dHat2"], sc["kappa"], sc["xi"], True)
+    ctx.csr_begin(); ctx.csr_add()
+    ctx.friction_basis(sc["dHat2"], sc["kappa"], sc["xi"], fetch=False)
+    ctx.set_prev_positions(sc["X"] - 1e-5)
+    ctx.friction_energy_dev(1e-10, 0.4); ctx.friction_gradient_dev(1e-10, 0.4, True)
+    ctx.friction_hessian_dev(1e-10, 0.4, True); ctx.csr_add()
+    nnz = ctx.csr_finish(fetch=False)
+    t = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True)
+    a = ctx.step_size(sc["xi"], 1.0)
+    ctx.min_dist2_dev(sc["xi"]); ctx.sync()
+    print(sc.get("name"), n, nt, nnz, len(t), a)
+print("sanitizer script done")
