@@ -170,10 +170,10 @@ static inline void device_excl_scan(const u32* in, u32* out, size_t n, ScanWork&
     wk.total.reserve(1, s);
     if (n == 0) { CIPC_CUDA(cudaMemsetAsync(wk.total.p, 0, sizeof(u32), s)); return; }
     const int nt = div_up(n, SCAN_TILE);
-    // default: three streaming kernels; CIPC_SCAN_1PASS=1 selects the decoupled look-back kernel (same speed in the hash build
-    // at 1M triangles: the scans there are not the limiter)
-    static const bool onePass = getenv("CIPC_SCAN_1PASS") != nullptr;
-    if (onePass) {
+    // default: the one-pass look-back kernel (one launch + one memset instead of three launches: the small scans of the hash
+    // build are launch-latency bound; equal speed on the large ones); CIPC_SCAN_3PASS=1 selects the three streaming kernels
+    static const bool threePass = getenv("CIPC_SCAN_3PASS") != nullptr;
+    if (!threePass) {
         wk.desc.reserve((size_t)nt + 1, s);
         CIPC_CUDA(cudaMemsetAsync(wk.desc.p, 0, ((size_t)nt + 1) * sizeof(u64), s));
         CIPC_LAUNCH(k_scan_onepass, nt, SCAN_BT, 0, s, in, out, n, wk.desc.p + 1, (u32*)wk.desc.p, wk.total.p, (u32)nt);

@@ -11,7 +11,9 @@ exchanges the path needs are
     barrier gradient all-reduce(sum) of 3*nV f64                (IPC.h:1034-1042)
     constraint set   all-gather of (count, int4 payload); PP/PE stencils that were produced on several
                      ranks are merged by adding their multiplicities (IPC.h:599-654 keys on the raw tuple)
-    Hessian triplets stay on the rank that owns the constraint (gathered by the host solver)
+    Hessian triplets stay on the rank that owns the constraint; an all-gather of the per-rank counts gives every rank the
+                     offset of its slice in the global (row, col, value) stream, and `gather_triplets` assembles that
+                     stream on every rank when one process must own it
 
 Nothing here computes contact terms: it only combines per-rank results.
 """
@@ -89,6 +91,43 @@ class DistContact:
         outs = [torch.zeros_like(buf) for _ in range(self.world)]
         dist.all_gather(outs, buf, group=self.group)
         return merge_constraint_sets([o[:c].cpu().numpy() for o, c in zip(outs, counts)])
+
+
+    def triplet_offsets(self, n_local):
+        """-> (offset of this rank's triplets in the global stream, global count, per-rank counts): the ranks' slices are
+        laid out in rank order, like the reference appends blocks in constraint order"""
+        torch, dist = self.torch, self.dist
+        n = torch.tensor([int(n_local)], dtype=torch.int64, device=self.device)
+        counts = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(counts, n, group=self.group)
+        counts = [int(c.item()) for c in counts]
+        return sum(counts[:self.rank]), sum(counts), counts
+
+    def gather_triplets(self, trip):
+        """trip: this rank's triplets as a torch uint8 tensor of 16-byte records (device for nccl, host for gloo) or a numpy
+        structured array; returns the global stream (all ranks' slices in rank order) in the same kind of container"""
+        torch, dist = self.torch, self.dist
+        as_np = isinstance(trip, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(trip).view(np.uint8).reshape(-1)).to(self.device) if as_np else trip.reshape(-1)
+        assert t.dtype == torch.uint8 and t.numel() % 16 == 0
+        off, total, counts = self.triplet_offsets(t.numel() // 16)
+        mx = max(max(counts), 1) * 16
+        pad = torch.zeros(mx, dtype=torch.uint8, device=self.device)
+        pad[:t.numel()] = t
+        outs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(outs, pad, group=self.group)
+        full = torch.cat([o[:c * 16] for o, c in zip(outs, counts)])
+        return full.cpu().numpy().view(trip.dtype) if as_np else full
+
+
+def wrap_device_u8(ptr, nbytes, device_index):
+    """torch uint8 view (no copy) of device memory handed out by the C ABI (cipc_dev_triplets)"""
+    import torch
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+
+    return torch.as_tensor(_Arr(), device=torch.device("cuda", device_index))
 
 
 def wrap_device_f64(ptr, n, device_index):

@@ -71,6 +71,12 @@ parts = [np.array([[-2, 9, -1, -1], [3, 4, 5, 6]], np.int32), np.array([[-2, 9, 
 m = dc.gather_constraints(parts[r])
 got = {tuple(x) for x in m}
 assert got == {(3, 4, 5, 6), (-7, 1, 2, 3), (-2, 9, -1, -3), (-8, 1, -1, -1)}, got
+T = np.dtype([("row", np.int32), ("col", np.int32), ("val", np.float64)])
+mine = np.zeros(3 + 2 * r, T); mine["row"] = 100 * r + np.arange(len(mine)); mine["val"] = r + 0.5
+off, total, counts = dc.triplet_offsets(len(mine))
+assert counts == [3, 5] and total == 8 and off == (0 if r == 0 else 3)
+full = dc.gather_triplets(mine)
+assert len(full) == 8 and list(full["row"]) == [0, 1, 2, 100, 101, 102, 103, 104] and np.all(full["val"][:3] == 0.5) and np.all(full["val"][3:] == 1.5)
 dist.destroy_process_group()
 print("rank", r, "ok")
 """
