@@ -1083,7 +1083,7 @@ struct __align__(32) YHdr {
 template <int CLS> struct YShape { static constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2); static constexpr int NY = (CLS == 0) ? 3 : (CLS == 1 ? 2 : 1); };
 
 template <int CLS>
-__global__ void __launch_bounds__(128, 3) k_hessian_factor(const double4* __restrict__ X, const int4* __restrict__ cs,
+__global__ void __launch_bounds__(128, 4) k_hessian_factor(const double4* __restrict__ X, const int4* __restrict__ cs,
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
     double* __restrict__ Yout, YHdr* __restrict__ hdr, u32* denseList, u32* denseCount)
 {
@@ -1238,13 +1238,16 @@ __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int
 // overlaps the store stream of another, and the factors never travel through HBM (-3.3 GB per launch at 1M triangles).
 // The factor-only kernel above stays in use when the triplets are delivered to the HOST (compact factors cross PCIe).
 constexpr int FUSED_BD = 128;
+#ifndef FUSED_MINB
+#define FUSED_MINB 4
+#endif
 template <int CLS> struct FusedShape {
     static constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, YD = NY * NN;
     static constexpr int YS = (YD % 2 == 0) ? YD + 1 : YD; // odd stride: conflict-free 8-byte accesses, one stencil per lane
     static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
 };
 template <int CLS>
-__global__ void __launch_bounds__(FUSED_BD, 3) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
+__global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
     cipc_triplet* __restrict__ trip, u32* denseList, u32* denseCount)
 {
