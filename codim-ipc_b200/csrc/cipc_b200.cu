@@ -310,6 +310,57 @@ __global__ void k_emit_entries(Topo T, GridDesc G, const u64* __restrict__ boxLo
                 ++o;
             }
 }
+// ---- dense cell table (counting sort): when the grid is small enough to index every cell (DENSE_CELL_LIMIT), the
+// cell-sorted entry lists are built without a radix sort: count entries per (cell, kind) bin with atomics, scan the bins
+// -- the scanned table IS the kind-range table ks[cell*4 + k] -- and scatter every entry to its bin with a running
+// per-bin counter, writing the cell-local pair code on the way.  Entries of one (cell, kind) run come out in arbitrary
+// order, which the pair enumeration does not depend on (pairs are normalised when they are emitted).  Three launches and
+// one host round trip replace ~25 launches and two round trips.
+constexpr long DENSE_CELL_LIMIT = 16L << 20;
+__global__ void k_cell_count(Topo T, GridDesc G, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, Slab sl, u32* __restrict__ bins)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nP = T.nBN + T.nBE + T.nBT;
+    if (g >= nP) return;
+    const u32 kind = g < T.nBN ? 0u : (g < T.nBN + T.nBE ? 1u : 2u);
+    const u64 a = boxLo[g], b = boxHi[g];
+    int l[3] = {ux(a), uy(a), uz(a)}, h[3] = {ux(b), uy(b), uz(b)};
+    l[sl.axis] = max(l[sl.axis], sl.s0);
+    h[sl.axis] = min(h[sl.axis], sl.s1 - 1);
+    for (int iz = l[2]; iz <= h[2]; ++iz)
+        for (int iy = l[1]; iy <= h[1]; ++iy)
+            for (int ix = l[0]; ix <= h[0]; ++ix) {
+                const u32 cell = (u32)ix + (u32)G.gx * ((u32)iy + (u32)G.gy * (u32)iz);
+                atomicAdd(&bins[cell * 4u + kind], 1u);
+            }
+}
+__device__ __forceinline__ uint2 entry_code(const int* c, const int* l, const int* fl, const int* fh, int fsh);
+__global__ void k_cell_fill(Topo T, GridDesc G, const u64* __restrict__ boxLo, const u64* __restrict__ boxHi, const ulonglong2* __restrict__ fine,
+    Slab sl, u32* __restrict__ next, u32* __restrict__ vals, uint2* __restrict__ codes)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nP = T.nBN + T.nBE + T.nBT;
+    if (g >= nP) return;
+    u32 kind, id;
+    if (g < T.nBN) { kind = 0; id = g; }
+    else if (g < T.nBN + T.nBE) { kind = 1; id = g - T.nBN; }
+    else { kind = 2; id = g - T.nBN - T.nBE; }
+    const u64 a = boxLo[g], b = boxHi[g];
+    const ulonglong2 f = fine[g];
+    const int l0[3] = {ux(a), uy(a), uz(a)}, fl[3] = {ux(f.x), uy(f.x), uz(f.x)}, fh[3] = {ux(f.y), uy(f.y), uz(f.y)};
+    int l[3] = {l0[0], l0[1], l0[2]}, h[3] = {ux(b), uy(b), uz(b)};
+    l[sl.axis] = max(l[sl.axis], sl.s0);
+    h[sl.axis] = min(h[sl.axis], sl.s1 - 1);
+    for (int iz = l[2]; iz <= h[2]; ++iz)
+        for (int iy = l[1]; iy <= h[1]; ++iy)
+            for (int ix = l[0]; ix <= h[0]; ++ix) {
+                const u32 cell = (u32)ix + (u32)G.gx * ((u32)iy + (u32)G.gy * (u32)iz);
+                const u32 pos = atomicAdd(&next[cell * 4u + kind], 1u);
+                const int c[3] = {ix, iy, iz};
+                vals[pos] = id;
+                codes[pos] = entry_code(c, l0, fl, fh, G.fsh);
+            }
+}
 __global__ void k_cell_heads(const u32* __restrict__ keys, u32 n, u32* heads)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,14 +431,19 @@ __global__ void k_entry_codes(const u32* __restrict__ keys, const u32* __restric
     const ulonglong2 f = fine[g];
     const int c[3] = {(int)cx, (int)cy, (int)cz};
     const int l[3] = {ux(lo), uy(lo), uz(lo)}, fl[3] = {ux(f.x), uy(f.x), uz(f.x)}, fh[3] = {ux(f.y), uy(f.y), uz(f.y)};
+    codes[i] = entry_code(c, l, fl, fh, G.fsh);
+}
+// pair code of primitive (voxel box lower corner l, fine box fl..fh) as an entry of cell c
+__device__ __forceinline__ uint2 entry_code(const int* c, const int* l, const int* fl, const int* fh, int fsh)
+{
     u32 a = 0, b = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        a |= (u32)clampi(fl[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (10 * d);
-        b |= (u32)clampi(fh[d] - (c[d] << G.fsh), 0, (1 << G.fsh) - 1) << (10 * d);
+        a |= (u32)clampi(fl[d] - (c[d] << fsh), 0, (1 << fsh) - 1) << (10 * d);
+        b |= (u32)clampi(fh[d] - (c[d] << fsh), 0, (1 << fsh) - 1) << (10 * d);
         if (l[d] == c[d]) b |= 1u << (29 + d);
     }
-    codes[i] = make_uint2(a, b | CODE_GUARDS);
+    return make_uint2(a, b | CODE_GUARDS);
 }
 __device__ __forceinline__ bool code_pair_ok(const uint2 a, const uint2 b)
 {
@@ -490,7 +546,8 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
         return pt_cd_broadphase(p, q0, q1, q2, dist);
     };
     auto do_ee = [&](u32 a, u32 b, int& ra, int& rb) -> bool {
-        const int eI = (int)vals[a], eJ = (int)vals[b];
+        const int e0_ = (int)vals[a], e1_ = (int)vals[b];
+        const int eI = min(e0_, e1_), eJ = max(e0_, e1_); // the reference pairs eI with eJ > eI; runs may be unordered
         const int2 ea = T.BE[eI], eb = T.BE[eJ];
         ra = eI; rb = eJ;
         if (!ee_pair_ok(T, ea, eb)) return false;
@@ -565,10 +622,10 @@ __global__ void __launch_bounds__(PAIRS_WARPS * 32) k_pairs(Topo T, const double
                         if (ok) {
                             svJ = (int)vals[j];
                             const int vJ = T.BN[svJ];
-                            ok = !((T.flags[vI] & 1) && (T.flags[vJ] & 1));
+                            ok = svJ >= T.codim1 && !((T.flags[vI] & 1) && (T.flags[vJ] & 1)); // particle-particle only (runs may be unordered)
                             if (CCD && ok) ok = pp_ccd_broadphase(p, ldx(X, vJ), dp, ldx(P, vJ), dist);
                         }
-                        emit(ok, svI, svJ, 3);
+                        emit(ok, min(svI, svJ), max(svI, svJ), 3);
                     }
                     if (T.nRod > 0) flush(3); // the buffer holds one candidate kind at a time
                 }
@@ -1483,7 +1540,7 @@ struct cipc_ctx {
     DevBuf<u32> slabHist;
     DevBuf<u32> cnt, keys, vals, heads, headScan, ks;
     DevBuf<uint2> codes; // per sorted entry: cell-local pair code (k_entry_codes)
-    DevBuf<u32> taskCnt, nTasksDev;
+    DevBuf<u32> taskCnt, nTasksDev, binNext;
     DevBuf<uint2> taskDesc; // pair-enumeration tasks: (cell, task index within the cell)
     SortWork sortwk;
     ScanWork scanwk;
@@ -1704,6 +1761,45 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
         sl.s1 = bound(c->rank + 1);
         CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
     }
+    const long gridCells = (long)H.G.gx * H.G.gy * H.G.gz;
+    static const bool forceSort = getenv("CIPC_HASH_SORT") != nullptr; // cross-check switch: radix-sort path for every grid
+    if (gridCells <= DENSE_CELL_LIMIT && gridCells <= 4L * nP && !forceSort) {
+        // dense cell table (grids with at most a few cells per primitive): count -> scan (= kind-range table) -> tasks ->
+        // fill; one host round trip for the entry and task totals
+        const u32 nCells = (u32)gridCells;
+        const size_t bins = (size_t)nCells * 4;
+        u32 tot[2]; // entries, tasks
+        u32* totDev = c->counters.p + 4;
+        H.qch = std::min(256u, std::max(8u, (u32)(4L * nP / 50000L))); // entries are ~4 per primitive; the exact count is not known yet
+        {
+            cipc_ctx::Scope s1(c, "hb_count_scan");
+            c->binNext.reserve(bins, c->st); c->ks.reserve(bins, c->st); c->taskCnt.reserve((size_t)2 * nCells, c->st);
+            CIPC_CUDA(cudaMemsetAsync(c->binNext.p, 0, bins * 4, c->st));
+            CIPC_LAUNCH(k_cell_count, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, sl, c->binNext.p);
+            device_excl_scan(c->binNext.p, c->ks.p, bins, c->scanwk, c->st);
+            CIPC_CUDA(cudaMemcpyAsync(totDev, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToDevice, c->st));
+            CIPC_CUDA(cudaMemcpyAsync(c->binNext.p, c->ks.p, bins * 4, cudaMemcpyDeviceToDevice, c->st)); // running fill positions
+            CIPC_LAUNCH(k_task_counts, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, H.qch, c->taskCnt.p);
+            device_excl_scan(c->taskCnt.p, c->taskCnt.p, (size_t)2 * nCells, c->scanwk, c->st);
+            CIPC_CUDA(cudaMemcpyAsync(c->nTasksDev.p, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToDevice, c->st));
+            CIPC_CUDA(cudaMemcpyAsync(totDev + 1, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToDevice, c->st));
+            CIPC_CUDA(cudaMemcpyAsync(tot, totDev, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
+        }
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        const u32 nE = tot[0];
+        H.nEntries = nE;
+        H.nCells = nE ? nCells : 0;
+        H.maxTasks = tot[1];
+        c->ctr["hash_entries"] = nE;
+        c->ctr["hash_cells"] = nCells;
+        if (nE == 0) return;
+        cipc_ctx::Scope s5(c, "hb_tables");
+        c->vals.reserve(nE, c->st); c->codes.reserve(nE, c->st); c->taskDesc.reserve((size_t)tot[1] + 1, c->st);
+        CIPC_LAUNCH(k_cell_fill, div_up(nP, TB), TB, 0, c->st, T, H.G, c->boxLo.p, c->boxHi.p, c->fine.p, sl, c->binNext.p, c->vals.p, c->codes.p);
+        CIPC_LAUNCH(k_task_desc, div_up(nCells, TB), TB, 0, c->st, c->ks.p, nCells, H.qch, c->taskCnt.p, c->taskDesc.p);
+        return;
+    }
+    // ---- sparse / very large grids: entries radix-sorted by (cell, kind)
     u32 nE;
     {
         cipc_ctx::Scope s1(c, "hb_count_scan");
@@ -1781,7 +1877,7 @@ void run_pairs(cipc_ctx* c, const HashInfo& H, double dist, u32 counts[4])
     // the hash only holds this rank's slab of voxels (build_cell_lists), so every local cell is processed here
     const u32 e0 = 0, e1 = H.nCells;
     for (int k = 0; k < 4; ++k) counts[k] = 0;
-    if (e1 <= e0) return;
+    if (e1 <= e0 || H.maxTasks == 0) return;
     for (int attempt = 0; attempt < 3; ++attempt) {
         CandOut out;
         for (int k = 0; k < 4; ++k) {
