@@ -345,6 +345,13 @@ class ContactContext:
         self._ck(self.L.cipc_barrier_hessian_dev(self.h, int(elasticIPC), C.c_double(dHat2), k, C.c_double(thickness), int(projectSPD), C.byref(n)))
         return n.value
 
+    def barrier_gradient_hessian_dev(self, dHat2, kappa, thickness, elasticIPC=False):
+        """barrier gradient (dev_ptrs()['g'], overwritten) and projected Hessian (dev_triplets) in one pass over the stencils"""
+        k = (C.c_double * 3)(*[float(x) for x in kappa])
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_barrier_gradient_hessian_dev(self.h, int(elasticIPC), C.c_double(dHat2), k, C.c_double(thickness), C.byref(n)))
+        return n.value
+
     def get_triplets(self, n):
         trip = np.zeros(n, TRIPLET_DTYPE)
         if n:

@@ -938,10 +938,11 @@ __device__ __forceinline__ void gadd(double* g, int v, const double* d3, double 
     atomicAdd(&g[3 * v + 2], sc * d3[2]);
 }
 __global__ void __launch_bounds__(128) k_barrier_gradient(const double4* __restrict__ X, const double4* __restrict__ X0,
-    const int4* __restrict__ cs, const double2* __restrict__ info, u32 n, BarrierParams bp, double* g)
+    const int4* __restrict__ cs, const double2* __restrict__ info, u32 n, BarrierParams bp, double* g, const u32* __restrict__ idx)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const u32 k_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k_ >= n) return;
+    const u32 i = idx ? idx[k_] : k_; // optional index list (mollified stencils of the fused gradient + Hessian call)
     const Stencil s = decode(cs[i]);
     const double w = info[i].x;
     const double d = stencil_dist2(X, s) - bp.thickness2;
@@ -1306,7 +1307,7 @@ template <int CLS> struct FusedShape {
 template <int CLS>
 __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
-    cipc_triplet* __restrict__ trip, u32* denseList, u32* denseCount)
+    cipc_triplet* __restrict__ trip, u32* denseList, u32* denseCount, double* gOut)
 {
     constexpr int NN = FusedShape<CLS>::NN, NY = FusedShape<CLS>::NY, YS = FusedShape<CLS>::YS;
     extern __shared__ __align__(16) unsigned char fused_sm[];
@@ -1323,6 +1324,19 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
         const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
         int* h = sH + threadIdx.x * 8;
         h[1] = s.v[0]; h[2] = s.v[1]; h[3] = s.v[2]; h[4] = s.v[3]; h[5] = 0;
+        if (gOut) { // barrier gradient of the same stencil (cipc_barrier_gradient_hessian_dev): w m b' grad d, as k_barrier_gradient
+            double dg[12];
+            const int rows3[3] = {0, 1, 2};
+            if (CLS == 0) {
+                const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
+                d4_derivs(s.kind == K_EE, x, dg, nullptr, 0.0);
+            }
+            else if (CLS == 1) pe_derivs(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), dg, nullptr, 9, rows3, 0.0);
+            else pp_derivs(ldd(X, s.v[0]), ldd(X, s.v[1]), dg, nullptr, 6, rows3, 0.0);
+            constexpr int NBL = YShape<CLS>::NB;
+#pragma unroll
+            for (int k = 0; k < NBL; ++k) gadd(gOut, s.v[k], dg + 3 * k, beta);
+        }
         if (!(beta < 0.0) || !(alpha > 0.0)) { // outside the barrier's support: dense path (see k_hessian_factor)
             h[0] = (int)0xffffffffu;
             denseList[atomicAdd(denseCount, 1u)] = i;
@@ -1942,7 +1956,7 @@ int do_barrier_gradient(cipc_ctx* c, int elastic, double dHat2, const double* ka
     c->g.reserve((size_t)3 * c->T.nV, c->st);
     cipc_ctx::Scope sc(c, "barrier_g");
     CIPC_CUDA(cudaMemsetAsync(c->g.p, 0, (size_t)3 * c->T.nV * sizeof(double), c->st));
-    if (c->nC) CIPC_LAUNCH(k_barrier_gradient, div_up(c->nC, 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->nC, bp, c->g.p);
+    if (c->nC) CIPC_LAUNCH(k_barrier_gradient, div_up(c->nC, 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->nC, bp, c->g.p, (const u32*)nullptr);
     return CIPC_OK;
 }
 int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
@@ -2622,7 +2636,7 @@ int cipc_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double
     });
 }
 static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
-    int64_t* nTrip, bool devTriplets)
+    int64_t* nTrip, bool devTriplets, bool withGradient = false)
 {
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
@@ -2657,17 +2671,25 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                 if (projectSPD && devTriplets) {
                     // device-resident triplets: fused factor + expansion, the factors never leave the SM
                     u32* dl = c->clsIdx[3].p; u32* dn = c->counters.p + 15;
+                    double* gOut = nullptr;
+                    if (withGradient) { // the barrier gradient of every stencil rides on the same pass
+                        c->g.reserve((size_t)3 * c->T.nV, c->st);
+                        CIPC_CUDA(cudaMemsetAsync(c->g.p, 0, (size_t)3 * c->T.nV * sizeof(double), c->st));
+                        gOut = c->g.p;
+                        if (nk[3]) CIPC_LAUNCH(k_barrier_gradient, div_up(nk[3], 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, nk[3], bp, c->g.p,
+                            (const u32*)c->clsIdx[3].p); // mollified stencils (the first nk[3] entries of the dense list)
+                    }
                     {
                         cipc_ctx::Scope sk(c, "k_hessian_fused0"); // the longest launch of the stage: PT/EE blocks
                         if (nk[0]) CIPC_LAUNCH(k_hessian_fused<0>, div_up(nk[0], FUSED_BD), FUSED_BD, FusedShape<0>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
-                            c->tripOff.p, c->clsIdx[0].p, nk[0], bp, c->trip.p, dl, dn);
+                            c->tripOff.p, c->clsIdx[0].p, nk[0], bp, c->trip.p, dl, dn, gOut);
                     }
                     {
                         cipc_ctx::Scope sk(c, "k_hessian_fused12");
                         if (nk[1]) CIPC_LAUNCH(k_hessian_fused<1>, div_up(nk[1], FUSED_BD), FUSED_BD, FusedShape<1>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
-                            c->tripOff.p, c->clsIdx[1].p, nk[1], bp, c->trip.p, dl, dn);
+                            c->tripOff.p, c->clsIdx[1].p, nk[1], bp, c->trip.p, dl, dn, gOut);
                         if (nk[2]) CIPC_LAUNCH(k_hessian_fused<2>, div_up(nk[2], FUSED_BD), FUSED_BD, FusedShape<2>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
-                            c->tripOff.p, c->clsIdx[2].p, nk[2], bp, c->trip.p, dl, dn);
+                            c->tripOff.p, c->clsIdx[2].p, nk[2], bp, c->trip.p, dl, dn, gOut);
                     }
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
                     CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
@@ -2726,6 +2748,10 @@ int cipc_barrier_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const dou
     int64_t* nTrip)
 {
     return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, true);
+}
+int cipc_barrier_gradient_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int64_t* nTrip)
+{
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, 1, nTrip, true, true);
 }
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 {

@@ -166,6 +166,11 @@ int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const
  * the expanded stream over PCIe. */
 int cipc_barrier_hessian_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
                              int projectSPD, int64_t* nTriplets_out);
+/* Compute_Barrier_Gradient + Compute_Barrier_Hessian (projectSPD = true) in one pass over the stencils, as the Newton
+ * iteration evaluates them back to back (Shell/IMPLICIT_EULER.h:464, INC_POTENTIAL.h:374): the gradient (cipc_dev_gradient,
+ * overwritten) is accumulated by the fused Hessian kernels from the positions they already hold */
+int cipc_barrier_gradient_hessian_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
+                                      int64_t* nTriplets_out);
 int cipc_step_size_dev(cipc_ctx* ctx, int elasticIPC, double thickness, double stepSize_in);
 int cipc_min_dist2_dev(cipc_ctx* ctx, double thickness);
 int cipc_sync(cipc_ctx* ctx);

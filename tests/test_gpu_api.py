@@ -152,3 +152,20 @@ def test_empty_constraint_set_through_every_stage(ctx):
     assert 0.0 < a <= 1.0
     with pytest.raises(Exception):  # the reference dereferences min_element of an empty vector; the C ABI reports it
         ctx.min_dist2(sc["xi"])
+
+
+def test_fused_gradient_hessian_equals_separate_calls(ctx):
+    """cipc_barrier_gradient_hessian_dev == cipc_barrier_gradient + cipc_barrier_hessian on every stencil kind"""
+    from codim_ipc_b200 import scenes, multi
+    for sc in (scenes.mixed_small(), scenes.noodles(4, 40), scenes.cloth_stack(20, 4)):
+        ctx.set_scene(sc)
+        ctx.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+        g_ref = ctx.barrier_gradient(sc["dHat2"], sc["kappa"], sc["xi"])
+        t_ref = ctx.barrier_hessian(sc["dHat2"], sc["kappa"], sc["xi"], True).copy()
+        n = ctx.barrier_gradient_hessian_dev(sc["dHat2"], sc["kappa"], sc["xi"])
+        ctx.sync()
+        nV = len(sc["X"])
+        g = multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, 0).cpu().numpy().reshape(nV, 3)
+        t = ctx.get_triplets(n)
+        assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
+        assert n == len(t_ref) and np.array_equal(t["row"], t_ref["row"]) and np.abs(t["val"] - t_ref["val"]).max() <= 1e-13 * np.abs(t_ref["val"]).max()
