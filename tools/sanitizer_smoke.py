@@ -1,3 +1,5 @@
+"""Every stage of the library (constraint set, E, g, fused Hessians, friction, CSR, step size, min-dist) on three small
+scenes; run it under `compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitizer_smoke.py` on a GPU box."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np
