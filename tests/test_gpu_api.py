@@ -169,3 +169,46 @@ def test_fused_gradient_hessian_equals_separate_calls(ctx):
         t = ctx.get_triplets(n)
         assert np.abs(g - g_ref).max() <= 1e-12 * np.abs(g_ref).max()
         assert n == len(t_ref) and np.array_equal(t["row"], t_ref["row"]) and np.abs(t["val"] - t_ref["val"]).max() <= 1e-13 * np.abs(t_ref["val"]).max()
+
+
+def test_rank_partition_sums_to_single_rank_terms():
+    """world=3 contexts on one device: barrier and friction energies / gradients and the per-rank CSR matrices of the
+    Hessians add up to the single-rank results (what the all-reduces of DESIGN.md section 6 assemble)."""
+    import scipy.sparse as sp
+    import codim_ipc_b200 as cipc
+    from codim_ipc_b200 import scenes
+    sc = scenes.mixed_small()
+    nV = len(sc["X"])
+    rng = np.random.default_rng(4)
+    Xn = sc["X"] - rng.normal(size=sc["X"].shape) * 1e-5
+
+    def terms(c):
+        c.set_scene(sc)
+        c.constraint_set(sc["dHat2"], sc["xi"], fetch=False)
+        E = c.barrier_energy(sc["dHat2"], sc["kappa"], sc["xi"])
+        g = c.barrier_gradient(sc["dHat2"], sc["kappa"], sc["xi"])
+        c.csr_begin()
+        c.barrier_gradient_hessian_dev(sc["dHat2"], sc["kappa"], sc["xi"]); c.csr_add()
+        c.friction_basis(sc["dHat2"], sc["kappa"], sc["xi"], fetch=False)
+        c.set_prev_positions(Xn)
+        Ef = c.friction_energy(1e-10, 0.4)
+        gf = c.friction_gradient(1e-10, 0.4)
+        c.friction_hessian_dev(1e-10, 0.4, True); c.csr_add()
+        rp, ci, v = c.csr_finish()
+        A = sp.csr_matrix((v, ci, rp), shape=(3 * nV, 3 * nV))
+        return E, g, Ef, gf, A
+
+    full = cipc.ContactContext(0)
+    E, g, Ef, gf, A = terms(full)
+    full.close()
+    Es = Efs = 0.0; gs = np.zeros_like(g); gfs = np.zeros_like(gf); As = None
+    for r in range(3):
+        c = cipc.ContactContext(0, rank=r, world=3)
+        e, gg, ef, ggf, a = terms(c)
+        c.close()
+        Es += e; Efs += ef; gs += gg; gfs += ggf
+        As = a if As is None else As + a
+    assert abs(Es - E) <= 1e-12 * abs(E) and abs(Efs - Ef) <= 1e-12 * abs(Ef)
+    assert np.abs(gs - g).max() <= 1e-12 * np.abs(g).max() and np.abs(gfs - gf).max() <= 1e-12 * np.abs(gf).max()
+    D = (As - A).tocoo()
+    assert (np.abs(D.data).max() if D.nnz else 0.0) <= 1e-11 * np.abs(A.data).max()
