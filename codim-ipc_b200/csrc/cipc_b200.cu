@@ -1343,16 +1343,13 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
         }
         else {
             h[0] = (int)off[i];
-            double Y[NY * NN];
+            double* Y = sY + threadIdx.x * YS; // the factor routines write every entry exactly once: straight into the thread's slot
             if (CLS == 0) {
                 const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
                 hess4_factor(s.kind == K_EE, x, alpha, beta, Y);
             }
             else if (CLS == 1) hess_pe_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), alpha, beta, Y);
             else hess_pp_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), alpha, beta, Y);
-            double* y = sY + threadIdx.x * YS;
-#pragma unroll
-            for (int k = 0; k < NY * NN; ++k) y[k] = Y[k];
         }
     }
     __syncwarp();
