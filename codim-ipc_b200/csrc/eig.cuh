@@ -106,7 +106,8 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
                     fro += (r == c ? 1.0 : 2.0) * s * s;
                 }
     if (fro > 0.0) {
-        const double tol = 1e-28 * fro;
+        const double tol = 1e-25 * fro; // off-diagonal norm <= 3e-13 ||M||: far below the 1e-9 parity gate
+        const double iscale = rsqrt(fro);
         for (int sweep = 0; sweep < 14; ++sweep) {
             double off = 0.0;
             for (int p = 0; p < K; ++p)
@@ -117,8 +118,11 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
                     const double apq = SA(p, q);
                     if (apq * apq <= 1e-36 * fro) continue;
                     const double app = SA(p, p), aqq = SA(q, q);
-                    const double theta = (aqq - app) / (2.0 * apq);
-                    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    // rotation angle in fp32 on scaled entries, rotation orthogonal to fp64 rounding, exact similarity
+                    // transform (a_pq is updated, not zeroed): see hess4_factor
+                    const float df = (float)((aqq - app) * iscale), af = (float)(apq * iscale) * 2.0f;
+                    const float h2 = fmaf(df, df, af * af);
+                    const double t = (double)__fdividef(df >= 0.0f ? af : -af, fabsf(df) + h2 * rsqrtf(h2));
                     const double c = rsqrt(t * t + 1.0), s = t * c;
                     for (int k = 0; k < K; ++k) {
                         if (k != p && k != q) {
@@ -131,9 +135,10 @@ __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, i
                         SV(k, p) = c * vkp - s * vkq;
                         SV(k, q) = s * vkp + c * vkq;
                     }
-                    SA(p, p) = app - t * apq;
-                    SA(q, q) = aqq + t * apq;
-                    SA(p, q) = 0.0;
+                    const double cc = c * c, ss = s * s, cs = c * s;
+                    SA(p, p) = cc * app - 2.0 * cs * apq + ss * aqq;
+                    SA(q, q) = ss * app + 2.0 * cs * apq + cc * aqq;
+                    SA(p, q) = cs * (app - aqq) + (cc - ss) * apq;
                 }
         }
     }
