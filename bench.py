@@ -15,9 +15,14 @@ Workload: cfg5, the 1M-triangle stacked-cloth scene the BASELINE target is quote
            ("strong" scaling); NCCL all-reduces the step size (min), energy and gradient (sum), min-dist (min)
 
 `--impl reference` times the reference's own CPU implementation of the path -- FEM/IPC.h + Grid/SPATIAL_HASH.h
-compiled from its sources into oracle/_ref/libcipc_refdrv.so (stand-ins only for Eigen/Cabana/pybind11), or the
-oracle port when that library is absent -- with all host threads on a bounded sample of the same workload,
-scaled to the full size.
+compiled from its sources into oracle/_ref/libcipc_refdrv_fast.so (the reference's own compiler flags; stand-ins only
+for Eigen/Cabana/pybind11), or the oracle port when that library is absent -- with all host threads ON THE SAME WORKLOAD
+(every warm-up and timed step is one full contact stage of `--workload`; only cfg5_4m, whose 4.28G triplets overflow the
+reference's `int curStartInd` (IPC.h:1368), is sampled and marked `extrapolated`).
+
+The GPU arm's `cpu_baseline` leg (rank 0, N=1) runs the same reference drivers on the same scene (>= 2 samples, min and
+mean reported) and a PARITY leg: the parity build of the reference (-ffp-contract=off) and the CUDA path evaluate the same
+scene and the SURVEY 8(d) gates are asserted and printed as `"parity": {...}`.
 """
 import argparse
 import json
@@ -39,7 +44,16 @@ WORKLOADS = {  # name -> (n, layers)
     "cfg5_250k": (112, 10),
     "cfg5_62k": (56, 10),
 }
-CPU_SAMPLE = {"cfg5_4m": ("cfg5_250k", 16.0), "cfg5_1m": ("cfg5_250k", 4.0), "cfg5_250k": ("cfg5_62k", 4.0), "cfg5_62k": ("cfg5_62k", 1.0)}
+# the CPU arms run the requested workload itself; only cfg5_4m is sampled (see the module docstring) and flagged as such
+CPU_SAMPLE = {"cfg5_4m": ("cfg5_1m", None)}
+L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB write), working set >> L2"
+PAR_NOTE = "GPU arm: candidate pairs partitioned by hash-cell ranges across n_gpus ranks; reference arm: all host cores of rank 0"
+
+
+def scene_config(name, sc):
+    """`config` of the JSON line: names the workload; identical in the GPU arm and the reference arm"""
+    return {"workload": name, "triangles": int(len(sc["BT"])), "nodes": int(len(sc["X"])), "boundary_edges": int(len(sc["BE"])),
+            "dHat": float(np.sqrt(sc["dHat2"])), "xi": float(sc["xi"]), "l2": L2_NOTE, "parallelism": PAR_NOTE}
 
 
 def make_scene(name):
@@ -80,25 +94,28 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_backend():
-    """("reference", RefScene) when oracle/_ref/libcipc_refdrv.so -- the reference's own FEM/IPC.h + SPATIAL_HASH.h compiled
-    from its sources (oracle/Makefile `ref`) -- is present, else ("port", OracleScene): the oracle restatement"""
+def cpu_backend(parity=False):
+    """(kind, Scene class).  kind = "reference": oracle/_ref -- the reference's own FEM/IPC.h + SPATIAL_HASH.h compiled from its
+    sources (oracle/Makefile `ref`): the TIMING build (the reference's own flags) unless parity=True (the -ffp-contract=off
+    build whose constraint-set membership is bit-comparable).  kind = "port": the oracle restatement (when oracle/_ref is absent)."""
     from oracle import cipc_oracle as O
+    if not parity and O.refdrv_fast() is not None:
+        return "reference", O.RefSceneFast
     if O.refdrv() is not None:
         return "reference", O.RefScene
     return "port", O.OracleScene
 
 
-def cpu_contact_stage(sc, threads=None):
-    """one contact stage on the CPU (the reference's own drivers when built, else the oracle port);
-    returns (seconds, per-stage dict, nConstraints)"""
+def cpu_set_threads(Scene, threads):
     from oracle import cipc_oracle as O
-    kind, Scene = cpu_backend()
-    if threads:
-        O.set_num_threads(threads)
-        if kind == "reference":
-            O.refdrv().ref_set_num_threads(int(threads))
-    S = Scene(sc)
+    O.set_num_threads(threads)
+    for L in (O.refdrv(), O.refdrv_fast()):
+        if L is not None:
+            L.ref_set_num_threads(int(threads))
+
+
+def cpu_contact_stage(S, sc):
+    """one contact stage on the CPU scene object S; returns (seconds, per-stage dict, nConstraints)"""
     st = {}
     t0 = time.perf_counter()
     cs, info = S.constraint_set(sc["dHat2"], sc["xi"]); t1 = time.perf_counter(); st["constraint_set"] = t1 - t0
@@ -110,31 +127,133 @@ def cpu_contact_stage(sc, threads=None):
     return t6 - t0, st, len(cs)
 
 
+def cpu_describe(kind):
+    return ("the reference's own FEM/IPC.h + Grid/SPATIAL_HASH.h drivers (oracle/_ref timing build: -O3 -mavx2 -mfma -mbmi2 -fopenmp as the "
+            "reference's CMakeLists.txt:20, Par_Each on OpenMP)" if kind == "reference"
+            else "oracle port (-O3 -mavx2 -mfma -fopenmp, the reference's parallel structure)")
+
+
+def cpu_samples(workload, n_warm, n_timed):
+    """run n_warm + n_timed full contact stages of `workload` (cfg5_4m: of its sample) on all host cores"""
+    sample, _ = CPU_SAMPLE.get(workload, (workload, 1.0))
+    sc = make_scene(sample)
+    cores = os.cpu_count()  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
+    kind, Scene = cpu_backend()
+    cpu_set_threads(Scene, cores)
+    S = Scene(sc)
+    times, st, nC = [], {}, 0
+    for i in range(n_warm + n_timed):
+        t, st, nC = cpu_contact_stage(S, sc)
+        if i >= n_warm:
+            times.append(t)
+    scale, extrap = 1.0, None
+    if sample != workload:
+        # cfg5_4m only: scaled by the constraint count of the full workload (known from the scene generator's density) -- an
+        # extrapolation, flagged at the top level of the JSON line
+        full = WORKLOADS[workload][0] ** 2 * 2 * WORKLOADS[workload][1]
+        scale = full / float(len(sc["BT"]))
+        extrap = {"extrapolated": True, "sample_workload": sample, "scale": scale,
+                  "why": "4.28G triplets overflow the reference's int triplet offsets (FEM/IPC.h:1368) and 68 GB of host triplets"}
+    return dict(kind=kind, cores=cores, times=[t * scale for t in times], stages=st, nC=nC, sample=sample, scene=sc, scale=scale, extrap=extrap)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cipc_oracle as O
-    sample, scale = CPU_SAMPLE[args.workload]
-    sc = make_scene(sample)
-    cores = os.cpu_count()  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
-    kind = cpu_backend()[0]
-    times = []
-    for i in range(args.warmup + args.steps):
-        t, st, nC = cpu_contact_stage(sc, cores)
-        if i >= args.warmup:
-            times.append(t)
-    ms = 1e3 * float(np.mean(times)) * scale
-    what = ("the reference's own FEM/IPC.h + Grid/SPATIAL_HASH.h drivers (oracle/_ref, -O3 -mavx2 -mfma -fopenmp, Par_Each on OpenMP)"
-            if kind == "reference" else "oracle port (-O3 -mavx2 -mfma -fopenmp, reference's parallel structure)")
-    desc = "%s on %s (%d triangles, %d constraints), x%.0f to %s" % (what, sample, len(sc["BT"]), nC, scale, args.workload)
+    r = cpu_samples(args.workload, args.warmup, args.steps)
+    ms = 1e3 * float(np.mean(r["times"]))
+    sc_full = r["scene"] if r["sample"] == args.workload else make_scene(args.workload)
+    desc = "%s: %d warm-up + %d timed full contact stages of %s (%d triangles, %d constraints)%s" % (
+        cpu_describe(r["kind"]), args.warmup, args.steps, r["sample"], len(r["scene"]["BT"]), r["nC"],
+        "" if r["extrap"] is None else ", scaled x%.2f to %s" % (r["scale"], args.workload))
     line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "triangles": WORKLOADS[args.workload][0] ** 2 * 2 * WORKLOADS[args.workload][1]},
-            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": desc,
-                             "stages_s": {k: round(v, 4) for k, v in st.items()}},
-            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "config": scene_config(args.workload, sc_full),
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": r["cores"], "kind": r["kind"], "sample": desc,
+                             "min_ms": 1e3 * min(r["times"]), "max_ms": 1e3 * max(r["times"]),
+                             "stages_s": {k: round(v, 4) for k, v in r["stages"].items()}},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "counts": {"constraints": int(r["nC"])}}
+    if r["extrap"] is not None:
+        line.update(r["extrap"])
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- parity leg (GPU arm, rank 0, N=1)
+TOL_EGH = 1e-9   # north_star: energy, gradient and Hessian entries within 1e-9 relative in fp64
+TOL_STEP = 1e-12  # CCD step size within 1e-12 relative and never larger than the reference's
+
+
+def parity_leg(ctx, sc, local, workload):
+    """The CUDA path and the reference (parity build of oracle/_ref, else the oracle port) evaluate the SAME scene; the SURVEY
+    8(d) gates are evaluated and returned.  The Hessian compared is the one the timed kernel produces: the device-resident
+    fused gradient + Hessian pass (k_hessian_fused) read back with cipc_get_triplets, block by block against the reference's
+    triplet vector; the factor + host-expansion delivery of Compute_Barrier_Hessian is compared as well."""
+    import psutil
+    from codim_ipc_b200 import multi
+    from oracle import cipc_oracle as O
+    kind, Scene = cpu_backend(parity=True)
+    cpu_set_threads(Scene, os.cpu_count())
+    R = Scene(sc)
+    dHat2, xi, kappa = sc["dHat2"], sc["xi"], sc["kappa"]
+    nV = len(sc["X"])
+    out = {"workload": workload, "against": ("oracle/_ref parity build (the reference's FEM/IPC.h, -ffp-contract=off)" if kind == "reference"
+                                             else "oracle port"), "tolerances": {"E_g_H": TOL_EGH, "step": TOL_STEP}}
+    key = lambda a: np.lexsort(a.T[::-1])
+    ctx.set_scene(sc)
+    cs_g, info_g = ctx.constraint_set(dHat2, xi)
+    cs_r, info_r = R.constraint_set(dHat2, xi)
+    og, orr = key(cs_g), key(cs_r)
+    cs_g, info_g, cs, info = cs_g[og], info_g[og], cs_r[orr], info_r[orr]
+    same = cs_g.shape == cs.shape and np.array_equal(cs_g, cs) and np.array_equal(info_g, info)
+    out["constraint_set"] = {"n_gpu": int(len(cs_g)), "n_ref": int(len(cs)), "identical_as_sorted_sets": bool(same)}
+    def step_gate():
+        a_g = ctx.step_size(xi, 1.0); a_r = R.step_size(sc["p"], xi, 1.0)
+        return {"gpu": a_g, "ref": a_r, "rel_diff": (a_r - a_g) / a_r, "ok": bool(a_g <= a_r and (a_r - a_g) <= TOL_STEP * a_r)}
+
+    if not same or len(cs) == 0:
+        out["step_size"] = step_gate()
+        out["pass"] = bool(same and out["step_size"]["ok"])
+        return out
+    ctx.set_constraints(cs, info)
+    E_r = R.barrier(cs, info, dHat2, kappa, xi, E0=0.5); E_g = ctx.barrier_energy(dHat2, kappa, xi, E=0.5)
+    out["energy"] = {"rel_err": abs(E_g - E_r) / abs(E_r), "ok": bool(abs(E_g - E_r) <= TOL_EGH * abs(E_r))}
+    g_r = R.barrier_gradient(cs, info, dHat2, kappa, xi); g_g = ctx.barrier_gradient(dHat2, kappa, xi)
+    gs = float(np.abs(g_r).max())
+    # the timed kernels: gradient + Hessian in one pass, results resident on the device
+    nT = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
+    g_f = multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, local).cpu().numpy().reshape(nV, 3)
+    e1, e2 = float(np.abs(g_g - g_r).max()) / gs, float(np.abs(g_f - g_r).max()) / gs
+    out["gradient"] = {"inf_norm_ref": gs, "rel_err_host_api": e1, "rel_err_fused_kernel": e2, "ok": bool(max(e1, e2) <= TOL_EGH)}
+    need = 2 * nT * 16 + (4 << 30)
+    sub = None
+    if psutil.virtual_memory().available < need:  # bounded host memory: every k-th stencil instead of all of them
+        k = int(np.ceil(need / max(psutil.virtual_memory().available, 1))) * 2
+        sub = np.arange(0, len(cs), k)
+        ctx.set_constraints(cs[sub], info[sub])
+        nT = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
+    csH, infoH = (cs, info) if sub is None else (cs[sub], info[sub])
+    trip = ctx.get_triplets(nT)
+    n_r = R.barrier_hessian_notfetch(csH, infoH, dHat2, kappa, xi, True)
+    ptr_r, _ = R.triplets_data()
+    c1 = O.compare_triplet_blocks(trip.ctypes.data, ptr_r, csH) if n_r == nT else None
+    trip = ctx.barrier_hessian(dHat2, kappa, xi, True, out=trip)  # factor kernels + host expansion (the shim's delivery)
+    c2 = O.compare_triplet_blocks(trip.ctypes.data, ptr_r, csH) if n_r == len(trip) else None
+    del trip
+    if hasattr(R, "release_triplets"):
+        R.release_triplets()
+    okH = all(c is not None and c["index_mismatches"] == 0 and c["max_block_rel_err"] <= TOL_EGH for c in (c1, c2))
+    out["hessian"] = {"triplets_gpu": int(nT), "triplets_ref": int(n_r), "blocks": int(len(csH)), "all_blocks": sub is None,
+                      "fused_kernel_vs_ref": c1, "host_delivery_vs_ref": c2, "ok": bool(okH)}
+    if sub is not None:
+        ctx.set_constraints(cs, info)
+    d_g, m_g = ctx.min_dist2(xi); d_r, m_r = R.min_dist2(cs, xi)
+    out["min_dist2"] = {"dist2_bit_identical": bool(np.array_equal(d_g, d_r)), "min_equal": bool(m_g == m_r),
+                        "ok": bool(np.array_equal(d_g, d_r) and m_g == m_r)}
+    out["step_size"] = step_gate()
+    out["pass"] = bool(same and all(out[k]["ok"] for k in ("energy", "gradient", "hessian", "min_dist2", "step_size")))
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -148,6 +267,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-friction", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--stage-report", action="store_true", help="print the per-stage device times to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -404,29 +524,33 @@ def main():
     if os.path.exists(tr_path):
         try:
             tj = json.load(open(tr_path))
-            if tj.get("workload") == args.workload:
+            if tj.get("workload") == args.workload and world == 1:  # captured for this workload at N=1 only
                 roof["traffic"] = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
 
     cpu = None
-    if not args.no_cpu:
-        sample, scale = CPU_SAMPLE[args.workload]
-        scs = make_scene(sample)
-        kind = cpu_backend()[0]
-        tcpu, st, nCs = cpu_contact_stage(scs, os.cpu_count())
-        cpu = {"value": 1e3 * tcpu * scale, "unit": "ms", "cores": os.cpu_count(), "kind": kind,
-               "sample": "one contact stage of %s on %s (%d triangles, %d constraints, %.1f s), scaled x%.0f by triangle count" % (
-                   "the reference's own drivers (oracle/_ref)" if kind == "reference" else "the oracle port",
-                   sample, len(scs["BT"]), nCs, tcpu, scale),
-               "stages_s": {k: round(v, 4) for k, v in st.items()}}
+    extrap = None
+    if not args.no_cpu and world == 1:
+        r = cpu_samples(args.workload, 0, 2)  # the first sample warms the allocator / page cache of the CPU path
+        cpu = {"value": 1e3 * min(r["times"]), "unit": "ms", "cores": r["cores"], "kind": r["kind"],
+               "sample": "%s: 2 full contact stages of %s (%d triangles, %d constraints)%s; value = min, mean_ms beside it" % (
+                   cpu_describe(r["kind"]), r["sample"], len(r["scene"]["BT"]), r["nC"],
+                   "" if r["extrap"] is None else ", scaled x%.2f to %s (EXTRAPOLATED)" % (r["scale"], args.workload)),
+               "min_ms": 1e3 * min(r["times"]), "mean_ms": 1e3 * float(np.mean(r["times"])), "samples_ms": [round(1e3 * t, 1) for t in r["times"]],
+               "stages_s": {k: round(v, 4) for k, v in r["stages"].items()}}
+        if r["extrap"] is not None:
+            cpu["extrapolated"] = r["extrap"]
+        del r
+    parity = None
+    if not args.no_parity and world == 1 and args.workload not in CPU_SAMPLE:
+        parity = parity_leg(ctx, sc, local, args.workload)
 
     line = {"metric": METRIC, "value": dev_ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "triangles": nT, "nodes": nV, "boundary_edges": len(sc["BE"]), "constraints_rank0": int(nC),
-                       "triplets_rank0": int(nTrip), "dHat": float(np.sqrt(dHat2)), "xi": float(xi), "l2": "flushed between timed steps (256 MiB write); working set >> L2",
-                       "parallelism": "pairs partitioned by hash-cell ranges x%d" % world},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "config": scene_config(args.workload, sc),
+            "counts": {"constraints_rank0": int(nC), "triplets_rank0": int(nTrip), "world": world},
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters,
             "friction_stages_ms": friction, "csr_stages_ms": csr}
     if args.stage_report:

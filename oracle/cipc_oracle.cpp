@@ -1256,6 +1256,41 @@ void oracle_fetch_triplets(int* rows, int* cols, double* vals)
 {
     for (size_t i = 0; i < g_trip.size(); ++i) { rows[i] = g_trip[i].row; cols[i] = g_trip[i].col; vals[i] = g_trip[i].val; }
 }
+// ---- checker helpers for full-size parity (bench.py's parity leg, tests/test_gpu_cfg5_full.py): the triplet streams of two
+// implementations (16-byte {int row; int col; double val} records, blocks in constraint order) are compared block by block
+// without leaving native memory.  out[0] = max_c ||Ha - Hb||_F / ||Hb||_F, out[1] = number of (row, col) mismatches,
+// out[2] = max_c |v^T (Ha - Hb) v| / ||Hb||_F with v = cos(1 + 0.37 k) (the golden fixtures' quadratic probe),
+// out[3] = number of blocks, out[4] = total number of triplets implied by cs
+const void* oracle_triplets_data(long* n) { if (n) *n = (long)g_trip.size(); return g_trip.data(); }
+void oracle_compare_triplet_blocks(const void* a_, const void* b_, const int* cs, int nC, double* out)
+{
+    const Triplet* A = (const Triplet*)a_;
+    const Triplet* B = (const Triplet*)b_;
+    std::vector<long> off((size_t)nC + 1, 0);
+    for (int i = 0; i < nC; ++i) {
+        const int* c = cs + 4 * (size_t)i;
+        const int n = (c[0] >= 0 || c[3] >= 0) ? 12 : (c[2] >= 0 ? 9 : 6);
+        off[i + 1] = off[i] + n * n;
+    }
+    double worst = 0, worstQ = 0;
+    long mism = 0;
+#pragma omp parallel for schedule(static) reduction(max : worst, worstQ) reduction(+ : mism)
+    for (int i = 0; i < nC; ++i) {
+        const long o = off[i], m = off[i + 1] - off[i];
+        const int n = m == 144 ? 12 : (m == 81 ? 9 : 6);
+        double d2 = 0, b2 = 0, q = 0;
+        for (long t = 0; t < m; ++t) {
+            const Triplet &x = A[o + t], &y = B[o + t];
+            if (x.row != y.row || x.col != y.col) ++mism;
+            const double d = x.val - y.val;
+            d2 += d * d; b2 += y.val * y.val;
+            q += std::cos(1.0 + 0.37 * (double)(t / n)) * d * std::cos(1.0 + 0.37 * (double)(t % n));
+        }
+        if (b2 > 0) { worst = std::max(worst, std::sqrt(d2 / b2)); worstQ = std::max(worstQ, std::fabs(q) / std::sqrt(b2)); }
+        else if (d2 > 0) worst = std::max(worst, 1.0);
+    }
+    out[0] = worst; out[1] = (double)mism; out[2] = worstQ; out[3] = (double)nC; out[4] = (double)off[nC];
+}
 int oracle_step_size(void* h, int elastic, const double* searchDir, double thickness, int use_hash, double* stepSize,
     double* timers3, long* nPairs)
 {

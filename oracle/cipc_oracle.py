@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _REF = None
 _REFDRV = None
+_REFDRV_FAST = None
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -33,8 +34,11 @@ def build(force=False):
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "libcipc_oracle.so"], stdout=subprocess.DEVNULL)
-    ref_sos = [os.path.join(_HERE, "_ref", f) for f in ("libcipc_refdist.so", "libcipc_refdrv.so")]
-    if os.path.isdir("/root/reference/Library/Math/Distance") and (force or not all(os.path.exists(f) for f in ref_sos)):
+    ref_sos = [os.path.join(_HERE, "_ref", f) for f in ("libcipc_refdist.so", "libcipc_refdrv.so", "libcipc_refdrv_fast.so")]
+    ref_srcs = [os.path.join(_HERE, "ref_build", f) for f in ("ref_drivers.cpp", "ref_distance.cpp")] + [os.path.join(_HERE, "Makefile")]
+    if os.path.isdir("/root/reference/Library/Math/Distance") and (
+            force or not all(os.path.exists(f) for f in ref_sos)
+            or max(os.path.getmtime(f) for f in ref_srcs) > min(os.path.getmtime(f) for f in ref_sos)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -48,6 +52,7 @@ def lib():
         L.oracle_dist2_unclassified.restype = C.c_double
         L.oracle_friction_coef.restype = C.c_double
         L.oracle_friction_hessian.restype = C.c_long
+        L.oracle_triplets_data.restype = C.c_void_p
         _LIB = L
     return _LIB
 
@@ -68,23 +73,36 @@ def ref():
     return _REF
 
 
+def _load_refdrv(name):
+    p = os.path.join(_HERE, "_ref", name)
+    if not os.path.exists(p):
+        build()
+    if not os.path.exists(p):
+        return None
+    R = C.CDLL(p)
+    R.ref_scene_create.restype = C.c_void_p
+    R.ref_barrier_hessian.restype = C.c_long
+    R.ref_friction_hessian.restype = C.c_long
+    R.ref_friction_coef.restype = C.c_double
+    R.ref_timer.restype = C.c_double
+    R.ref_triplets_data.restype = C.c_void_p
+    return R
+
+
 def refdrv():
-    """The reference's own drivers (see RefScene), or None when oracle/_ref was never built."""
+    """The reference's own drivers (see RefScene), PARITY build (-ffp-contract=off), or None when oracle/_ref was never built."""
     global _REFDRV
     if _REFDRV is None:
-        p = os.path.join(_HERE, "_ref", "libcipc_refdrv.so")
-        if not os.path.exists(p):
-            build()
-        if not os.path.exists(p):
-            return None
-        R = C.CDLL(p)
-        R.ref_scene_create.restype = C.c_void_p
-        R.ref_barrier_hessian.restype = C.c_long
-        R.ref_friction_hessian.restype = C.c_long
-        R.ref_friction_coef.restype = C.c_double
-        R.ref_timer.restype = C.c_double
-        _REFDRV = R
+        _REFDRV = _load_refdrv("libcipc_refdrv.so")
     return _REFDRV
+
+
+def refdrv_fast():
+    """The same drivers compiled with exactly the reference's flags (default FMA contraction): the TIMING build."""
+    global _REFDRV_FAST
+    if _REFDRV_FAST is None:
+        _REFDRV_FAST = _load_refdrv("libcipc_refdrv_fast.so")
+    return _REFDRV_FAST
 
 
 def num_threads():
@@ -176,6 +194,12 @@ class OracleScene:
             self._fn("fetch_triplets")(_ip(rows), _ip(cols), _dp(vals))
         return rows, cols, vals
 
+    def triplets_data(self):
+        """(address, count) of the 16-byte {int row; int col; double val} records of the last Hessian, in place"""
+        n = C.c_long(0)
+        p = self._fn("triplets_data")(C.byref(n))
+        return p, n.value
+
     def barrier_hessian_notfetch(self, cs, info, dHat2, kappa, thickness, projectSPD=True, elastic=False):
         """computes the triplets inside the oracle without copying them out (CPU-baseline timing); returns their number"""
         cs = np.ascontiguousarray(cs, np.int32); info = np.ascontiguousarray(info, np.float64)
@@ -262,8 +286,31 @@ class RefScene(OracleScene):
     def timer(self, name):
         return self._lib().ref_timer(name.encode())
 
+    def release_triplets(self):
+        self._lib().ref_triplets_release()
+
     def timer_reset(self):
         self._lib().ref_timer_reset()
+
+
+class RefSceneFast(RefScene):
+    """RefScene on the TIMING build (the reference's own compiler flags); never used for parity."""
+
+    def _lib(self):
+        L = refdrv_fast()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libcipc_refdrv_fast.so is not built (needs /root/reference)")
+        return L
+
+
+def compare_triplet_blocks(ptr_a, ptr_b, cs):
+    """block-by-block comparison of two triplet streams (addresses of 16-byte records, blocks in the order of `cs`):
+    -> dict(max_block_rel_err, index_mismatches, max_quad_rel_err, blocks, triplets); b is the reference side"""
+    cs = np.ascontiguousarray(cs, np.int32).reshape(-1, 4)
+    out = np.zeros(5)
+    lib().oracle_compare_triplet_blocks(C.c_void_p(ptr_a), C.c_void_p(ptr_b), _ip(cs), len(cs), _dp(out))
+    return dict(max_block_rel_err=float(out[0]), index_mismatches=int(out[1]), max_quad_rel_err=float(out[2]), blocks=int(out[3]),
+                triplets=int(out[4]))
 
 
 # ---- per-stencil probes (kind: 0 PP, 1 PE, 2 PT, 3 EE, 4 EE cross-norm^2)

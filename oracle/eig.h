@@ -15,8 +15,12 @@ namespace cipc_oracle {
 
 // A: n x n row-major symmetric (only read).  V: eigenvectors as columns (row-major n x n),
 // d: eigenvalues ascending.
-static inline void sym_eig(int n, const double* A, double* V, double* d)
+// NT > 0 fixes the size at compile time (the reference's Eigen solver is a fixed-size instantiation too, so the compiler
+// unrolls / vectorises its loops; a run-time n would under-state the reference's CPU speed in oracle/_ref timings)
+template <int NT>
+static inline void sym_eig_t(int n_, const double* A, double* V, double* d)
 {
+    const int n = NT > 0 ? NT : n_;
     double e[12];
     for (int i = 0; i < n * n; ++i) V[i] = A[i];
     // ---- Householder reduction to tridiagonal form (accumulating the transform in V)
@@ -147,6 +151,16 @@ static inline void sym_eig(int n, const double* A, double* V, double* d)
             d[k] = d[i]; d[i] = p;
             for (int j = 0; j < n; ++j) std::swap(V[j * n + i], V[j * n + k]);
         }
+    }
+}
+
+static inline void sym_eig(int n, const double* A, double* V, double* d)
+{
+    switch (n) {
+    case 12: sym_eig_t<12>(n, A, V, d); break;
+    case 9: sym_eig_t<9>(n, A, V, d); break;
+    case 6: sym_eig_t<6>(n, A, V, d); break;
+    default: sym_eig_t<0>(n, A, V, d); break;
     }
 }
 

@@ -174,6 +174,10 @@ void ref_fetch_triplets(int* rows, int* cols, double* vals)
 {
     for (size_t i = 0; i < g_trip.size(); ++i) { rows[i] = g_trip[i].row(); cols[i] = g_trip[i].col(); vals[i] = g_trip[i].value(); }
 }
+// the reference's triplet vector in place (16-byte {int,int,double} records): full-size parity checks compare it with the
+// CUDA path's stream without a copy (oracle_compare_triplet_blocks)
+const void* ref_triplets_data(long* n) { static_assert(sizeof(Eigen::Triplet<T>) == 16, "triplet layout"); if (n) *n = (long)g_trip.size(); return g_trip.data(); }
+void ref_triplets_release() { std::vector<Eigen::Triplet<T>>().swap(g_trip); }
 int ref_step_size(void* h, int elastic, const double* searchDir, double thickness, int /*use_hash*/, double* stepSize,
     double* /*timers3*/, long* nPairs)
 {
