@@ -223,6 +223,7 @@ def parity_leg(ctx, sc, local, workload):
     gs = float(np.abs(g_r).max())
     # the timed kernels: gradient + Hessian in one pass, results resident on the device
     nT = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
+    ctx.sync()  # the library may run on its own stream: torch's copy below is not ordered against it
     g_f = multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, local).cpu().numpy().reshape(nV, 3)
     e1, e2 = float(np.abs(g_g - g_r).max()) / gs, float(np.abs(g_f - g_r).max()) / gs
     out["gradient"] = {"inf_norm_ref": gs, "rel_err_host_api": e1, "rel_err_fused_kernel": e2, "ok": bool(max(e1, e2) <= TOL_EGH)}
@@ -290,8 +291,12 @@ def main():
     sc = make_scene(args.workload)
     nV, nT = len(sc["X"]), len(sc["BT"])
     ctx = cipc.ContactContext(local, rank, world)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)  # the library's kernels, torch events and NCCL share one stream
+    # one explicit stream for the library's kernels, torch's events / copies and NCCL (a handle of 0 -- torch's default
+    # stream -- would make cipc_set_stream fall back to the library's own non-blocking stream, which nothing else orders against)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
     ctx.set_scene(sc)
     dHat2, xi, kappa = sc["dHat2"], sc["xi"], sc["kappa"]
     scal = multi.wrap_device_f64(ctx.dev_ptrs()["scalars"], 16, local)

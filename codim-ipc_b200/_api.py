@@ -62,6 +62,8 @@ def load_library():
     L.cipc_event_elapsed_ms.restype = C.c_double
     L.cipc_counter.restype = C.c_int64
     L.cipc_kernel_launches.restype = C.c_int64
+    L.cipc_hash_bytes.restype = C.c_uint64
+    L.cipc_hash_bytes.argtypes = [C.c_void_p, C.c_size_t]
     for f in ("cipc_dev_positions", "cipc_dev_gradient", "cipc_dev_scalars", "cipc_dev_triplets"):
         getattr(L, f).restype = C.c_void_p
     _lib = L
@@ -215,6 +217,20 @@ class ContactContext:
             self._ck(self.L.cipc_get_triplets(self.h, trip.ctypes.data_as(C.c_void_p)))
         return trip[:n.value]
 
+    def barrier_hessian_merged(self, dHat2, kappa, thickness, projectSPD=True, elasticIPC=False, fetch=True, out=None):
+        """Compute_Barrier_Hessian delivered as MERGED triplets: one triplet per distinct (row, col) of the contact matrix
+        (what setFromTriplets would produce from the raw stream), summed on the device at 3x3-block granularity"""
+        k = (C.c_double * 3)(*[float(x) for x in kappa])
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_barrier_hessian_merged(self.h, int(elasticIPC), C.c_double(dHat2), k, C.c_double(thickness), int(projectSPD), C.byref(n)))
+        if not fetch:
+            return n.value
+        trip = out if out is not None else np.zeros(n.value, TRIPLET_DTYPE)
+        assert len(trip) >= n.value and trip.dtype == TRIPLET_DTYPE
+        if n.value:
+            self._ck(self.L.cipc_get_triplets(self.h, trip.ctypes.data_as(C.c_void_p)))
+        return trip[:n.value]
+
     def step_size(self, thickness, stepSize=1.0, elasticIPC=False):
         a = C.c_double(stepSize)
         self._ck(self.L.cipc_step_size(self.h, int(elasticIPC), C.c_double(thickness), C.byref(a)))
@@ -279,6 +295,18 @@ class ContactContext:
     def friction_hessian(self, epsvh2, mu, projectSPD=True, fetch=True, out=None):
         n = C.c_int64(0)
         self._ck(self.L.cipc_friction_hessian(self.h, C.c_double(epsvh2), C.c_double(mu), int(projectSPD), C.byref(n)))
+        if not fetch:
+            return n.value
+        trip = out if out is not None else np.zeros(n.value, TRIPLET_DTYPE)
+        assert len(trip) >= n.value and trip.dtype == TRIPLET_DTYPE
+        if n.value:
+            self._ck(self.L.cipc_get_triplets(self.h, trip.ctypes.data_as(C.c_void_p)))
+        return trip[:n.value]
+
+    def friction_hessian_merged(self, epsvh2, mu, projectSPD=True, fetch=True, out=None):
+        """Compute_Friction_Hessian delivered as merged triplets (see barrier_hessian_merged)"""
+        n = C.c_int64(0)
+        self._ck(self.L.cipc_friction_hessian_merged(self.h, C.c_double(epsvh2), C.c_double(mu), int(projectSPD), C.byref(n)))
         if not fetch:
             return n.value
         trip = out if out is not None else np.zeros(n.value, TRIPLET_DTYPE)

@@ -893,6 +893,10 @@ __device__ __forceinline__ double stencil_dist2(const double4* __restrict__ X, c
 }
 __device__ __forceinline__ int block_dim_of(const int4 c) { return (c.x >= 0 || c.w >= 0) ? 12 : (c.z >= 0 ? 9 : 6); }
 
+} // namespace cipc
+#include "merge.cuh"
+namespace cipc {
+
 struct BarrierParams {
     double dHat2;      // already offset: dHat2 + 2 sqrt(dHat2) xi   (IPC.h:756-757)
     double thickness2; // xi^2
@@ -1102,7 +1106,7 @@ __device__ __forceinline__ void put_triplet(cipc_triplet* o, int row, int col, d
 template <int CLS>
 __global__ void __launch_bounds__(128) k_hessian_lowrank(const double4* __restrict__ X, const int4* __restrict__ cs,
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
-    int projectSPD, cipc_triplet* trip)
+    int projectSPD, cipc_triplet* trip, int blkMode)
 {
     const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -1117,7 +1121,18 @@ __global__ void __launch_bounds__(128) k_hessian_lowrank(const double4* __restri
     constexpr int NB = (CLS == 0) ? 4 : (CLS == 1 ? 3 : 2);
     constexpr int NN = 3 * NB;
     int vid[4] = {s.v[0], s.v[1], s.v[2], s.v[3]};
+    double* ob = reinterpret_cast<double*>(trip) + (size_t)off[i] * 9; // block mode: off[] counts blocks, 9 doubles each
     auto emit = [&](int I, int J, const double* B) {
+        if (blkMode) { // upper block triangle, stored for (min vertex, max vertex) (merge.cuh)
+            if (J < I) return;
+            double* q = ob + 9 * (I * NB - I * (I - 1) / 2 + (J - I));
+            const bool sw = vid[I] > vid[J];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 3; ++b2) q[3 * a + b2] = sw ? B[3 * b2 + a] : B[3 * a + b2];
+            return;
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -1304,10 +1319,12 @@ template <int CLS> struct FusedShape {
     static constexpr int YS = (YD % 2 == 0) ? YD + 1 : YD; // odd stride: conflict-free 8-byte accesses, one stencil per lane
     static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
 };
-template <int CLS>
+// BLK: the stencil's upper 3x3 blocks (9 doubles each, merge.cuh) are written instead of 16-byte triplets -- 720 instead of
+// 2304 bytes per PT/EE stencil -- and `off` counts blocks.
+template <int CLS, bool BLK>
 __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
-    cipc_triplet* __restrict__ trip, u32* denseList, u32* denseCount, double* gOut)
+    void* __restrict__ outp, u32* denseList, u32* denseCount, double* gOut)
 {
     constexpr int NN = FusedShape<CLS>::NN, NY = FusedShape<CLS>::NY, YS = FusedShape<CLS>::YS;
     extern __shared__ __align__(16) unsigned char fused_sm[];
@@ -1353,14 +1370,15 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
         }
     }
     __syncwarp();
-    warp_expand_stencils<NN, NY, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, trip);
+    if (BLK) warp_expand_blocks<YShape<CLS>::NB, NY, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<double*>(outp));
+    else warp_expand_stencils<NN, NY, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<cipc_triplet*>(outp));
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 constexpr int DENSE_BD = 64;                              // threads per block of the dense path
 constexpr int DENSE_SMEM = (45 + 81) * DENSE_BD * 8;       // upper triangle of the 9x9 matrix + eigenvectors per thread
 __global__ void __launch_bounds__(DENSE_BD) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
     const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
-    const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip)
+    const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip, int blkMode)
 {
     extern __shared__ double dense_sm[];
     if (nDev) n = *nDev; // list length produced on the device (fallbacks of the factor kernels)
@@ -1371,6 +1389,7 @@ __global__ void __launch_bounds__(DENSE_BD) k_barrier_hessian(const double4* __r
         stencil_hessian(X, X0, cs[i], info[i].x, bp, false, H, vids, nb);
         if (projectSPD) psd_project_reduced_smem(H, nb, dense_sm, threadIdx.x, DENSE_BD);
         const int nn = 3 * nb;
+        if (blkMode) { store_blocks_dense(H, nb, vids, reinterpret_cast<double*>(trip) + (size_t)off[i] * 9); continue; }
         cipc_triplet* o = trip + (size_t)off[i] * 9;
         for (int I = 0; I < nb; ++I)
             for (int a = 0; a < 3; ++a)
@@ -1591,6 +1610,13 @@ struct cipc_ctx {
     size_t nBlk = 0;
     u32 nU = 0;
     bool csrValid = false;
+    // block-mode Hessian + device-side merge (merge.cuh): unique upper blocks (mRow, mCol, mVal) of the Hessian computed last
+    DevBuf<u64> ent;
+    DevBuf<u32> rowStart, rowCur, mHeads, mScan, mRow, mCol, mStart;
+    DevBuf<double> mVal;
+    u32 nBlkLast = 0, nUm = 0, nDiag = 0;
+    bool mergedValid = false;
+    PinnedBuf pinMK, pinMV;
     // lagged friction (FEM/FRICTION.h): the friction set lives on the device between calls
     DevBuf<double4> Xn;
     bool haveXn = false;
@@ -1671,6 +1697,28 @@ u64 fnv(const void* p, size_t n, u64 h)
     h = a ^ (b * 3) ^ (d * 5) ^ (e * 7);
     for (; i < n; ++i) h = (h ^ c[i]) * 0x100000001b3ULL;
     return h ^ (h >> 29) ^ (u64)n;
+}
+
+// change detector for large host arrays (topology lists, the caller's constraint set): hashed in 1 MiB pieces by a few
+// host threads, the piece hashes chained in order -- ~1 ms per 50 MB instead of ~5 ms single-threaded
+struct HashSeg { const unsigned char* p; size_t n; };
+u64 hash_segments(const HashSeg* segs, int nSeg, u64 h)
+{
+    const size_t PIECE = (size_t)1 << 20;
+    std::vector<HashSeg> pieces;
+    for (int k = 0; k < nSeg; ++k)
+        for (size_t o = 0; o < segs[k].n; o += PIECE) pieces.push_back({segs[k].p + o, std::min(PIECE, segs[k].n - o)});
+    std::vector<u64> ph(pieces.size());
+    const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, pieces.size() / 4));
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (size_t k; (k = next.fetch_add(1)) < pieces.size();) ph[k] = fnv(pieces[k].p, pieces[k].n, 0x9E3779B97F4A7C15ULL + k);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return fnv(ph.data(), ph.size() * sizeof(u64), h);
 }
 
 void upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int stride_bytes)
@@ -1997,6 +2045,7 @@ int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
         run_pairs<true>(c, H, thickness, counts);
     }
     c->ctr["ccd_pairs"] = (int64_t)counts[0] + counts[1] + counts[2] + counts[3];
+    c->ctr["ccd_pairs_ee"] = counts[1];
     {
         cipc_ctx::Scope sc(c, "ccd_accd");
         u64 bits;
@@ -2004,10 +2053,16 @@ int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
         CIPC_CUDA(cudaMemcpyAsync(c->scal.p + 1, &bits, 8, cudaMemcpyHostToDevice, c->st));
         CIPC_CUDA(cudaMemsetAsync(c->errFlag.p, 0, sizeof(int), c->st));
         AccdOut out{(u64*)(c->scal.p + 1), c->errFlag.p};
-        if (counts[0]) CIPC_LAUNCH(k_accd_pt, div_up(counts[0], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[0].p, counts[0], thickness, alpha, out);
-        if (counts[2]) CIPC_LAUNCH(k_accd_pe, div_up(counts[2], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[2].p, counts[2], thickness, alpha, out);
-        if (counts[3]) CIPC_LAUNCH(k_accd_pp, div_up(counts[3], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[3].p, counts[3], thickness, alpha, out);
-        if (counts[1]) CIPC_LAUNCH(k_accd_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[1].p, counts[1], thickness, alpha, out);
+        {
+            cipc_ctx::Scope sp(c, "ccd_accd_pt");
+            if (counts[0]) CIPC_LAUNCH(k_accd_pt, div_up(counts[0], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[0].p, counts[0], thickness, alpha, out);
+            if (counts[2]) CIPC_LAUNCH(k_accd_pe, div_up(counts[2], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[2].p, counts[2], thickness, alpha, out);
+            if (counts[3]) CIPC_LAUNCH(k_accd_pp, div_up(counts[3], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[3].p, counts[3], thickness, alpha, out);
+        }
+        {
+            cipc_ctx::Scope se(c, "ccd_accd_ee");
+            if (counts[1]) CIPC_LAUNCH(k_accd_ee, div_up(counts[1], 128), 128, 0, c->st, T, c->X.p, c->P.p, c->cand[1].p, counts[1], thickness, alpha, out);
+        }
     }
     return CIPC_OK;
 }
@@ -2020,6 +2075,42 @@ int do_min_dist(cipc_ctx* c, bool wantDist)
     if (wantDist) c->dist2.reserve(c->nC, c->st);
     if (c->nC) CIPC_LAUNCH(k_min_dist, RED_GRID, RED_BT, 0, c->st, c->X.p, c->cs.p, c->nC, wantDist ? c->dist2.p : nullptr, (long long*)(c->scal.p + 2));
     return CIPC_OK;
+}
+
+enum HessOutF { HF_HOST = 0, HF_DEV = 1, HF_BLK = 2 };
+// ---- device-side merge of the block stream of the Hessian computed last (merge.cuh): blkVal holds `tot` upper blocks of the
+// `nSt` stencils `st` at the offsets in tripOff; afterwards (mRow, mCol, mVal) are the nUm unique upper blocks sorted by
+// (row, col), nDiag of them diagonal, and nTrip = 9 (nUm + off-diagonal) is the number of MERGED triplets of the full matrix
+void merge_blocks(cipc_ctx* c, const int4* st, u32 nSt, u32 tot)
+{
+    cipc_ctx::Scope sc(c, "hessian_merge");
+    const int nV = c->T.nV;
+    need(nV < (1 << 28), "block merge: more than 2^28 nodes");
+    c->rowStart.reserve((size_t)nV + 1, c->st); c->rowCur.reserve((size_t)nV + 1, c->st);
+    c->ent.reserve((size_t)tot + 1, c->st); c->mHeads.reserve((size_t)tot + 1, c->st); c->mScan.reserve((size_t)tot + 1, c->st);
+    CIPC_CUDA(cudaMemsetAsync(c->rowCur.p, 0, ((size_t)nV + 1) * 4, c->st));
+    CIPC_LAUNCH(k_blk_rows<false>, div_up(nSt, TB), TB, 0, c->st, st, c->tripOff.p, nSt, c->rowCur.p, (u64*)nullptr);
+    device_excl_scan(c->rowCur.p, c->rowStart.p, (size_t)nV + 1, c->scanwk, c->st);
+    CIPC_CUDA(cudaMemcpyAsync(c->rowCur.p, c->rowStart.p, ((size_t)nV + 1) * 4, cudaMemcpyDeviceToDevice, c->st));
+    CIPC_LAUNCH(k_blk_rows<true>, div_up(nSt, TB), TB, 0, c->st, st, c->tripOff.p, nSt, c->rowCur.p, c->ent.p);
+    u32* nRowsDev = c->counters.p + 7;
+    CIPC_CUDA(cudaMemsetAsync(nRowsDev, 0, 4, c->st));
+    CIPC_LAUNCH(k_row_sort, div_up(nV, MRS_ROWS), MRS_BT, 0, c->st, c->rowStart.p, nV, c->ent.p, c->mHeads.p, nRowsDev);
+    device_excl_scan(c->mHeads.p, c->mScan.p, tot, c->scanwk, c->st);
+    u32 h[2];
+    CIPC_CUDA(cudaMemcpyAsync(&h[0], c->scanwk.total.p, 4, cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaMemcpyAsync(&h[1], nRowsDev, 4, cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaStreamSynchronize(c->st));
+    const u32 nU = h[0];
+    c->mRow.reserve((size_t)nU + 1, c->st); c->mCol.reserve((size_t)nU + 1, c->st); c->mStart.reserve((size_t)nU + 1, c->st);
+    c->mVal.reserve((size_t)nU * 9 + 16, c->st);
+    CIPC_LAUNCH(k_blk_uniq, div_up(tot, TB), TB, 0, c->st, c->ent.p, c->mHeads.p, c->mScan.p, tot, c->rowStart.p, nV, c->mRow.p, c->mCol.p, c->mStart.p);
+    CIPC_LAUNCH(k_blk_sum, div_up(nU, 32), 288, 0, c->st, c->blkVal.p, c->ent.p, c->mStart.p, nU, tot, c->mVal.p);
+    c->nUm = nU;
+    c->nDiag = h[1]; // every vertex of a stencil owns a diagonal block, which opens its row
+    c->nTrip = (int64_t)9 * ((int64_t)nU + (int64_t)(nU - h[1]));
+    c->mergedValid = true;
+    c->ctr["merge_blocks_in"] = tot; c->ctr["merge_blocks_unique"] = nU; c->ctr["merge_blocks_diag"] = h[1];
 }
 
 // ---- friction stage bodies (FEM/FRICTION.h)
@@ -2063,17 +2154,20 @@ int do_friction_gradient(cipc_ctx* c, double epsvh2, double mu, bool accumulate)
         std::sqrt(epsvh2), mu, c->g.p);
     return CIPC_OK;
 }
-int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu, bool devTriplets)
+int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu, HessOutF mode)
 {
     need(c->haveX && c->haveXn, "positions / previous positions not set");
+    const bool devTriplets = mode != HF_HOST, blk = mode == HF_BLK;
     c->nTrip = 0;
     c->factorValid = false;
+    c->mergedValid = false;
     c->hessStencils = c->fcs.p; c->hessN = c->nF;
     if (!c->nF) return CIPC_OK;
     cipc_ctx::Scope sc(c, "friction_H");
     const u32 nF = c->nF;
     c->tripOff.reserve(nF, c->st);
-    CIPC_LAUNCH(k_block_sizes, div_up(nF, TB), TB, 0, c->st, c->fcs.p, nF, c->tripOff.p);
+    if (blk) CIPC_LAUNCH(k_blk_sizes, div_up(nF, TB), TB, 0, c->st, c->fcs.p, nF, c->tripOff.p);
+    else CIPC_LAUNCH(k_block_sizes, div_up(nF, TB), TB, 0, c->st, c->fcs.p, nF, c->tripOff.p);
     device_excl_scan(c->tripOff.p, c->tripOff.p, nF, c->scanwk, c->st);
     for (int k = 0; k < 4; ++k) c->clsIdx[k].reserve(nF, c->st);
     CIPC_CUDA(cudaMemsetAsync(c->counters.p + 12, 0, 4 * sizeof(u32), c->st)); // also zeroes counters[15], the dense-list length
@@ -2084,18 +2178,27 @@ int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu, bool devTriplets)
     CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
     CIPC_CUDA(cudaStreamSynchronize(c->st));
     need(nk[3] == 0, "mollified stencil in the friction constraint set");
-    c->nTrip = (int64_t)tot * 9;
-    c->trip.reserve((size_t)c->nTrip, c->st);
+    void* outp;
+    if (blk) {
+        c->blkVal.reserve((size_t)tot * 9 + 16, c->st);
+        c->nBlkLast = tot;
+        outp = c->blkVal.p;
+    }
+    else {
+        c->nTrip = (int64_t)tot * 9;
+        c->trip.reserve((size_t)c->nTrip, c->st);
+        outp = c->trip.p;
+    }
     const double epsvh = std::sqrt(epsvh2);
     if (devTriplets) {
-        // device-resident stream: factors go through shared memory only (k_friction_fused)
+        // device-resident output: factors go through shared memory only (k_friction_fused)
         cipc_ctx::Scope sk(c, "k_friction_fused");
-        if (nk[0]) CIPC_LAUNCH(k_friction_fused<0>, div_up(nk[0], FUSED_BD), FUSED_BD, FrFusedShape<0>::SMEM, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p,
-            c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[0].p, nk[0], epsvh, epsvh2, mu, c->trip.p);
-        if (nk[1]) CIPC_LAUNCH(k_friction_fused<1>, div_up(nk[1], FUSED_BD), FUSED_BD, FrFusedShape<1>::SMEM, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p,
-            c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[1].p, nk[1], epsvh, epsvh2, mu, c->trip.p);
-        if (nk[2]) CIPC_LAUNCH(k_friction_fused<2>, div_up(nk[2], FUSED_BD), FUSED_BD, FrFusedShape<2>::SMEM, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p,
-            c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[2].p, nk[2], epsvh, epsvh2, mu, c->trip.p);
+#define CIPC_FRF(CLS, B) CIPC_LAUNCH((k_friction_fused<CLS, B>), div_up(nk[CLS], FUSED_BD), FUSED_BD, FrFusedShape<CLS>::SMEM, c->st, c->X.p, c->Xn.p, \
+    c->fcs.p, c->fcp.p, c->fB.p, c->fnf.p, c->tripOff.p, c->clsIdx[CLS].p, nk[CLS], epsvh, epsvh2, mu, outp)
+        if (nk[0]) { if (blk) CIPC_FRF(0, true); else CIPC_FRF(0, false); }
+        if (nk[1]) { if (blk) CIPC_FRF(1, true); else CIPC_FRF(1, false); }
+        if (nk[2]) { if (blk) CIPC_FRF(2, true); else CIPC_FRF(2, false); }
+#undef CIPC_FRF
         for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
     }
     else {
@@ -2120,6 +2223,7 @@ int do_friction_hessian(cipc_ctx* c, double epsvh2, double mu, bool devTriplets)
     c->ny[0] = c->ny[1] = c->ny[2] = 2;
     }
     c->ctr["friction_4pt"] = nk[0]; c->ctr["friction_pe"] = nk[1]; c->ctr["friction_pp"] = nk[2];
+    if (blk) merge_blocks(c, c->fcs.p, nF, tot);
     return CIPC_OK;
 }
 
@@ -2278,10 +2382,105 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     }
 }
 
+// Delivers the MERGED triplets (cipc_barrier_hessian_merged / cipc_friction_hessian_merged): the unique upper blocks cross PCIe
+// (80 bytes per block: row, col, 9 values) in pieces and the host threads write, for every block, its 9 triplets and --
+// off-diagonal blocks -- the 9 triplets of the transposed block.  Layout of `out`: [0, 9 nU) the upper blocks in (row, col)
+// order, [9 nU, 9 (nU + nOff)) the mirrored blocks in the same order.
+void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
+{
+    const size_t nU = c->nUm;
+    if (!nU) return;
+    u32* hR = (u32*)c->pinMK.reserve(nU * 8 + 64);
+    u32* hC = hR + nU;
+    double* hV = (double*)c->pinMV.reserve(nU * 72 + 64);
+    CIPC_CUDA(cudaMemcpyAsync(hR, c->mRow.p, nU * 4, cudaMemcpyDeviceToHost, c->st));
+    CIPC_CUDA(cudaMemcpyAsync(hC, c->mCol.p, nU * 4, cudaMemcpyDeviceToHost, c->st));
+    cudaEvent_t keysEv;
+    CIPC_CUDA(cudaEventCreateWithFlags(&keysEv, cudaEventDisableTiming));
+    CIPC_CUDA(cudaEventRecord(keysEv, c->st));
+    const size_t PIECE = (size_t)1 << 19; // blocks per piece (36 MiB of values)
+    const size_t nPieces = (nU + PIECE - 1) / PIECE;
+    std::vector<cudaEvent_t> evs(nPieces);
+    for (size_t k = 0; k < nPieces; ++k) {
+        const size_t a = k * PIECE, b = std::min(nU, a + PIECE);
+        CIPC_CUDA(cudaMemcpyAsync(hV + a * 9, c->mVal.p + a * 9, (b - a) * 72, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+        CIPC_CUDA(cudaEventRecord(evs[k], c->st));
+    }
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("CIPC_HOST_THREADS")) nt = atoi(e);
+    nt = std::max(1, std::min(nt, 256));
+    bool failed = cudaEventSynchronize(keysEv) != cudaSuccess;
+    cudaEventDestroy(keysEv);
+    // off-diagonal blocks before each chunk of CH blocks (the mirrored region is indexed by the off-diagonal rank)
+    const size_t CH = 4096, nChunks = (nU + CH - 1) / CH; // PIECE is a multiple of CH
+    std::vector<size_t> offBefore(nChunks + 1, 0);
+    {
+        std::atomic<size_t> next(0);
+        auto cnt = [&]() {
+            for (size_t k; (k = next.fetch_add(1)) < nChunks;) {
+                const size_t a = k * CH, b = std::min(nU, a + CH);
+                size_t n = 0;
+                for (size_t u = a; u < b; ++u) n += hR[u] != hC[u];
+                offBefore[k + 1] = n;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < std::min<int>(nt, 8); ++t) th.emplace_back(cnt);
+        cnt();
+        for (auto& t : th) t.join();
+        for (size_t k = 0; k < nChunks; ++k) offBefore[k + 1] += offBefore[k];
+    }
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    std::atomic<size_t> landed(0), next(0);
+    auto put = [&](cipc_triplet* o, unsigned r, unsigned cc, double v) {
+        long long vb;
+        memcpy(&vb, &v, 8);
+        const __m128i t = _mm_set_epi64x(vb, (long long)(((unsigned long long)cc << 32) | r));
+        if (aligned) _mm_stream_si128(reinterpret_cast<__m128i*>(o), t); else _mm_storeu_si128(reinterpret_cast<__m128i*>(o), t);
+    };
+    auto worker = [&]() {
+        for (size_t k; (k = next.fetch_add(1)) < nChunks;) {
+            const size_t a = k * CH, b = std::min(nU, a + CH);
+            while (landed.load(std::memory_order_acquire) <= (b - 1) / PIECE) std::this_thread::yield();
+            size_t off = offBefore[k];
+            for (size_t u = a; u < b; ++u) {
+                const unsigned r3 = 3u * hR[u], c3 = 3u * hC[u];
+                const double* v = hV + u * 9;
+                cipc_triplet* o = out + u * 9;
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) put(o + 3 * i + j, r3 + i, c3 + j, v[3 * i + j]);
+                if (r3 != c3) {
+                    cipc_triplet* m = out + (nU + off) * 9;
+                    for (int j = 0; j < 3; ++j)
+                        for (int i = 0; i < 3; ++i) put(m + 3 * j + i, c3 + j, r3 + i, v[3 * i + j]);
+                    ++off;
+                }
+            }
+        }
+        _mm_sfence();
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+    for (size_t k = 0; k < nPieces; ++k) { // this thread publishes the pieces as they land, then joins the work
+        if (!failed && cudaEventSynchronize(evs[k]) != cudaSuccess) failed = true;
+        landed.store(k + 1, std::memory_order_release);
+    }
+    worker();
+    for (auto& t : th) t.join();
+    for (auto e : evs) cudaEventDestroy(e);
+    if (failed) throw CudaError("device-to-host copy of the merged Hessian blocks failed");
+}
+
 // ========================================================================================= C ABI
 extern "C" {
 
-const char* cipc_version(void) { return "cipc_b200 0.1 (sm_100a)"; }
+const char* cipc_version(void) { return "cipc_b200 0.2 (sm_100a)"; }
+uint64_t cipc_hash_bytes(const void* p, size_t n)
+{
+    const HashSeg sg{(const unsigned char*)p, n};
+    return hash_segments(&sg, 1, 0xcbf29ce484222325ULL);
+}
 int64_t cipc_kernel_launches(void) { return g_launches; }
 
 int cipc_create(int device, int rank, int world, cipc_ctx** out)
@@ -2307,12 +2506,18 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
         c->nTasksDev.reserve(1, c->st);
         CIPC_CUDA(cudaMemsetAsync(c->scal.p, 0, 16 * sizeof(double), c->st));
         CIPC_CUDA(cudaFuncSetAttribute(k_barrier_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM));
-        CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<0>::SMEM));
-        CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<1>::SMEM));
-        CIPC_CUDA(cudaFuncSetAttribute(k_hessian_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<2>::SMEM));
-        CIPC_CUDA(cudaFuncSetAttribute(k_friction_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<0>::SMEM));
-        CIPC_CUDA(cudaFuncSetAttribute(k_friction_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<1>::SMEM));
-        CIPC_CUDA(cudaFuncSetAttribute(k_friction_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<2>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_hessian_fused<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<0>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_hessian_fused<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<1>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_hessian_fused<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<2>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_hessian_fused<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<0>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_hessian_fused<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<1>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_hessian_fused<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, FusedShape<2>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_friction_fused<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<0>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_friction_fused<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<1>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_friction_fused<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<2>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_friction_fused<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<0>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_friction_fused<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<1>::SMEM));
+        CIPC_CUDA(cudaFuncSetAttribute((k_friction_fused<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, FrFusedShape<2>::SMEM));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
     }
     catch (const std::exception& e) {
@@ -2377,29 +2582,14 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         const int hdr[8] = {nV, nBN, nBE, nBT, nRod, codim[0], codim[1], nNnx};
         h = fnv(hdr, sizeof(hdr), h);
         {
-            // the three index arrays (tens of MB at 1M triangles) are hashed in 1 MiB pieces by a few host threads and the
-            // piece hashes are chained in order: the check costs ~1 ms instead of ~5 ms per call
-            struct Seg { const unsigned char* p; size_t n; };
-            const Seg segs[4] = {{(const unsigned char*)BN, (size_t)nBN * 4}, {(const unsigned char*)BE, (size_t)nBE * be_stride * 4},
+            const HashSeg segs[4] = {{(const unsigned char*)BN, (size_t)nBN * 4}, {(const unsigned char*)BE, (size_t)nBE * be_stride * 4},
                 {(const unsigned char*)BT, (size_t)nBT * bt_stride * 4}, {(const unsigned char*)dbc, (size_t)nV}};
-            const size_t PIECE = (size_t)1 << 20;
-            std::vector<Seg> pieces;
-            for (const Seg& sg : segs)
-                for (size_t o = 0; o < sg.n; o += PIECE) pieces.push_back({sg.p + o, std::min(PIECE, sg.n - o)});
-            std::vector<u64> ph(pieces.size());
-            const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, pieces.size() / 4));
-            std::atomic<size_t> next(0);
-            auto work = [&]() {
-                for (size_t k; (k = next.fetch_add(1)) < pieces.size();) ph[k] = fnv(pieces[k].p, pieces[k].n, 0x9E3779B97F4A7C15ULL + k);
-            };
-            std::vector<std::thread> th;
-            for (int t = 1; t < nt; ++t) th.emplace_back(work);
-            work();
-            for (auto& t : th) t.join();
-            h = fnv(ph.data(), ph.size() * sizeof(u64), h);
+            h = hash_segments(segs, 4, h);
         }
         if (nNnx) h = fnv(nnxPairs, (size_t)nNnx * 8, h);
         if (BNArea) h = fnv(BNArea, (size_t)nBN * 8, h ^ 1);
+        if (BEArea) h = fnv(BEArea, (size_t)nBE * 8, h ^ 2);
+        if (BTArea) h = fnv(BTArea, (size_t)nBT * 8, h ^ 3);
         if (h == c->topoHash && c->T.nV == nV) return (int)CIPC_OK; // unchanged: keep the resident copy
         Topo& T = c->T;
         T.nV = nV; T.nBN = nBN; T.nBE = nBE; T.nBT = nBT; T.nRod = nRod; T.codim0 = codim[0]; T.codim1 = codim[1];
@@ -2533,10 +2723,16 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             cipc_ctx::Scope sc(c, "ccs_narrow");
             CIPC_CUDA(cudaMemsetAsync(c->counters.p + 8, 0, 4 * sizeof(u32), c->st));
             NarrowOut out{c->cs.p, c->raw.p, c->counters.p + 8};
-            if (counts[0]) CIPC_LAUNCH(k_narrow_pt, div_up(counts[0], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[0].p, counts[0], dHat2o, out);
-            if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->restLen2.p, c->cand[1].p, counts[1], dHat2o, out);
-            if (counts[2]) CIPC_LAUNCH(k_narrow_pe, div_up(counts[2], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[2].p, counts[2], dHat2o, out);
-            if (counts[3]) CIPC_LAUNCH(k_narrow_pp, div_up(counts[3], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[3].p, counts[3], dHat2o, out);
+            {
+                cipc_ctx::Scope sp(c, "ccs_narrow_pt"); // point queries: PT + the codimensional PE / PP candidates (the reference's _PT scope)
+                if (counts[0]) CIPC_LAUNCH(k_narrow_pt, div_up(counts[0], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[0].p, counts[0], dHat2o, out);
+                if (counts[2]) CIPC_LAUNCH(k_narrow_pe, div_up(counts[2], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[2].p, counts[2], dHat2o, out);
+                if (counts[3]) CIPC_LAUNCH(k_narrow_pp, div_up(counts[3], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->cand[3].p, counts[3], dHat2o, out);
+            }
+            {
+                cipc_ctx::Scope se(c, "ccs_narrow_ee");
+                if (counts[1]) CIPC_LAUNCH(k_narrow_ee, div_up(counts[1], NARROW_BT), NARROW_BT, 0, c->st, T, c->X.p, c->restLen2.p, c->cand[1].p, counts[1], dHat2o, out);
+            }
             CIPC_CUDA(cudaMemcpyAsync(hc, c->counters.p + 8, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
             CIPC_CUDA(cudaStreamSynchronize(c->st));
         }
@@ -2632,21 +2828,27 @@ int cipc_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double
         return (int)CIPC_OK;
     });
 }
+enum HessOut { H_HOST = 0, H_DEV = 1, H_BLK = 2 };
+// H_HOST: factors for the host-side expansion (cipc_get_triplets ships them over PCIe); H_DEV: the (row, col, value) stream in
+// HBM (fused factor + expansion); H_BLK: upper 3x3 blocks + device-side merge into the unique blocks (merge.cuh)
 static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
-    int64_t* nTrip, bool devTriplets, bool withGradient = false)
+    int64_t* nTrip, HessOut mode, bool withGradient = false)
 {
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->haveX, "positions not set");
         c->begin_call();
         const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
+        const bool blk = mode == H_BLK;
         c->nTrip = 0;
         c->factorValid = false;
+        c->mergedValid = false;
         c->hessStencils = c->cs.p; c->hessN = c->nC;
         if (c->nC) {
             cipc_ctx::Scope sc(c, "barrier_H");
             c->tripOff.reserve(c->nC, c->st);
-            CIPC_LAUNCH(k_block_sizes, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->tripOff.p);
+            if (blk) CIPC_LAUNCH(k_blk_sizes, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->tripOff.p);
+            else CIPC_LAUNCH(k_block_sizes, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->tripOff.p);
             device_excl_scan(c->tripOff.p, c->tripOff.p, c->nC, c->scanwk, c->st);
             u32 tot, nk[4];
             CIPC_CUDA(cudaMemcpyAsync(&tot, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
@@ -2655,18 +2857,29 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
             CIPC_LAUNCH(k_classify, div_up(c->nC, TB), TB, 0, c->st, c->cs.p, c->nC, c->clsIdx[0].p, c->clsIdx[1].p, c->clsIdx[2].p,
                 c->clsIdx[3].p, c->counters.p + 12);
             CIPC_CUDA(cudaMemcpyAsync(nk, c->counters.p + 12, 4 * sizeof(u32), cudaMemcpyDeviceToHost, c->st));
-            CIPC_CUDA(cudaStreamSynchronize(c->st)); // one host round trip for the triplet total and the class counts
-            c->nTrip = (int64_t)tot * 9;
-            c->trip.reserve((size_t)c->nTrip, c->st);
+            CIPC_CUDA(cudaStreamSynchronize(c->st)); // one host round trip for the triplet / block total and the class counts
+            void* outp;
+            if (blk) {
+                c->blkVal.reserve((size_t)tot * 9 + 16, c->st);
+                c->nBlkLast = tot;
+                outp = c->blkVal.p;
+            }
+            else {
+                c->nTrip = (int64_t)tot * 9;
+                c->trip.reserve((size_t)c->nTrip, c->st);
+                outp = c->trip.p;
+            }
+            cipc_triplet* outT = reinterpret_cast<cipc_triplet*>(outp);
+            const int bm = blk ? 1 : 0;
             const char* dense = getenv("CIPC_HESSIAN_DENSE"); // cross-check switch: force the dense eigen path for every stencil
             if (dense && dense[0] == '1') {
                 cipc_ctx::Scope sk(c, "k_barrier_hessian");
                 CIPC_LAUNCH(k_barrier_hessian, div_up(c->nC, DENSE_BD), DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
-                    (const u32*)nullptr, c->nC, (const u32*)nullptr, bp, projectSPD, c->trip.p);
+                    (const u32*)nullptr, c->nC, (const u32*)nullptr, bp, projectSPD, outT, bm);
             }
             else {
-                if (projectSPD && devTriplets) {
-                    // device-resident triplets: fused factor + expansion, the factors never leave the SM
+                if (projectSPD && mode != H_HOST) {
+                    // device-resident output: fused factor + expansion, the factors never leave the SM
                     u32* dl = c->clsIdx[3].p; u32* dn = c->counters.p + 15;
                     double* gOut = nullptr;
                     if (withGradient) { // the barrier gradient of every stencil rides on the same pass
@@ -2676,21 +2889,21 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                         if (nk[3]) CIPC_LAUNCH(k_barrier_gradient, div_up(nk[3], 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, nk[3], bp, c->g.p,
                             (const u32*)c->clsIdx[3].p); // mollified stencils (the first nk[3] entries of the dense list)
                     }
+#define CIPC_FUSED(CLS, B) CIPC_LAUNCH((k_hessian_fused<CLS, B>), div_up(nk[CLS], FUSED_BD), FUSED_BD, FusedShape<CLS>::SMEM, c->st, c->X.p, c->cs.p, \
+    c->info.p, c->tripOff.p, c->clsIdx[CLS].p, nk[CLS], bp, outp, dl, dn, gOut)
                     {
                         cipc_ctx::Scope sk(c, "k_hessian_fused0"); // the longest launch of the stage: PT/EE blocks
-                        if (nk[0]) CIPC_LAUNCH(k_hessian_fused<0>, div_up(nk[0], FUSED_BD), FUSED_BD, FusedShape<0>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
-                            c->tripOff.p, c->clsIdx[0].p, nk[0], bp, c->trip.p, dl, dn, gOut);
+                        if (nk[0]) { if (blk) CIPC_FUSED(0, true); else CIPC_FUSED(0, false); }
                     }
                     {
                         cipc_ctx::Scope sk(c, "k_hessian_fused12");
-                        if (nk[1]) CIPC_LAUNCH(k_hessian_fused<1>, div_up(nk[1], FUSED_BD), FUSED_BD, FusedShape<1>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
-                            c->tripOff.p, c->clsIdx[1].p, nk[1], bp, c->trip.p, dl, dn, gOut);
-                        if (nk[2]) CIPC_LAUNCH(k_hessian_fused<2>, div_up(nk[2], FUSED_BD), FUSED_BD, FusedShape<2>::SMEM, c->st, c->X.p, c->cs.p, c->info.p,
-                            c->tripOff.p, c->clsIdx[2].p, nk[2], bp, c->trip.p, dl, dn, gOut);
+                        if (nk[1]) { if (blk) CIPC_FUSED(1, true); else CIPC_FUSED(1, false); }
+                        if (nk[2]) { if (blk) CIPC_FUSED(2, true); else CIPC_FUSED(2, false); }
                     }
+#undef CIPC_FUSED
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
                     CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
-                        (const u32*)dn, bp, projectSPD, c->trip.p);
+                        (const u32*)dn, bp, projectSPD, outT, bm);
                 }
                 else if (projectSPD) {
                     // (A) factor, (B) expand; stencils the factor kernels reject are appended to the dense list
@@ -2716,21 +2929,22 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     c->ny[0] = 3; c->ny[1] = 2; c->ny[2] = 1;
                     // mollified stencils + rejected ones: dense eigen path, list length read on the device
                     CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
-                        (const u32*)dn, bp, projectSPD, c->trip.p);
+                        (const u32*)dn, bp, projectSPD, outT, 0);
                 }
                 else {
                     cipc_ctx::Scope sk(c, "k_barrier_hessian");
                     if (nk[0]) CIPC_LAUNCH(k_hessian_lowrank<0>, div_up(nk[0], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
-                        c->clsIdx[0].p, nk[0], bp, projectSPD, c->trip.p);
+                        c->clsIdx[0].p, nk[0], bp, projectSPD, outT, bm);
                     if (nk[1]) CIPC_LAUNCH(k_hessian_lowrank<1>, div_up(nk[1], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
-                        c->clsIdx[1].p, nk[1], bp, projectSPD, c->trip.p);
+                        c->clsIdx[1].p, nk[1], bp, projectSPD, outT, bm);
                     if (nk[2]) CIPC_LAUNCH(k_hessian_lowrank<2>, div_up(nk[2], 128), 128, 0, c->st, c->X.p, c->cs.p, c->info.p, c->tripOff.p,
-                        c->clsIdx[2].p, nk[2], bp, projectSPD, c->trip.p);
+                        c->clsIdx[2].p, nk[2], bp, projectSPD, outT, bm);
                     if (nk[3]) CIPC_LAUNCH(k_barrier_hessian, div_up(nk[3], DENSE_BD), DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
-                        c->clsIdx[3].p, nk[3], (const u32*)nullptr, bp, projectSPD, c->trip.p);
+                        c->clsIdx[3].p, nk[3], (const u32*)nullptr, bp, projectSPD, outT, bm);
                 }
                 c->ctr["hessian_4pt"] = nk[0]; c->ctr["hessian_pe"] = nk[1]; c->ctr["hessian_pp"] = nk[2]; c->ctr["hessian_mollified"] = nk[3];
             }
+            if (blk) merge_blocks(c, c->cs.p, c->nC, tot);
         }
         if (nTrip) *nTrip = c->nTrip;
         return (int)CIPC_OK;
@@ -2739,21 +2953,27 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
 int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
     int64_t* nTrip)
 {
-    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, false);
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, H_HOST);
+}
+int cipc_barrier_hessian_merged(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
+    int64_t* nTrip)
+{
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, H_BLK);
 }
 int cipc_barrier_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
     int64_t* nTrip)
 {
-    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, true);
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, H_DEV);
 }
 int cipc_barrier_gradient_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int64_t* nTrip)
 {
-    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, 1, nTrip, true, true);
+    return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, 1, nTrip, H_DEV, true);
 }
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 {
     return guarded(ctx, [&]() {
         if (!ctx->nTrip) return (int)CIPC_OK;
+        if (ctx->mergedValid) { deliver_merged_host(ctx, out); return (int)CIPC_OK; }
         const char* dma = getenv("CIPC_TRIPLETS_DMA"); // =1: always copy the expanded stream over PCIe
         if (ctx->factorValid && !(dma && dma[0] == '1')) deliver_triplets_host(ctx, out);
         else {
@@ -2803,7 +3023,7 @@ int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDi
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         c->begin_call();
-        if (c->nC == 0) return (int)CIPC_ERR_ARG; // reference dereferences min_element of an empty vector
+        if (c->nC == 0) return (int)CIPC_OK; // the reference returns early on an empty set and leaves dist2 / minDist2 untouched (IPC.h:2253)
         int r = do_min_dist(c, dist2 != nullptr);
         if (r) return r;
         long long bits;
@@ -2933,7 +3153,7 @@ int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSP
     (void)projectSPD; // the inner 2x2 matrix is positive semi-definite in closed form: makePD is the identity (friction.cuh)
     return guarded(ctx, [&]() {
         ctx->begin_call();
-        int r = do_friction_hessian(ctx, epsvh2, mu, false);
+        int r = do_friction_hessian(ctx, epsvh2, mu, HF_HOST);
         if (nTrip) *nTrip = ctx->nTrip;
         return r;
     });
@@ -2943,7 +3163,18 @@ int cipc_friction_hessian_dev(cipc_ctx* ctx, double epsvh2, double mu, int proje
     (void)projectSPD;
     return guarded(ctx, [&]() {
         ctx->begin_call();
-        int r = do_friction_hessian(ctx, epsvh2, mu, true);
+        int r = do_friction_hessian(ctx, epsvh2, mu, HF_DEV);
+        if (nTrip) *nTrip = ctx->nTrip;
+        return r;
+    });
+}
+
+int cipc_friction_hessian_merged(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTrip)
+{
+    (void)projectSPD;
+    return guarded(ctx, [&]() {
+        ctx->begin_call();
+        int r = do_friction_hessian(ctx, epsvh2, mu, HF_BLK);
         if (nTrip) *nTrip = ctx->nTrip;
         return r;
     });

@@ -273,10 +273,10 @@ template <int CLS> struct FrFusedShape {
     static constexpr int NN = 3 * ((CLS == 0) ? 4 : (CLS == 1 ? 3 : 2)), YD = 2 * NN, YS = YD + 1;
     static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
 };
-template <int CLS>
+template <int CLS, bool BLK>
 __global__ void __launch_bounds__(FUSED_BD) k_friction_fused(const double4* __restrict__ X, const double4* __restrict__ Xn,
     const int4* __restrict__ fcs, const double2* __restrict__ fcp, const double* __restrict__ fB, const double* __restrict__ fnf,
-    const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, double epsvh, double epsvh2, double mu, cipc_triplet* __restrict__ trip)
+    const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, double epsvh, double epsvh2, double mu, void* __restrict__ outp)
 {
     constexpr int NN = FrFusedShape<CLS>::NN, YS = FrFusedShape<CLS>::YS;
     extern __shared__ __align__(16) unsigned char fr_fused_sm[];
@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(FUSED_BD) k_friction_fused(const double4* __re
         for (int k = 0; k < 2 * NN; ++k) y[k] = Y[k];
     }
     __syncwarp();
-    warp_expand_stencils<NN, 2, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, trip);
+    if (BLK) warp_expand_blocks<NN / 3, 2, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<double*>(outp)); // upper blocks (merge.cuh)
+    else warp_expand_stencils<NN, 2, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<cipc_triplet*>(outp));
 }
 
 } // namespace cipc

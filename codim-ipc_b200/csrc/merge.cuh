@@ -1,0 +1,182 @@
+// merge.cuh -- device-side merge of the per-stencil Hessian blocks into the unique 3x3 blocks of the (symmetric) contact
+// matrix, upper block triangle only: what Eigen's setFromTriplets (Math/CSR_MATRIX.h:49-56, fed by
+// Shell/INC_POTENTIAL.h:374-382) does with the 144/81/36 triplets of every stencil -- sum the duplicates -- done in HBM
+// before anything crosses PCIe.  At 1M triangles 7.2M stencils emit 61M upper blocks that collapse to 7.3M unique ones:
+// the host receives 0.6 GB instead of 14.5 GB and the solver's assembly sorts 119M triplets instead of 909M.
+//
+// Block stream (written by the fused Hessian kernels in block mode, cipc_b200.cu): stencil i with vertices v_0..v_{nb-1}
+// owns blocks [off[i], off[i] + nb(nb+1)/2), one per local pair I <= J in row-major order, 9 doubles each (row-major 3x3),
+// stored for the ORIENTED vertex pair (min(v_I, v_J), max(v_I, v_J)) -- the block is transposed when v_I > v_J.
+//
+// Merge (no global sort; keys come from the stencil list, the block values are only gathered once at the end):
+//   1. k_blk_count    per stencil: rowCnt[min vertex] += 1 per pair                       (L2-resident atomics)
+//   2. scan           rowCnt -> rowStart
+//   3. k_blk_scatter  per stencil: ent[rowCur[row]++] = (col << 32 | block id)            (8 B per block)
+//   4. k_row_sort     one CTA per 16 rows: bitonic sort of the rows' entries by (row, col, block id) in shared memory
+//                     (global memory when the group is larger than the buffer), head flags of the unique (row, col) runs
+//   5. scan           head flags -> unique index
+//   6. k_blk_uniq     per run head: (row, col, first entry)
+//   7. k_blk_sum      nine threads per unique block: sum of the run in (block id) order -- a reproducible sum
+// Included by cipc_b200.cu after decode() / Stencil are defined.
+#pragma once
+
+namespace cipc {
+
+__device__ __forceinline__ int stencil_nb(const int4 c) { return (c.x >= 0 || c.w >= 0) ? 4 : (c.z >= 0 ? 3 : 2); }
+__host__ __device__ __forceinline__ int upper_pairs(int nb) { return nb * (nb + 1) / 2; }
+
+// blocks per stencil (10 / 6 / 3): scanned into the block offsets
+__global__ void k_blk_sizes(const int4* __restrict__ cs, u32 n, u32* sz)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sz[i] = (u32)upper_pairs(stencil_nb(cs[i]));
+}
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_blk_rows(const int4* __restrict__ cs, const u32* __restrict__ off, u32 n, u32* __restrict__ rowCnt,
+    u64* __restrict__ ent)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Stencil s = decode(cs[i]);
+    const int nb = (s.kind == K_PE) ? 3 : (s.kind == K_PP ? 2 : 4);
+    u32 b = SCATTER ? off[i] : 0u;
+    for (int I = 0; I < nb; ++I)
+        for (int J = I; J < nb; ++J, ++b) {
+            const u32 r = (u32)min(s.v[I], s.v[J]), c = (u32)max(s.v[I], s.v[J]);
+            const u32 pos = atomicAdd(&rowCnt[r], 1u);
+            if (SCATTER) ent[pos] = ((u64)c << 32) | b;
+        }
+}
+// Sorts the entries of MRS_ROWS consecutive rows (contiguous in `ent`) by (row, col, block id).  The comparator network
+// is the all-ascending bitonic variant (first step of every merge mirrors the partner index), so an arbitrary length
+// works with virtual +inf padding: comparators that reach past n are skipped.
+constexpr int MRS_ROWS = 16, MRS_CAP = 4096, MRS_BT = 256;
+__global__ void __launch_bounds__(MRS_BT) k_row_sort(const u32* __restrict__ rowStart, int nV, u64* __restrict__ ent, u32* __restrict__ heads,
+    u32* __restrict__ nRowsUsed)
+{
+    __shared__ u64 sh[MRS_CAP];
+    __shared__ u32 rs[MRS_ROWS + 1];
+    const int r0 = blockIdx.x * MRS_ROWS, r1 = min(r0 + MRS_ROWS, nV);
+    if ((int)threadIdx.x <= r1 - r0) rs[threadIdx.x] = rowStart[r0 + threadIdx.x];
+    __syncthreads();
+    const u32 s0 = rs[0], n = rs[r1 - r0] - s0;
+    if (n == 0) return;
+    if (threadIdx.x == 0) {
+        u32 used = 0;
+        for (int k = 0; k < r1 - r0; ++k) used += rs[k + 1] > rs[k];
+        atomicAdd(nRowsUsed, used);
+    }
+    u64* buf = n <= (u32)MRS_CAP ? sh : ent + s0;
+    for (u32 i = threadIdx.x; i < n; i += MRS_BT) {
+        int lr = 0;
+        while (s0 + i >= rs[lr + 1]) ++lr;
+        buf[i] = ent[s0 + i] | ((u64)lr << 60);
+    }
+    __syncthreads();
+    auto cx = [&](u32 i, u32 p) {
+        if (p > i && p < n) {
+            const u64 a = buf[i], b = buf[p];
+            if (a > b) { buf[i] = b; buf[p] = a; }
+        }
+    };
+    for (u32 k = 2; (k >> 1) < n; k <<= 1) {
+        for (u32 i = threadIdx.x; i < n; i += MRS_BT) cx(i, i ^ (k - 1));
+        __syncthreads();
+        for (u32 j = k >> 2; j > 0; j >>= 1) {
+            for (u32 i = threadIdx.x; i < n; i += MRS_BT) cx(i, i ^ j);
+            __syncthreads();
+        }
+    }
+    for (u32 i = threadIdx.x; i < n; i += MRS_BT)
+        heads[s0 + i] = (i == 0 || (buf[i] >> 32) != (buf[i - 1] >> 32)) ? 1u : 0u; // (row, col) changes
+    __syncthreads(); // buf may alias ent: strip the row tags only after every head flag is formed
+    for (u32 i = threadIdx.x; i < n; i += MRS_BT) ent[s0 + i] = buf[i] & 0x0fffffffffffffffULL;
+}
+__global__ void k_blk_uniq(const u64* __restrict__ ent, const u32* __restrict__ heads, const u32* __restrict__ headScan, u32 n,
+    const u32* __restrict__ rowStart, int nV, u32* __restrict__ urow, u32* __restrict__ ucol, u32* __restrict__ ustart)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !heads[i]) return;
+    const u32 u = headScan[i];
+    int lo = 0, hi = nV; // last row whose start is <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rowStart[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    urow[u] = (u32)lo;
+    ucol[u] = (u32)(ent[i] >> 32);
+    ustart[u] = i;
+}
+__global__ void __launch_bounds__(288) k_blk_sum(const double* __restrict__ blkVal, const u64* __restrict__ ent, const u32* __restrict__ ustart, u32 nU,
+    u32 nEnt, double* __restrict__ uval)
+{
+    const u32 u = blockIdx.x * 32u + threadIdx.x / 9u, k = threadIdx.x % 9u;
+    if (u >= nU) return;
+    const u32 s0 = ustart[u], s1 = (u + 1 < nU) ? ustart[u + 1] : nEnt;
+    double acc = 0.0;
+    for (u32 i = s0; i < s1; ++i) acc += blkVal[(size_t)(u32)ent[i] * 9 + k];
+    uval[(size_t)u * 9 + k] = acc;
+}
+
+// ---- block-mode output of the Hessian kernels
+// pair index b (row-major upper triangle of an NB x NB grid) -> (I, J)
+template <int NB>
+__device__ __forceinline__ void upper_pair_ij(int b, int& I, int& J)
+{
+    I = 0;
+    int rowLen = NB;
+    while (b >= rowLen) { b -= rowLen; --rowLen; ++I; }
+    J = I + b;
+}
+// Block-mode twin of warp_expand_stencils: lane l owns the doubles e = l + 32 j of every stencil's block run
+// (9 nb(nb+1)/2 doubles, contiguous), so a warp writes 256 contiguous bytes per store instruction.
+template <int NB, int NY, int YS>
+__device__ __forceinline__ void warp_expand_blocks(const double* sY, const int* sH, u32 wq0, u32 g, u32 lane, double* __restrict__ blk)
+{
+    constexpr int NN = 3 * NB, PER = 9 * (NB * (NB + 1) / 2), NJ = (PER + 31) / 32;
+    int pI[NJ], pJ[NJ], ra[NJ], rc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int e = (int)lane + 32 * j;
+        const int b = (e < PER ? e : 0) / 9, k = (e < PER ? e : 0) - 9 * b;
+        upper_pair_ij<NB>(b, pI[j], pJ[j]);
+        ra[j] = k / 3; rc[j] = k - 3 * ra[j];
+    }
+    const u32 wn = (wq0 < g) ? min(32u, g - wq0) : 0u;
+    for (u32 qq = 0; qq < wn; ++qq) {
+        const int* h = sH + (wq0 + qq) * 8;
+        const u32 o = (u32)h[0];
+        if (o == 0xffffffffu) continue;
+        const double* y = sY + (wq0 + qq) * YS;
+        const bool neg = h[5] != 0;
+        double* dst = blk + (size_t)o * 9;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int e = (int)lane + 32 * j;
+            if (e < PER) {
+                const bool sw = h[1 + pI[j]] > h[1 + pJ[j]]; // stored for (min vertex, max vertex): transposed when v_I > v_J
+                const int r = 3 * (sw ? pJ[j] : pI[j]) + ra[j], c = 3 * (sw ? pI[j] : pJ[j]) + rc[j];
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
+                __stcs(dst + e, neg ? -v : v);
+            }
+        }
+    }
+}
+// dense n x n block H (row-major, n = 3 nb) of one stencil -> its upper block run (dense path, unprojected path)
+__device__ __forceinline__ void store_blocks_dense(const double* H, int nb, const int* vids, double* __restrict__ dst)
+{
+    const int nn = 3 * nb;
+    int b = 0;
+    for (int I = 0; I < nb; ++I)
+        for (int J = I; J < nb; ++J, ++b) {
+            const bool sw = vids[I] > vids[J];
+            const int R = sw ? J : I, C = sw ? I : J;
+            for (int a = 0; a < 3; ++a)
+                for (int c = 0; c < 3; ++c) dst[b * 9 + a * 3 + c] = H[(3 * R + a) * nn + 3 * C + c];
+        }
+}
+
+} // namespace cipc

@@ -22,6 +22,7 @@
 #ifndef CIPC_B200_H
 #define CIPC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -86,6 +87,15 @@ int cipc_barrier_hessian(cipc_ctx* ctx, int elasticIPC, double dHat2, const doub
  * Projected blocks travel over PCIe as compact factors (288 B instead of 2304 B per PT/EE stencil) and are expanded by
  * the host cores (CIPC_HOST_THREADS, default all); CIPC_TRIPLETS_DMA=1 copies the expanded device stream instead. */
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out);
+/* Compute_Barrier_Hessian delivered as MERGED triplets.  The only consumer of the reference's triplet vector is
+ * sysMtr.Construct_From_Triplet = Eigen setFromTriplets (Shell/INC_POTENTIAL.h:382, Math/CSR_MATRIX.h:49-56), which sums
+ * entries with equal (row, col).  This call performs that sum on the device at 3x3-block granularity (upper block triangle,
+ * mirrored on delivery): nTriplets_out = number of DISTINCT (row, col) entries of the contact matrix (119M instead of 909M
+ * at 1M triangles), and the cipc_get_triplets that follows ships 80 bytes per unique upper block over PCIe.  The matrix
+ * assembled from the merged triplets equals the one assembled from cipc_barrier_hessian's to summation order (1e-9 gate in
+ * tests/test_gpu_merged.py).  Layout of the delivered array: the upper blocks in (row, col) order, then the mirrored blocks. */
+int cipc_barrier_hessian_merged(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness,
+                                int projectSPD, int64_t* nTriplets_out);
 /* the same triplet stream resident in HBM (expanded on the device on first use); NULL on error */
 cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx);
 
@@ -95,7 +105,8 @@ cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx);
 int cipc_step_size(cipc_ctx* ctx, int elasticIPC, double thickness, double* stepSize_inout);
 
 /* ---- Compute_Min_Dist2 ---------------------------------------------------------------------- */
-/* dist2 may be NULL; minDist2 = min_c dist2[c] - thickness^2 */
+/* dist2 may be NULL; minDist2 = min_c dist2[c] - thickness^2.  An empty resident set is a no-op (the reference returns
+ * early and leaves its outputs untouched, IPC.h:2253). */
 int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2);
 
 /* ---- lagged friction: FEM/FRICTION.h, FEM/FRICTION_UTILS.h ------------------------------- */
@@ -122,6 +133,8 @@ int cipc_friction_gradient(cipc_ctx* ctx, double epsvh2, double mu, double* g, i
 /* Compute_Friction_Hessian (FRICTION.h:381-663): 144/81/36 triplets per friction stencil; deliver them with
  * cipc_get_triplets / cipc_dev_triplets exactly like the barrier Hessian's (the caller appends) */
 int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTriplets_out);
+/* Compute_Friction_Hessian delivered as merged triplets (see cipc_barrier_hessian_merged) */
+int cipc_friction_hessian_merged(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTriplets_out);
 /* device-resident variants: energy -> cipc_dev_scalars()[4]; gradient -> cipc_dev_gradient(), added to what is there
  * when accumulate != 0 (e.g. after cipc_barrier_gradient_dev) */
 int cipc_friction_energy_dev(cipc_ctx* ctx, double epsvh2, double mu);
@@ -185,12 +198,16 @@ double cipc_event_elapsed_ms(cipc_ctx* ctx, int slot_a, int slot_b);
 /* ---- introspection ------------------------------------------------------------------------ */
 /* device milliseconds (CUDA events on the library's stream) of the named stage of the last call:
  * "ccs_hash_build","ccs_pairs","ccs_narrow","ccs_merge","barrier_E","barrier_g","barrier_H",
- * "ccd_hash_build","ccd_pairs","ccd_accd","min_dist" ; -1 if unknown */
+ * "ccd_hash_build","ccd_pairs","ccd_accd","min_dist"; per-kind sub-scopes "ccs_narrow_pt","ccs_narrow_ee","ccd_accd_pt",
+ * "ccd_accd_ee" ; -1 if unknown */
 double cipc_stage_ms(cipc_ctx* ctx, const char* stage);
 /* counters of the last call: "candidates_pt","candidates_ee","candidates_pe","candidates_pp",
  * "hash_entries","hash_cells","constraints","ccd_pairs" ; -1 if unknown */
 int64_t cipc_counter(cipc_ctx* ctx, const char* name);
 int64_t cipc_kernel_launches(void);  /* kernels launched by this library since load */
+/* 64-bit content hash of a host array, computed by a few host threads (~50 GB/s): the shim's change detector for the
+ * caller-owned containers (constraint set, friction set) it keeps resident on the device between calls */
+uint64_t cipc_hash_bytes(const void* p, size_t n);
 const char* cipc_version(void);
 
 /* ---- test hooks (device primitives, exercised by tests/) ----------------------------------- */
