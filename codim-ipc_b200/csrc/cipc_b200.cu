@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <immintrin.h>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <algorithm>
 #include <cmath>
@@ -2087,16 +2088,27 @@ void merge_blocks(cipc_ctx* c, const int4* st, u32 nSt, u32 tot)
     const int nV = c->T.nV;
     need(nV < (1 << 28), "block merge: more than 2^28 nodes");
     c->rowStart.reserve((size_t)nV + 1, c->st); c->rowCur.reserve((size_t)nV + 1, c->st);
-    c->ent.reserve((size_t)tot + 1, c->st); c->mHeads.reserve((size_t)tot + 1, c->st); c->mScan.reserve((size_t)tot + 1, c->st);
-    CIPC_CUDA(cudaMemsetAsync(c->rowCur.p, 0, ((size_t)nV + 1) * 4, c->st));
-    CIPC_LAUNCH(k_blk_rows<false>, div_up(nSt, TB), TB, 0, c->st, st, c->tripOff.p, nSt, c->rowCur.p, (u64*)nullptr);
-    device_excl_scan(c->rowCur.p, c->rowStart.p, (size_t)nV + 1, c->scanwk, c->st);
-    CIPC_CUDA(cudaMemcpyAsync(c->rowCur.p, c->rowStart.p, ((size_t)nV + 1) * 4, cudaMemcpyDeviceToDevice, c->st));
-    CIPC_LAUNCH(k_blk_rows<true>, div_up(nSt, TB), TB, 0, c->st, st, c->tripOff.p, nSt, c->rowCur.p, c->ent.p);
+    c->ent.reserve((size_t)tot + 1, c->st);
     u32* nRowsDev = c->counters.p + 7;
-    CIPC_CUDA(cudaMemsetAsync(nRowsDev, 0, 4, c->st));
-    CIPC_LAUNCH(k_row_sort, div_up(nV, MRS_ROWS), MRS_BT, 0, c->st, c->rowStart.p, nV, c->ent.p, c->mHeads.p, nRowsDev);
-    device_excl_scan(c->mHeads.p, c->mScan.p, tot, c->scanwk, c->st);
+    {
+        cipc_ctx::Scope s1(c, "mg_count");
+        CIPC_CUDA(cudaMemsetAsync(c->rowCur.p, 0, ((size_t)nV + 1) * 4, c->st));
+        CIPC_LAUNCH(k_blk_rows<false>, div_up(nSt, TB), TB, 0, c->st, st, c->tripOff.p, nSt, c->rowCur.p, (u64*)nullptr);
+        device_excl_scan(c->rowCur.p, c->rowStart.p, (size_t)nV + 1, c->scanwk, c->st);
+        CIPC_CUDA(cudaMemcpyAsync(c->rowCur.p, c->rowStart.p, ((size_t)nV + 1) * 4, cudaMemcpyDeviceToDevice, c->st));
+    }
+    {
+        cipc_ctx::Scope s1(c, "mg_scatter");
+        CIPC_LAUNCH(k_blk_rows<true>, div_up(nSt, TB), TB, 0, c->st, st, c->tripOff.p, nSt, c->rowCur.p, c->ent.p);
+    }
+    const u32 nGrp = div_up(nV, MRS_ROWS);
+    c->mHeads.reserve((size_t)nGrp + 1, c->st); c->mScan.reserve((size_t)nGrp + 1, c->st);
+    {
+        cipc_ctx::Scope s1(c, "mg_sort");
+        CIPC_CUDA(cudaMemsetAsync(nRowsDev, 0, 4, c->st));
+        CIPC_LAUNCH(k_row_sort, nGrp, MRS_BT, 0, c->st, c->rowStart.p, nV, c->ent.p, c->mHeads.p, nRowsDev);
+        device_excl_scan(c->mHeads.p, c->mScan.p, nGrp, c->scanwk, c->st);
+    }
     u32 h[2];
     CIPC_CUDA(cudaMemcpyAsync(&h[0], c->scanwk.total.p, 4, cudaMemcpyDeviceToHost, c->st));
     CIPC_CUDA(cudaMemcpyAsync(&h[1], nRowsDev, 4, cudaMemcpyDeviceToHost, c->st));
@@ -2104,8 +2116,14 @@ void merge_blocks(cipc_ctx* c, const int4* st, u32 nSt, u32 tot)
     const u32 nU = h[0];
     c->mRow.reserve((size_t)nU + 1, c->st); c->mCol.reserve((size_t)nU + 1, c->st); c->mStart.reserve((size_t)nU + 1, c->st);
     c->mVal.reserve((size_t)nU * 9 + 16, c->st);
-    CIPC_LAUNCH(k_blk_uniq, div_up(tot, TB), TB, 0, c->st, c->ent.p, c->mHeads.p, c->mScan.p, tot, c->rowStart.p, nV, c->mRow.p, c->mCol.p, c->mStart.p);
-    CIPC_LAUNCH(k_blk_sum, div_up(nU, 32), 288, 0, c->st, c->blkVal.p, c->ent.p, c->mStart.p, nU, tot, c->mVal.p);
+    {
+        cipc_ctx::Scope s1(c, "mg_uniq");
+        CIPC_LAUNCH(k_blk_uniq, nGrp, MRS_BT, 0, c->st, c->rowStart.p, nV, c->ent.p, c->mScan.p, c->mRow.p, c->mCol.p, c->mStart.p);
+    }
+    {
+        cipc_ctx::Scope s1(c, "mg_sum");
+        CIPC_LAUNCH(k_blk_sum, div_up(nU, 32), 288, 0, c->st, c->blkVal.p, c->ent.p, c->mStart.p, nU, tot, c->mVal.p);
+    }
     c->nUm = nU;
     c->nDiag = h[1]; // every vertex of a stencil owns a diagonal block, which opens its row
     c->nTrip = (int64_t)9 * ((int64_t)nU + (int64_t)(nU - h[1]));
@@ -2390,6 +2408,8 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
 {
     const size_t nU = c->nUm;
     if (!nU) return;
+    const auto tp0 = std::chrono::steady_clock::now();
+    auto us_since = [&](std::chrono::steady_clock::time_point t) { return (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t).count(); };
     u32* hR = (u32*)c->pinMK.reserve(nU * 8 + 64);
     u32* hC = hR + nU;
     double* hV = (double*)c->pinMV.reserve(nU * 72 + 64);
@@ -2412,6 +2432,7 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
     nt = std::max(1, std::min(nt, 256));
     bool failed = cudaEventSynchronize(keysEv) != cudaSuccess;
     cudaEventDestroy(keysEv);
+    c->ctr["deliver_us_keys"] = us_since(tp0);
     // off-diagonal blocks before each chunk of CH blocks (the mirrored region is indexed by the off-diagonal rank)
     const size_t CH = 4096, nChunks = (nU + CH - 1) / CH; // PIECE is a multiple of CH
     std::vector<size_t> offBefore(nChunks + 1, 0);
@@ -2431,14 +2452,15 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
         for (auto& t : th) t.join();
         for (size_t k = 0; k < nChunks; ++k) offBefore[k + 1] += offBefore[k];
     }
+    c->ctr["deliver_us_count"] = us_since(tp0);
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     std::atomic<size_t> landed(0), next(0);
-    auto put = [&](cipc_triplet* o, unsigned r, unsigned cc, double v) {
-        long long vb;
-        memcpy(&vb, &v, 8);
-        const __m128i t = _mm_set_epi64x(vb, (long long)(((unsigned long long)cc << 32) | r));
-        if (aligned) _mm_stream_si128(reinterpret_cast<__m128i*>(o), t); else _mm_storeu_si128(reinterpret_cast<__m128i*>(o), t);
-    };
+    // entry e = 3 i + j of a block: index qword (col << 32 | row) = base + (j << 32 | i); two entries per 128-bit register.  The
+    // mirrored block's entries are written in the same order with the halves of the index qword swapped (row <-> col).
+    const __m128i o01 = _mm_set_epi64x((1LL << 32) | 0, (0LL << 32) | 0), o23 = _mm_set_epi64x((0LL << 32) | 1, (2LL << 32) | 0),
+                  o45 = _mm_set_epi64x((2LL << 32) | 1, (1LL << 32) | 1), o67 = _mm_set_epi64x((1LL << 32) | 2, (0LL << 32) | 2),
+                  o8 = _mm_set_epi64x(0, (2LL << 32) | 2);
+    auto st = [&](__m128i* o, __m128i t) { if (aligned) _mm_stream_si128(o, t); else _mm_storeu_si128(o, t); };
     auto worker = [&]() {
         for (size_t k; (k = next.fetch_add(1)) < nChunks;) {
             const size_t a = k * CH, b = std::min(nU, a + CH);
@@ -2447,13 +2469,28 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
             for (size_t u = a; u < b; ++u) {
                 const unsigned r3 = 3u * hR[u], c3 = 3u * hC[u];
                 const double* v = hV + u * 9;
-                cipc_triplet* o = out + u * 9;
-                for (int i = 0; i < 3; ++i)
-                    for (int j = 0; j < 3; ++j) put(o + 3 * i + j, r3 + i, c3 + j, v[3 * i + j]);
+                const __m128i base = _mm_set1_epi64x((long long)(((unsigned long long)c3 << 32) | r3));
+                const __m128i i01 = _mm_add_epi64(base, o01), i23 = _mm_add_epi64(base, o23), i45 = _mm_add_epi64(base, o45),
+                              i67 = _mm_add_epi64(base, o67), i8 = _mm_add_epi64(base, o8);
+                const __m128i v01 = _mm_castpd_si128(_mm_loadu_pd(v)), v23 = _mm_castpd_si128(_mm_loadu_pd(v + 2)),
+                              v45 = _mm_castpd_si128(_mm_loadu_pd(v + 4)), v67 = _mm_castpd_si128(_mm_loadu_pd(v + 6)),
+                              v8 = _mm_castpd_si128(_mm_load_sd(v + 8));
+                __m128i* o = reinterpret_cast<__m128i*>(out + u * 9);
+                st(o + 0, _mm_unpacklo_epi64(i01, v01)); st(o + 1, _mm_unpackhi_epi64(i01, v01));
+                st(o + 2, _mm_unpacklo_epi64(i23, v23)); st(o + 3, _mm_unpackhi_epi64(i23, v23));
+                st(o + 4, _mm_unpacklo_epi64(i45, v45)); st(o + 5, _mm_unpackhi_epi64(i45, v45));
+                st(o + 6, _mm_unpacklo_epi64(i67, v67)); st(o + 7, _mm_unpackhi_epi64(i67, v67));
+                st(o + 8, _mm_unpacklo_epi64(i8, v8));
                 if (r3 != c3) {
-                    cipc_triplet* m = out + (nU + off) * 9;
-                    for (int j = 0; j < 3; ++j)
-                        for (int i = 0; i < 3; ++i) put(m + 3 * j + i, c3 + j, r3 + i, v[3 * i + j]);
+                    __m128i* m = reinterpret_cast<__m128i*>(out + (nU + off) * 9);
+                    const __m128i m01 = _mm_shuffle_epi32(i01, _MM_SHUFFLE(2, 3, 0, 1)), m23 = _mm_shuffle_epi32(i23, _MM_SHUFFLE(2, 3, 0, 1)),
+                                  m45 = _mm_shuffle_epi32(i45, _MM_SHUFFLE(2, 3, 0, 1)), m67 = _mm_shuffle_epi32(i67, _MM_SHUFFLE(2, 3, 0, 1)),
+                                  m8 = _mm_shuffle_epi32(i8, _MM_SHUFFLE(2, 3, 0, 1));
+                    st(m + 0, _mm_unpacklo_epi64(m01, v01)); st(m + 1, _mm_unpackhi_epi64(m01, v01));
+                    st(m + 2, _mm_unpacklo_epi64(m23, v23)); st(m + 3, _mm_unpackhi_epi64(m23, v23));
+                    st(m + 4, _mm_unpacklo_epi64(m45, v45)); st(m + 5, _mm_unpackhi_epi64(m45, v45));
+                    st(m + 6, _mm_unpacklo_epi64(m67, v67)); st(m + 7, _mm_unpackhi_epi64(m67, v67));
+                    st(m + 8, _mm_unpacklo_epi64(m8, v8));
                     ++off;
                 }
             }
@@ -2466,8 +2503,10 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
         if (!failed && cudaEventSynchronize(evs[k]) != cudaSuccess) failed = true;
         landed.store(k + 1, std::memory_order_release);
     }
+    c->ctr["deliver_us_copied"] = us_since(tp0);
     worker();
     for (auto& t : th) t.join();
+    c->ctr["deliver_us_total"] = us_since(tp0);
     for (auto e : evs) cudaEventDestroy(e);
     if (failed) throw CudaError("device-to-host copy of the merged Hessian blocks failed");
 }

@@ -12,10 +12,10 @@
 //   1. k_blk_count    per stencil: rowCnt[min vertex] += 1 per pair                       (L2-resident atomics)
 //   2. scan           rowCnt -> rowStart
 //   3. k_blk_scatter  per stencil: ent[rowCur[row]++] = (col << 32 | block id)            (8 B per block)
-//   4. k_row_sort     one CTA per 16 rows: bitonic sort of the rows' entries by (row, col, block id) in shared memory
-//                     (global memory when the group is larger than the buffer), head flags of the unique (row, col) runs
-//   5. scan           head flags -> unique index
-//   6. k_blk_uniq     per run head: (row, col, first entry)
+//   4. k_row_sort     one CTA per 16 rows: every warp sorts whole rows by (col, block id) in shared memory (a CTA-wide sort
+//                     when a row is long; in global memory when the group exceeds the buffer); unique (row, col) runs per group
+//   5. scan           unique runs per group -> first unique index of the group (nV / 16 entries)
+//   6. k_blk_uniq     second pass over the sorted groups: (row, col, first entry) of every run
 //   7. k_blk_sum      nine threads per unique block: sum of the run in (block id) order -- a reproducible sum
 // Included by cipc_b200.cu after decode() / Stencil are defined.
 #pragma once
@@ -47,66 +47,121 @@ __global__ void __launch_bounds__(256) k_blk_rows(const int4* __restrict__ cs, c
             if (SCATTER) ent[pos] = ((u64)c << 32) | b;
         }
 }
-// Sorts the entries of MRS_ROWS consecutive rows (contiguous in `ent`) by (row, col, block id).  The comparator network
-// is the all-ascending bitonic variant (first step of every merge mirrors the partner index), so an arbitrary length
-// works with virtual +inf padding: comparators that reach past n are skipped.
-constexpr int MRS_ROWS = 16, MRS_CAP = 4096, MRS_BT = 256;
-__global__ void __launch_bounds__(MRS_BT) k_row_sort(const u32* __restrict__ rowStart, int nV, u64* __restrict__ ent, u32* __restrict__ heads,
-    u32* __restrict__ nRowsUsed)
+// Sorts the entries of MRS_ROWS consecutive rows (contiguous in `ent`) by (col, block id) inside every row and counts the
+// group's unique (row, col) runs.  The comparator network is the all-ascending bitonic variant (the first step of every
+// merge mirrors the partner index), so an arbitrary length works with virtual +inf padding: comparators that reach past n
+// are skipped.  Fast path (every row of the group has at most MRS_WCAP entries -- a cloth vertex has ~130): each warp sorts
+// whole rows on its own in shared memory, __syncwarp only.  Otherwise the CTA sorts the whole group at once with the row in
+// the key's top bits -- in shared memory up to MRS_CAP entries, in place in global memory beyond.
+constexpr int MRS_ROWS = 16, MRS_CAP = 4096, MRS_BT = 256, MRS_WCAP = MRS_CAP / (MRS_BT / 32);
+template <class Sync>
+__device__ __forceinline__ void bitonic_asc(u64* buf, u32 n, u32 tid, u32 nthr, Sync sync)
 {
-    __shared__ u64 sh[MRS_CAP];
-    __shared__ u32 rs[MRS_ROWS + 1];
-    const int r0 = blockIdx.x * MRS_ROWS, r1 = min(r0 + MRS_ROWS, nV);
-    if ((int)threadIdx.x <= r1 - r0) rs[threadIdx.x] = rowStart[r0 + threadIdx.x];
-    __syncthreads();
-    const u32 s0 = rs[0], n = rs[r1 - r0] - s0;
-    if (n == 0) return;
-    if (threadIdx.x == 0) {
-        u32 used = 0;
-        for (int k = 0; k < r1 - r0; ++k) used += rs[k + 1] > rs[k];
-        atomicAdd(nRowsUsed, used);
-    }
-    u64* buf = n <= (u32)MRS_CAP ? sh : ent + s0;
-    for (u32 i = threadIdx.x; i < n; i += MRS_BT) {
-        int lr = 0;
-        while (s0 + i >= rs[lr + 1]) ++lr;
-        buf[i] = ent[s0 + i] | ((u64)lr << 60);
-    }
-    __syncthreads();
     auto cx = [&](u32 i, u32 p) {
-        if (p > i && p < n) {
+        if (p < n) {
             const u64 a = buf[i], b = buf[p];
             if (a > b) { buf[i] = b; buf[p] = a; }
         }
     };
-    for (u32 k = 2; (k >> 1) < n; k <<= 1) {
-        for (u32 i = threadIdx.x; i < n; i += MRS_BT) cx(i, i ^ (k - 1));
-        __syncthreads();
+    u32 np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const u32 nCmp = np2 >> 1; // comparators per step
+    for (u32 k = 2; k <= np2; k <<= 1) {
+        const u32 hk = k >> 1;
+        for (u32 t = tid; t < nCmp; t += nthr) { // mirror step: i in the lower half of its k-block, partner mirrored
+            const u32 blk = t / hk, pos = t - blk * hk, i = blk * k + pos;
+            if (i < n) cx(i, blk * k + (k - 1 - pos));
+        }
+        sync();
         for (u32 j = k >> 2; j > 0; j >>= 1) {
-            for (u32 i = threadIdx.x; i < n; i += MRS_BT) cx(i, i ^ j);
-            __syncthreads();
+            for (u32 t = tid; t < nCmp; t += nthr) {
+                const u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                if (i < n) cx(i, i | j);
+            }
+            sync();
         }
     }
-    for (u32 i = threadIdx.x; i < n; i += MRS_BT)
-        heads[s0 + i] = (i == 0 || (buf[i] >> 32) != (buf[i - 1] >> 32)) ? 1u : 0u; // (row, col) changes
-    __syncthreads(); // buf may alias ent: strip the row tags only after every head flag is formed
-    for (u32 i = threadIdx.x; i < n; i += MRS_BT) ent[s0 + i] = buf[i] & 0x0fffffffffffffffULL;
 }
-__global__ void k_blk_uniq(const u64* __restrict__ ent, const u32* __restrict__ heads, const u32* __restrict__ headScan, u32 n,
-    const u32* __restrict__ rowStart, int nV, u32* __restrict__ urow, u32* __restrict__ ucol, u32* __restrict__ ustart)
+__global__ void __launch_bounds__(MRS_BT) k_row_sort(const u32* __restrict__ rowStart, int nV, u64* __restrict__ ent, u32* __restrict__ grpUniq,
+    u32* __restrict__ nRowsUsed)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !heads[i]) return;
-    const u32 u = headScan[i];
-    int lo = 0, hi = nV; // last row whose start is <= i
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (rowStart[mid] <= i) lo = mid;
-        else hi = mid;
+    __shared__ u64 sh[MRS_CAP];
+    __shared__ u32 rs[MRS_ROWS + 1];
+    __shared__ u32 wcnt[MRS_BT / 32];
+    const int r0 = blockIdx.x * MRS_ROWS, nr = min(MRS_ROWS, nV - r0);
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if ((int)threadIdx.x <= nr) rs[threadIdx.x] = rowStart[r0 + threadIdx.x];
+    __syncthreads();
+    const u32 s0 = rs[0], n = rs[nr] - s0;
+    if (n == 0) { if (threadIdx.x == 0) grpUniq[blockIdx.x] = 0; return; }
+    u32 maxLen = 0, used = 0;
+    for (int k = 0; k < nr; ++k) { maxLen = max(maxLen, rs[k + 1] - rs[k]); used += rs[k + 1] > rs[k]; }
+    if (threadIdx.x == 0) atomicAdd(nRowsUsed, used);
+    u32 uniq = 0; // per thread, summed below
+    if (maxLen <= (u32)MRS_WCAP) {
+        u64* buf = sh + warp * MRS_WCAP;
+        for (int k = (int)warp; k < nr; k += MRS_BT / 32) {
+            const u32 a = rs[k], m = rs[k + 1] - a;
+            for (u32 i = lane; i < m; i += 32) buf[i] = ent[a + i];
+            __syncwarp();
+            bitonic_asc(buf, m, lane, 32u, [] { __syncwarp(); });
+            for (u32 i = lane; i < m; i += 32) {
+                const u64 e = buf[i];
+                uniq += (i == 0 || (e >> 32) != (buf[i - 1] >> 32)) ? 1u : 0u;
+                ent[a + i] = e;
+            }
+            __syncwarp();
+        }
     }
-    urow[u] = (u32)lo;
-    ucol[u] = (u32)(ent[i] >> 32);
-    ustart[u] = i;
+    else {
+        u64* buf = n <= (u32)MRS_CAP ? sh : ent + s0;
+        for (u32 i = threadIdx.x; i < n; i += MRS_BT) {
+            int lr = 0;
+            while (s0 + i >= rs[lr + 1]) ++lr;
+            buf[i] = ent[s0 + i] | ((u64)lr << 60);
+        }
+        __syncthreads();
+        bitonic_asc(buf, n, threadIdx.x, (u32)MRS_BT, [] { __syncthreads(); });
+        for (u32 i = threadIdx.x; i < n; i += MRS_BT) uniq += (i == 0 || (buf[i] >> 32) != (buf[i - 1] >> 32)) ? 1u : 0u; // (row, col) changes
+        __syncthreads(); // buf may alias ent: strip the row tags only after every comparison with the neighbour is done
+        for (u32 i = threadIdx.x; i < n; i += MRS_BT) ent[s0 + i] = buf[i] & 0x0fffffffffffffffULL;
+    }
+    for (int o = 16; o > 0; o >>= 1) uniq += __shfl_down_sync(0xffffffffu, uniq, o);
+    if (lane == 0) wcnt[warp] = uniq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int w = 0; w < MRS_BT / 32; ++w) t += wcnt[w];
+        grpUniq[blockIdx.x] = t;
+    }
+}
+// second pass over the sorted groups: (row, col, first entry) of every unique run, at grpBase[group] + rank inside the group
+__global__ void __launch_bounds__(MRS_BT) k_blk_uniq(const u32* __restrict__ rowStart, int nV, const u64* __restrict__ ent, const u32* __restrict__ grpBase,
+    u32* __restrict__ urow, u32* __restrict__ ucol, u32* __restrict__ ustart)
+{
+    __shared__ u32 rs[MRS_ROWS + 1];
+    const int r0 = blockIdx.x * MRS_ROWS, nr = min(MRS_ROWS, nV - r0);
+    if ((int)threadIdx.x <= nr) rs[threadIdx.x] = rowStart[r0 + threadIdx.x];
+    __syncthreads();
+    const u32 s0 = rs[0], n = rs[nr] - s0;
+    u32 base = grpBase[blockIdx.x];
+    for (u32 c0 = 0; c0 < n; c0 += MRS_BT) { // uniform trip count: block_excl_scan synchronises
+        const u32 i = c0 + threadIdx.x;
+        u32 head = 0, col = 0;
+        int lr = 0;
+        if (i < n) {
+            while (s0 + i >= rs[lr + 1]) ++lr;
+            col = (u32)(ent[s0 + i] >> 32);
+            head = (s0 + i == rs[lr] || col != (u32)(ent[s0 + i - 1] >> 32)) ? 1u : 0u;
+        }
+        u32 tot;
+        const u32 rank = block_excl_scan<MRS_BT>(head, tot);
+        if (head) {
+            const u32 u = base + rank;
+            urow[u] = (u32)(r0 + lr); ucol[u] = col; ustart[u] = s0 + i;
+        }
+        base += tot;
+    }
 }
 __global__ void __launch_bounds__(288) k_blk_sum(const double* __restrict__ blkVal, const u64* __restrict__ ent, const u32* __restrict__ ustart, u32 nU,
     u32 nEnt, double* __restrict__ uval)

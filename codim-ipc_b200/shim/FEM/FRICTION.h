@@ -9,8 +9,8 @@
 //
 // Reference signatures: FEM/FRICTION.h:16-25, 126-130, 172-180, 254-262, 381-390.
 // The friction set (constraintSet, closestPoint, tanBasis, normalForce) stays resident on the device between the
-// calls of one Newton solve; the containers the caller passes are checked by pointer, size and a strided sample
-// and uploaded again only when they are not the ones this shim filled last.
+// calls of one Newton solve; the containers the caller passes are checked by address, size and a 64-bit hash of their
+// full contents (cipc_hash_bytes) and uploaded again only when they are not the ones this shim filled last.
 #pragma once
 
 #include <FEM/IPC.h> // the contact shim: cipc_shim::State, upload helpers, the C ABI
@@ -35,8 +35,7 @@ struct FrictionState {
     const void* nfPtr = nullptr;
     size_t n = 0;
     bool full = false; // closestPoint / tanBasis are resident too
-    std::vector<double> nfSample;
-    std::vector<int> csSample;
+    uint64_t csHash = 0, nfHash = 0;
 };
 inline FrictionState& fstate()
 {
@@ -47,25 +46,15 @@ inline void remember_friction(const std::vector<VECTOR<int, 4>>& cs, const std::
 {
     FrictionState& f = fstate();
     f.csPtr = cs.data(); f.nfPtr = nf.data(); f.n = cs.size(); f.full = full;
-    f.nfSample.clear(); f.csSample.clear();
-    const size_t step = cs.size() / 257 + 1;
-    for (size_t i = 0; i < cs.size(); i += step) {
-        f.nfSample.push_back(nf[i]);
-        for (int d = 0; d < 4; ++d) f.csSample.push_back(cs[i][d]);
-    }
+    f.csHash = cs.empty() ? 0 : cipc_hash_bytes(cs.data(), cs.size() * sizeof(VECTOR<int, 4>));
+    f.nfHash = nf.empty() ? 0 : cipc_hash_bytes(nf.data(), nf.size() * sizeof(double));
 }
 inline bool friction_resident(const std::vector<VECTOR<int, 4>>& cs, const std::vector<double>& nf, bool needFull)
 {
     const FrictionState& f = fstate();
     if (!(cs.data() == f.csPtr && nf.data() == f.nfPtr && cs.size() == f.n && nf.size() == f.n && (f.full || !needFull))) return false;
-    const size_t step = cs.size() / 257 + 1;
-    size_t k = 0;
-    for (size_t i = 0; i < cs.size(); i += step, ++k) {
-        if (nf[i] != f.nfSample[k]) return false;
-        for (int d = 0; d < 4; ++d)
-            if (cs[i][d] != f.csSample[4 * k + d]) return false;
-    }
-    return true;
+    if (cs.empty()) return true;
+    return cipc_hash_bytes(cs.data(), cs.size() * sizeof(VECTOR<int, 4>)) == f.csHash && cipc_hash_bytes(nf.data(), nf.size() * sizeof(double)) == f.nfHash;
 }
 template <class CP, class TB>
 inline void ensure_friction(State& s, const std::vector<VECTOR<int, 4>>& cs, const std::vector<CP>& closestPoint, const std::vector<TB>& tanBasis,
@@ -194,10 +183,10 @@ void Compute_Friction_Hessian(MESH_NODE<T, dim>& X, MESH_NODE<T, dim>& Xn, const
         cipc_shim::upload_positions(s, Xn, cipc_set_prev_positions, "cipc_set_prev_positions");
         cipc_shim::ensure_friction(s, constraintSet, closestPoint, tanBasis, normalForce);
         int64_t n = 0;
-        cipc_shim::die(s.ctx, cipc_friction_hessian(s.ctx, epsvh2, mu, projectSPD ? 1 : 0, &n), "cipc_friction_hessian");
-        const size_t start = triplets.size(); // the new blocks are APPENDED (FRICTION.h:404-421)
-        triplets.resize(start + (size_t)n);
-        if (n) cipc_shim::die(s.ctx, cipc_get_triplets(s.ctx, reinterpret_cast<cipc_triplet*>(triplets.data() + start)), "cipc_get_triplets");
+        if (s.merged) cipc_shim::die(s.ctx, cipc_friction_hessian_merged(s.ctx, epsvh2, mu, projectSPD ? 1 : 0, &n), "cipc_friction_hessian_merged");
+        else cipc_shim::die(s.ctx, cipc_friction_hessian(s.ctx, epsvh2, mu, projectSPD ? 1 : 0, &n), "cipc_friction_hessian");
+        // the new entries are APPENDED (FRICTION.h:404-421), without the zero-fill of resize()
+        if (n) cipc_shim::die(s.ctx, cipc_get_triplets(s.ctx, reinterpret_cast<cipc_triplet*>(cipc_shim::grow_uninitialized(triplets, (size_t)n))), "cipc_get_triplets");
     }
 }
 

@@ -18,6 +18,17 @@
 //        (those instantiations are outside the scope of the graft).
 //
 // Reference signatures: FEM/IPC.h:19-36, 742-748, 943-948, 1258-1265, 1879-1890, 2246-2249.
+//
+// Environment knobs (read once): CIPC_DEVICE (CUDA ordinal, default 0); CIPC_TRIPLETS = merged (default) | raw.
+//   merged: Compute_Barrier_Hessian / Compute_Friction_Hessian append ONE triplet per distinct (row, col) of their matrix --
+//           the duplicates that the only consumer of the vector, sysMtr.Construct_From_Triplet = Eigen setFromTriplets
+//           (Shell/INC_POTENTIAL.h:382, Math/CSR_MATRIX.h:49-56), would sum anyway are summed on the device (cipc_*_hessian_merged).
+//           The assembled system matrix is the same to summation order (<= 1e-9); 0.6 GB instead of 14.5 GB cross PCIe at 1M
+//           triangles and Eigen sorts 119M instead of 909M triplets.
+//   raw:    the reference's exact 144 / 81 / 36 triplets per stencil, in constraint order (what the parity tests compare).
+// Timer tree: the reference's sub-scopes (Compute_Constraint_Set_Build_Hash / _PT / _EE / _Merge,
+// Compute_Intersection_Free_StepSize_Build_Hash / _PT / _EE; IPC.h:44,148,361,571,1903,1959,2170) are filled from the
+// device-side CUDA-event times of the stages (cipc_stage_ms) under the top-level scope, see add_profiler_scope below.
 #pragma once
 
 #define Compute_Constraint_Set Compute_Constraint_Set_CPU
@@ -36,11 +47,13 @@
 
 #include <cipc_b200.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
+#include <string>
 #include <type_traits>
 #include <vector>
 
@@ -58,10 +71,12 @@ inline void die(cipc_ctx* ctx, int st, const char* where)
 
 struct State {
     cipc_ctx* ctx = nullptr;
-    // identity of the constraint set that is resident on the device (what Compute_Constraint_Set last handed out)
+    bool merged = true; // CIPC_TRIPLETS
+    // identity of the constraint set that is resident on the device (what Compute_Constraint_Set last handed out):
+    // address, size and a 64-bit hash of the whole array (cipc_hash_bytes, threaded: ~2 ms per 100 MB)
     const void* csPtr = nullptr;
     size_t csSize = 0;
-    std::vector<int> csSample;
+    uint64_t csHash = 0;
     std::vector<double> stage3, stage2; // packed staging
     std::vector<int32_t> nnx;
     std::vector<uint8_t> dbc;
@@ -73,8 +88,72 @@ inline State& state()
         const char* dev = getenv("CIPC_DEVICE");
         int st = cipc_create(dev ? atoi(dev) : 0, 0, 1, &s.ctx);
         if (st != CIPC_OK) { printf("cipc_b200: no CUDA device; the contact path has no CPU fallback\n"); exit(-1); }
+        const char* tm = getenv("CIPC_TRIPLETS");
+        s.merged = !(tm && std::string(tm) == "raw");
     }
     return s;
+}
+
+// ---- the reference's timer tree (Utils/PROFILER.h:34-40,70-97): a child scope of the scope that is open right now gets the
+// device time of a stage added.  Builds that replace TIMER_FLAG (tests) define CIPC_SHIM_ADD_SCOPE themselves.
+#ifndef CIPC_SHIM_ADD_SCOPE
+inline void add_profiler_scope(const char* name, double seconds)
+{
+    using namespace TIMER;
+    const auto key = std::make_pair(std::string(name), scope_stack.back());
+    int id;
+    const auto it = name_scope.find(key);
+    if (it != name_scope.end()) id = it->second;
+    else { // same bookkeeping as ScopedTimer's constructor
+        id = (int)scope_name.size();
+        name_scope[key] = id;
+        scope_name.push_back(key);
+        scope_duration.emplace_back(0);
+        global_duration.emplace_back(0);
+        scope_edges.emplace_back();
+        scope_edges[scope_stack.back()].push_back(id);
+    }
+    scope_duration[id] += std::chrono::duration<double>(seconds);
+}
+#define CIPC_SHIM_ADD_SCOPE(name, seconds) ::JGSL::cipc_shim::add_profiler_scope(name, seconds)
+#endif
+inline double stage_s(State& s, const char* name)
+{
+    const double ms = cipc_stage_ms(s.ctx, name);
+    return ms > 0 ? 1e-3 * ms : 0.0;
+}
+// pair enumeration is one launch for all candidate kinds: its time is split by candidate counts between the reference's
+// _PT scope (point queries: PT + codimensional PE / PP) and _EE scope; narrow phase / ACCD are timed per kind
+inline void report_scopes(State& s, const char* base, const char* hash, const char* pairs, const char* kPT, const char* kEE, const char* merge,
+    double nPT, double nEE)
+{
+    const double f = (nPT + nEE) > 0 ? nPT / (nPT + nEE) : 0.5, tp = stage_s(s, pairs);
+    const std::string b(base);
+    CIPC_SHIM_ADD_SCOPE((b + "_Build_Hash").c_str(), stage_s(s, hash));
+    CIPC_SHIM_ADD_SCOPE((b + "_PT").c_str(), tp * f + stage_s(s, kPT));
+    CIPC_SHIM_ADD_SCOPE((b + "_EE").c_str(), tp * (1 - f) + stage_s(s, kEE));
+    if (merge) CIPC_SHIM_ADD_SCOPE((b + "_Merge").c_str(), stage_s(s, merge));
+}
+
+// Appends n records to a vector of trivially-copyable elements WITHOUT value-initialising them and returns the first new
+// slot.  vector::resize would zero-fill the new range on one thread (14.5 GB of raw triplets at 1M triangles) before the
+// delivery overwrites it; here the delivery threads are the first to touch the pages.  libstdc++ and libc++ both lay a
+// vector out as three pointers (begin, end, end of storage); -DCIPC_SHIM_STD_RESIZE selects the portable resize().
+template <class V>
+inline typename V::value_type* grow_uninitialized(V& v, size_t n)
+{
+    typedef typename V::value_type E;
+    const size_t old = v.size();
+#if (defined(__GLIBCXX__) || defined(_LIBCPP_VERSION)) && !defined(CIPC_SHIM_STD_RESIZE)
+    static_assert(std::is_trivially_copyable<E>::value && sizeof(V) == 3 * sizeof(void*), "three-pointer vector of plain records");
+    v.reserve(old + n);
+    struct Raw { E* b; E* e; E* c; };
+    Raw& r = reinterpret_cast<Raw&>(v);
+    r.e += n;
+#else
+    v.resize(old + n);
+#endif
+    return v.data() + old;
 }
 
 // positions: MESH_NODE<T,3> = BASE_STORAGE<VECTOR<T,3>>; element i is 4 contiguous doubles.  When the
@@ -124,30 +203,24 @@ inline void upload_topology(State& s, size_t nV, const std::vector<int>& boundar
             (int)nRod, cd, s.dbc.data(), (int)(s.nnx.size() / 2), s.nnx.data(), nullptr, nullptr, nullptr),
         "cipc_set_topology");
 }
-// the barrier calls receive the constraint set by const reference; skip the upload when it is (by pointer, size
-// and a strided sample) the set Compute_Constraint_Set just produced, which is what every reference call site passes
-inline void ensure_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs, const std::vector<VECTOR<double, 2>>& info)
+// the barrier calls receive the constraint set by const reference; skip the upload when it is (by address, size and the hash
+// of its full contents) the set Compute_Constraint_Set just produced, which is what every reference call site passes
+inline bool constraints_resident(State& s, const std::vector<VECTOR<int, 4>>& cs)
 {
-    bool same = (cs.data() == s.csPtr && cs.size() == s.csSize);
-    if (same) {
-        const size_t step = cs.size() / 257 + 1;
-        size_t k = 0;
-        for (size_t i = 0; i < cs.size() && same; i += step, ++k)
-            for (int d = 0; d < 4; ++d) same = same && (cs[i][d] == s.csSample[4 * k + d]);
-    }
-    if (same) return;
-    s.stage2.resize(2 * cs.size());
-    for (size_t i = 0; i < cs.size(); ++i) { s.stage2[2 * i] = info[i][0]; s.stage2[2 * i + 1] = info[i][1]; }
-    die(s.ctx, cipc_set_constraints(s.ctx, cs.empty() ? nullptr : cs[0].data, s.stage2.data(), (int)cs.size()), "cipc_set_constraints");
-    s.csPtr = nullptr;
+    return cs.data() == s.csPtr && cs.size() == s.csSize && (cs.empty() || cipc_hash_bytes(cs.data(), cs.size() * sizeof(VECTOR<int, 4>)) == s.csHash);
 }
 inline void remember_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs)
 {
     s.csPtr = cs.data(); s.csSize = cs.size();
-    s.csSample.clear();
-    const size_t step = cs.size() / 257 + 1;
-    for (size_t i = 0; i < cs.size(); i += step)
-        for (int d = 0; d < 4; ++d) s.csSample.push_back(cs[i][d]);
+    s.csHash = cs.empty() ? 0 : cipc_hash_bytes(cs.data(), cs.size() * sizeof(VECTOR<int, 4>));
+}
+inline void ensure_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs, const std::vector<VECTOR<double, 2>>& info)
+{
+    if (constraints_resident(s, cs)) return;
+    s.stage2.resize(2 * cs.size());
+    for (size_t i = 0; i < cs.size(); ++i) { s.stage2[2 * i] = info[i][0]; s.stage2[2 * i + 1] = info[i][1]; }
+    die(s.ctx, cipc_set_constraints(s.ctx, cs.empty() ? nullptr : cs[0].data, s.stage2.data(), (int)cs.size()), "cipc_set_constraints");
+    remember_constraints(s, cs); // the caller's set is the resident one now
 }
 
 template <class T, int dim, bool shell, bool elasticIPC>
@@ -187,6 +260,9 @@ void Compute_Constraint_Set(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeAt
         cipc_shim::die(s.ctx, cipc_get_constraints(s.ctx, n ? constraintSet[0].data : nullptr, s.stage2.data()), "cipc_get_constraints");
         for (int i = 0; i < n; ++i) { stencilInfo[i][0] = s.stage2[2 * i]; stencilInfo[i][1] = s.stage2[2 * i + 1]; }
         cipc_shim::remember_constraints(s, constraintSet);
+        cipc_shim::report_scopes(s, "Compute_Constraint_Set", "ccs_hash_build", "ccs_pairs", "ccs_narrow_pt", "ccs_narrow_ee", "ccs_merge",
+            (double)(cipc_counter(s.ctx, "candidates_pt") + cipc_counter(s.ctx, "candidates_pe") + cipc_counter(s.ctx, "candidates_pp")),
+            (double)cipc_counter(s.ctx, "candidates_ee"));
     }
 }
 
@@ -245,10 +321,10 @@ void Compute_Barrier_Hessian(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeA
         cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
         cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
         int64_t n = 0;
-        cipc_shim::die(s.ctx, cipc_barrier_hessian(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian");
-        const size_t start = triplets.size(); // the new blocks are APPENDED (IPC.h:1371,1388)
-        triplets.resize(start + (size_t)n);
-        if (n) cipc_shim::die(s.ctx, cipc_get_triplets(s.ctx, reinterpret_cast<cipc_triplet*>(triplets.data() + start)), "cipc_get_triplets");
+        if (s.merged) cipc_shim::die(s.ctx, cipc_barrier_hessian_merged(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian_merged");
+        else cipc_shim::die(s.ctx, cipc_barrier_hessian(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian");
+        // the new entries are APPENDED (IPC.h:1371,1388), without the zero-fill of resize()
+        if (n) cipc_shim::die(s.ctx, cipc_get_triplets(s.ctx, reinterpret_cast<cipc_triplet*>(cipc_shim::grow_uninitialized(triplets, (size_t)n))), "cipc_get_triplets");
     }
 }
 
@@ -270,6 +346,8 @@ void Compute_Intersection_Free_StepSize(MESH_NODE<T, dim>& X, const std::vector<
         cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
         cipc_shim::die(s.ctx, cipc_set_search_dir(s.ctx, searchDir.data()), "cipc_set_search_dir");
         cipc_shim::die(s.ctx, cipc_step_size(s.ctx, 0, thickness, &stepSize), "cipc_step_size");
+        const double nAll = (double)cipc_counter(s.ctx, "ccd_pairs"), nEE = (double)cipc_counter(s.ctx, "ccd_pairs_ee");
+        cipc_shim::report_scopes(s, "Compute_Intersection_Free_StepSize", "ccd_hash_build", "ccd_pairs", "ccd_accd_pt", "ccd_accd_ee", nullptr, nAll - nEE, nEE);
     }
 }
 
@@ -283,13 +361,13 @@ void Compute_Min_Dist2(MESH_NODE<T, dim>& X, const std::vector<VECTOR<int, dim +
     }
     else {
         TIMER_FLAG("Compute_Min_Dist");
+        if (constraintSet.empty()) return; // IPC.h:2253: dist2 and minDist2 stay untouched
         cipc_shim::State& s = cipc_shim::state();
         cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
-        if (!(constraintSet.data() == s.csPtr && constraintSet.size() == s.csSize)) {
-            s.stage2.assign(2 * constraintSet.size(), 1.0);
-            cipc_shim::die(s.ctx, cipc_set_constraints(s.ctx, constraintSet.empty() ? nullptr : constraintSet[0].data, s.stage2.data(),
-                               (int)constraintSet.size()), "cipc_set_constraints");
-            s.csPtr = nullptr;
+        if (!cipc_shim::constraints_resident(s, constraintSet)) {
+            s.stage2.assign(2 * constraintSet.size(), 1.0); // stencilInfo is not an argument here and not read by the distance pass
+            cipc_shim::die(s.ctx, cipc_set_constraints(s.ctx, constraintSet[0].data, s.stage2.data(), (int)constraintSet.size()), "cipc_set_constraints");
+            s.csPtr = nullptr; // the resident weights are placeholders: the next barrier call uploads its own
         }
         dist2.resize(constraintSet.size());
         cipc_shim::die(s.ctx, cipc_min_dist2(s.ctx, thickness, dist2.data(), &minDist2), "cipc_min_dist2");

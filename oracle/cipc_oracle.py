@@ -289,6 +289,15 @@ class RefScene(OracleScene):
     def release_triplets(self):
         self._lib().ref_triplets_release()
 
+    def contact_stage(self, sc):
+        """one contact stage in the reference's own call pattern (ref_drivers.cpp ref_contact_stage): -> (times dict [s], results dict)"""
+        tm = np.zeros(7); res = np.zeros(6)
+        k = np.ascontiguousarray(sc["kappa"], np.float64); p = np.ascontiguousarray(sc["p"], np.float64)
+        self._lib().ref_contact_stage(self.h, C.c_double(sc["dHat2"]), _dp(k), C.c_double(sc["xi"]), _dp(p), _dp(tm), _dp(res))
+        names = ("Compute_Constraint_Set", "Compute_Barrier", "Compute_Barrier_Gradient", "Compute_Barrier_Hessian",
+                 "Compute_Intersection_Free_StepSize", "Compute_Min_Dist2_a", "Compute_Min_Dist2_b")
+        return dict(zip(names, tm.tolist())), dict(E=res[0], step=res[1], minDist2=res[2], nC=int(res[3]), nTriplets=int(res[4]), tripletSum=res[5])
+
     def timer_reset(self):
         self._lib().ref_timer_reset()
 

@@ -54,10 +54,15 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("tests/", ""), f
 
 
-def test_shim_headers_compile_with_reference_signatures():
-    """the drop-in shims (codim-ipc_b200/shim/FEM/IPC.h, FRICTION.h) compile against stand-ins of the reference's
-    container types when driven with the reference's call signatures (no GPU needed: syntax / overload check only)"""
+def test_shim_headers_compile_against_the_reference_headers():
+    """the drop-in shims (codim-ipc_b200/shim/FEM/IPC.h, FRICTION.h) compile against the reference's REAL Storage / VECTOR /
+    FEM headers when driven with the reference's call signatures (tests/shim_harness/shim_drivers.cpp: all six contact and
+    five friction templates, GPU and *_CPU variants side by side).  Syntax / overload check only, no GPU needed; skipped where
+    the reference tree is absent (the GPU box)."""
     import subprocess
-    for src in ("main.cpp", "friction_main.cpp"):
-        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "codim-ipc_b200", "shim"), "-I", os.path.join(ROOT, "include"),
-                               "-I", os.path.join(ROOT, "tests", "shim_harness", "stub"), os.path.join(ROOT, "tests", "shim_harness", src)])
+    import pytest
+    if not os.path.isdir("/root/reference/Library/FEM"):
+        pytest.skip("reference tree absent")
+    subprocess.check_call(["g++", "-std=c++17", "-fopenmp", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "codim-ipc_b200", "shim"),
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "ref_build", "stub"), "-I", "/root/reference/Library",
+                           os.path.join(ROOT, "tests", "shim_harness", "shim_drivers.cpp")])

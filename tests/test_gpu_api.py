@@ -150,8 +150,9 @@ def test_empty_constraint_set_through_every_stage(ctx):
     assert len(ctx.friction_hessian(1e-10, 0.4, True)) == 0
     a = ctx.step_size(sc["xi"], 1.0)
     assert 0.0 < a <= 1.0
-    with pytest.raises(Exception):  # the reference dereferences min_element of an empty vector; the C ABI reports it
-        ctx.min_dist2(sc["xi"])
+    d, m = ctx.min_dist2(sc["xi"])  # the reference returns early on an empty set and leaves its outputs untouched (IPC.h:2253)
+    assert len(d) == 0 and m == 0.0
+    assert len(ctx.barrier_hessian_merged(sc["dHat2"], sc["kappa"], sc["xi"], True)) == 0
 
 
 def test_fused_gradient_hessian_equals_separate_calls(ctx):
