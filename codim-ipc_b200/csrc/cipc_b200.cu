@@ -15,6 +15,7 @@
 #include "eig.cuh"
 #include "hess.cuh"
 #include "prims.cuh"
+#include "hostpool.h"
 
 #include <cooperative_groups.h>
 #include <immintrin.h>
@@ -1561,6 +1562,7 @@ struct cipc_ctx {
     // state
     DevBuf<double4> X, X0, P, Xprev;
     bool haveX = false, haveX0 = false, haveP = false, haveXprev = false;
+    u64 tagX = 0, tagX0 = 0, tagP = 0, tagXn = 0; // content tags of the resident uploads (upload_vec3); 0 = unknown
     u64 xVersion = 1, edgeLenVersion = 0; // bumped whenever the resident positions or the topology change
     double edgeLenCached = 0.0;
     bool edgeLenPending = false;
@@ -1618,6 +1620,9 @@ struct cipc_ctx {
     u32 nBlkLast = 0, nUm = 0, nDiag = 0;
     bool mergedValid = false;
     PinnedBuf pinMK, pinMV;
+    StageRing ring;              // staging for transfers from / to pageable host memory (hostpool.h)
+    bool infoUniform = false;    // stencilInfo of the resident set is (infoW, infoD) for every constraint (non-elastic sets)
+    double infoW = 1.0, infoD = 0.0;
     // lagged friction (FEM/FRICTION.h): the friction set lives on the device between calls
     DevBuf<double4> Xn;
     bool haveXn = false;
@@ -1680,24 +1685,25 @@ int guarded(cipc_ctx* ctx, F f)
     }
 }
 
-// change detector for the topology arrays: four independent multiply-xorshift lanes over 32-byte strides
-// (memory-bandwidth bound, ~10 GB/s per core); not a cryptographic hash
-u64 fnv(const void* p, size_t n, u64 h)
+// change detector for host arrays (not a cryptographic hash): a Fletcher-style pair of running sums on four 64-bit lanes
+// over 32-byte strides (a += w; b += a -- position dependent, two vector adds per 32 bytes: memory-bandwidth bound),
+// folded through a multiply-xorshift mix
+__attribute__((target("avx2"))) u64 fnv(const void* p, size_t n, u64 h)
 {
     const unsigned char* c = (const unsigned char*)p;
-    u64 a = h ^ 0x9E3779B97F4A7C15ULL, b = h + 0xC2B2AE3D27D4EB4FULL, d = ~h, e = h * 0x100000001b3ULL;
+    __m256i a0 = _mm256_set1_epi64x((long long)(h ^ 0x9E3779B97F4A7C15ULL)), b0 = _mm256_setzero_si256();
+    __m256i a1 = _mm256_set1_epi64x((long long)(h + 0xC2B2AE3D27D4EB4FULL)), b1 = _mm256_setzero_si256();
     size_t i = 0;
-    for (; i + 32 <= n; i += 32) {
-        u64 w[4];
-        memcpy(w, c + i, 32);
-        a = (a ^ w[0]) * 0x100000001b3ULL; a ^= a >> 29;
-        b = (b ^ w[1]) * 0x9FB21C651E98DF25ULL; b ^= b >> 31;
-        d = (d ^ w[2]) * 0xD6E8FEB86659FD93ULL; d ^= d >> 32;
-        e = (e ^ w[3]) * 0xFF51AFD7ED558CCDULL; e ^= e >> 33;
+    for (; i + 64 <= n; i += 64) {
+        a0 = _mm256_add_epi64(a0, _mm256_loadu_si256((const __m256i*)(c + i))); b0 = _mm256_add_epi64(b0, a0);
+        a1 = _mm256_add_epi64(a1, _mm256_loadu_si256((const __m256i*)(c + i + 32))); b1 = _mm256_add_epi64(b1, a1);
     }
-    h = a ^ (b * 3) ^ (d * 5) ^ (e * 7);
+    u64 l[16];
+    _mm256_storeu_si256((__m256i*)l, a0); _mm256_storeu_si256((__m256i*)(l + 4), b0);
+    _mm256_storeu_si256((__m256i*)(l + 8), a1); _mm256_storeu_si256((__m256i*)(l + 12), b1);
+    for (int k = 0; k < 16; ++k) { h = (h ^ l[k]) * 0x9FB21C651E98DF25ULL; h ^= h >> 29; }
     for (; i < n; ++i) h = (h ^ c[i]) * 0x100000001b3ULL;
-    return h ^ (h >> 29) ^ (u64)n;
+    return h ^ (h >> 32) ^ (u64)n;
 }
 
 // change detector for large host arrays (topology lists, the caller's constraint set): hashed in 1 MiB pieces by a few
@@ -1710,31 +1716,35 @@ u64 hash_segments(const HashSeg* segs, int nSeg, u64 h)
     for (int k = 0; k < nSeg; ++k)
         for (size_t o = 0; o < segs[k].n; o += PIECE) pieces.push_back({segs[k].p + o, std::min(PIECE, segs[k].n - o)});
     std::vector<u64> ph(pieces.size());
-    const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, pieces.size() / 4));
-    std::atomic<size_t> next(0);
-    auto work = [&]() {
-        for (size_t k; (k = next.fetch_add(1)) < pieces.size();) ph[k] = fnv(pieces[k].p, pieces[k].n, 0x9E3779B97F4A7C15ULL + k);
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
+    if (pieces.size() < 8) for (size_t k = 0; k < pieces.size(); ++k) ph[k] = fnv(pieces[k].p, pieces[k].n, 0x9E3779B97F4A7C15ULL + k);
+    else HostPool::get().for_each(pieces.size(), [&](size_t k) { ph[k] = fnv(pieces[k].p, pieces[k].n, 0x9E3779B97F4A7C15ULL + k); });
     return fnv(ph.data(), ph.size() * sizeof(u64), h);
 }
 
-void upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int stride_bytes)
+// Uploads nV x (x, y, z) records.  `tag` remembers (content hash, stride) of what is resident in `dst`: the contact stage
+// passes the same X to up to eight consecutive calls (Shell/IMPLICIT_EULER.h:418-600), hashing 16 MB costs a fifth of
+// moving it.  Returns true when the device copy changed.
+bool upload_vec3(cipc_ctx* c, DevBuf<double4>& dst, const double* src, int stride_bytes, u64* tag)
 {
     const int n = c->T.nV;
+    if (stride_bytes != 32 && stride_bytes != 24) throw std::runtime_error("stride_bytes must be 24 or 32");
+    u64 hsh = 0;
+    if (tag) {
+        const HashSeg sg{(const unsigned char*)src, (size_t)n * stride_bytes};
+        hsh = hash_segments(&sg, 1, 0x51ED270B0000ULL + (u64)stride_bytes) | 1ULL;
+        if (hsh == *tag && dst.cap >= (size_t)n) return false;
+    }
     dst.reserve(n, c->st);
     if (stride_bytes == 32) {
-        CIPC_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)n * 32, cudaMemcpyHostToDevice, c->st));
+        staged_h2d(c->ring, c->st, dst.p, src, (size_t)n * 32);
     }
-    else if (stride_bytes == 24) {
+    else {
         c->stageD.reserve((size_t)3 * n, c->st);
-        CIPC_CUDA(cudaMemcpyAsync(c->stageD.p, src, (size_t)n * 24, cudaMemcpyHostToDevice, c->st));
+        staged_h2d(c->ring, c->st, c->stageD.p, src, (size_t)n * 24);
         CIPC_LAUNCH(k_expand3, div_up(n, TB), TB, 0, c->st, c->stageD.p, dst.p, n);
     }
-    else throw std::runtime_error("stride_bytes must be 24 or 32");
+    if (tag) *tag = hsh;
+    return true;
 }
 
 // ---- spatial hash (shared by the constraint-set and the step-size passes)
@@ -2349,9 +2359,7 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const double* y0 = hY; const double* y1 = y0 + (size_t)nk[0] * yd0; const double* y2 = y1 + (size_t)nk[1] * yd1;
     const YHdr* g0 = hH; const YHdr* g1 = g0 + nk[0]; const YHdr* g2 = g1 + nk[1];
-    int nt = (int)std::thread::hardware_concurrency();
-    if (const char* e = getenv("CIPC_HOST_THREADS")) nt = atoi(e);
-    nt = std::max(1, std::min(nt, 256));
+    advise_huge(out, (size_t)c->nTrip * sizeof(cipc_triplet));
     const size_t CH = 2048; // stencils per work item
     const size_t items0 = (nk[0] + CH - 1) / CH, items1 = (nk[1] + CH - 1) / CH, items2 = (nk[2] + CH - 1) / CH;
     std::atomic<size_t> next(0);
@@ -2382,16 +2390,17 @@ void deliver_triplets_host(cipc_ctx* c, cipc_triplet* out)
         }
         _mm_sfence();
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(worker);
     bool copyFailed = false;
-    for (size_t k = 0; k < evs.size(); ++k) { // this thread publishes the pieces as they land, then joins the work
-        if (cudaEventSynchronize(evs[k]) != cudaSuccess) copyFailed = true;
-        landed.store(copyFailed ? yD : evEnd[k], std::memory_order_release);
-    }
-    landed.store(yD, std::memory_order_release);
-    worker();
-    for (auto& t : th) t.join();
+    HostPool::get().run([&](int tid) {
+        if (tid == 0) { // the calling thread publishes the pieces as they land, then joins the work
+            for (size_t k = 0; k < evs.size(); ++k) {
+                if (cudaEventSynchronize(evs[k]) != cudaSuccess) copyFailed = true;
+                landed.store(copyFailed ? yD : evEnd[k], std::memory_order_release);
+            }
+            landed.store(yD, std::memory_order_release);
+        }
+        worker();
+    });
     for (auto e : evs) cudaEventDestroy(e);
     if (copyFailed) throw CudaError("device-to-host copy of the Hessian factors failed");
     if (nDense) {
@@ -2427,31 +2436,20 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
         CIPC_CUDA(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
         CIPC_CUDA(cudaEventRecord(evs[k], c->st));
     }
-    int nt = (int)std::thread::hardware_concurrency();
-    if (const char* e = getenv("CIPC_HOST_THREADS")) nt = atoi(e);
-    nt = std::max(1, std::min(nt, 256));
+    advise_huge(out, (size_t)c->nTrip * sizeof(cipc_triplet));
     bool failed = cudaEventSynchronize(keysEv) != cudaSuccess;
     cudaEventDestroy(keysEv);
     c->ctr["deliver_us_keys"] = us_since(tp0);
     // off-diagonal blocks before each chunk of CH blocks (the mirrored region is indexed by the off-diagonal rank)
     const size_t CH = 4096, nChunks = (nU + CH - 1) / CH; // PIECE is a multiple of CH
     std::vector<size_t> offBefore(nChunks + 1, 0);
-    {
-        std::atomic<size_t> next(0);
-        auto cnt = [&]() {
-            for (size_t k; (k = next.fetch_add(1)) < nChunks;) {
-                const size_t a = k * CH, b = std::min(nU, a + CH);
-                size_t n = 0;
-                for (size_t u = a; u < b; ++u) n += hR[u] != hC[u];
-                offBefore[k + 1] = n;
-            }
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < std::min<int>(nt, 8); ++t) th.emplace_back(cnt);
-        cnt();
-        for (auto& t : th) t.join();
-        for (size_t k = 0; k < nChunks; ++k) offBefore[k + 1] += offBefore[k];
-    }
+    HostPool::get().for_each(nChunks, [&](size_t k) {
+        const size_t a = k * CH, b = std::min(nU, a + CH);
+        size_t n = 0;
+        for (size_t u = a; u < b; ++u) n += hR[u] != hC[u];
+        offBefore[k + 1] = n;
+    });
+    for (size_t k = 0; k < nChunks; ++k) offBefore[k + 1] += offBefore[k];
     c->ctr["deliver_us_count"] = us_since(tp0);
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     std::atomic<size_t> landed(0), next(0);
@@ -2497,15 +2495,16 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
         }
         _mm_sfence();
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(worker);
-    for (size_t k = 0; k < nPieces; ++k) { // this thread publishes the pieces as they land, then joins the work
-        if (!failed && cudaEventSynchronize(evs[k]) != cudaSuccess) failed = true;
-        landed.store(k + 1, std::memory_order_release);
-    }
-    c->ctr["deliver_us_copied"] = us_since(tp0);
-    worker();
-    for (auto& t : th) t.join();
+    HostPool::get().run([&](int tid) {
+        if (tid == 0) { // the calling thread publishes the pieces as they land, then joins the work
+            for (size_t k = 0; k < nPieces; ++k) {
+                if (!failed && cudaEventSynchronize(evs[k]) != cudaSuccess) failed = true;
+                landed.store(k + 1, std::memory_order_release);
+            }
+            c->ctr["deliver_us_copied"] = us_since(tp0);
+        }
+        worker();
+    });
     c->ctr["deliver_us_total"] = us_since(tp0);
     for (auto e : evs) cudaEventDestroy(e);
     if (failed) throw CudaError("device-to-host copy of the merged Hessian blocks failed");
@@ -2515,6 +2514,15 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
 extern "C" {
 
 const char* cipc_version(void) { return "cipc_b200 0.2 (sm_100a)"; }
+int cipc_host_parallel_for(size_t n, size_t grain, cipc_range_fn fn, void* user)
+{
+    if (!fn) return CIPC_ERR_ARG;
+    if (grain == 0) grain = 1;
+    const size_t items = (n + grain - 1) / grain;
+    if (items <= 1) { if (n) fn(0, n, user); return CIPC_OK; }
+    HostPool::get().for_each(items, [&](size_t k) { fn(k * grain, std::min(n, (k + 1) * grain), user); });
+    return CIPC_OK;
+}
 uint64_t cipc_hash_bytes(const void* p, size_t n)
 {
     const HashSeg sg{(const unsigned char*)p, n};
@@ -2674,6 +2682,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         T.BN = c->BN.p; T.BE = c->BE.p; T.BT = c->BT.p; T.flags = c->flags.p; T.v2sv = c->v2sv.p; T.nnx = c->nnx.p; T.nNnx = nNnx;
         c->topoHash = h;
         c->haveX = c->haveX0 = c->haveP = c->haveXn = c->haveXprev = false;
+        c->tagX = c->tagX0 = c->tagP = c->tagXn = 0;
         ++c->xVersion;
         c->nC = 0;
         c->nF = 0;
@@ -2684,9 +2693,8 @@ int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes)
 {
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
-        upload_vec3(ctx, ctx->X, X, stride_bytes);
+        if (upload_vec3(ctx, ctx->X, X, stride_bytes, &ctx->tagX)) ++ctx->xVersion;
         ctx->haveX = true;
-        ++ctx->xVersion;
         return (int)CIPC_OK;
     });
 }
@@ -2694,9 +2702,10 @@ int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes)
 {
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
-        upload_vec3(ctx, ctx->X0, X0, stride_bytes);
-        ctx->restLen2.reserve(std::max(ctx->T.nBE, 1), ctx->st);
-        if (ctx->T.nBE) CIPC_LAUNCH(k_rest_len2, div_up(ctx->T.nBE, TB), TB, 0, ctx->st, ctx->X0.p, ctx->BE.p, ctx->T.nBE, ctx->restLen2.p);
+        if (upload_vec3(ctx, ctx->X0, X0, stride_bytes, &ctx->tagX0) || !ctx->haveX0) {
+            ctx->restLen2.reserve(std::max(ctx->T.nBE, 1), ctx->st);
+            if (ctx->T.nBE) CIPC_LAUNCH(k_rest_len2, div_up(ctx->T.nBE, TB), TB, 0, ctx->st, ctx->X0.p, ctx->BE.p, ctx->T.nBE, ctx->restLen2.p);
+        }
         ctx->haveX0 = true;
         return (int)CIPC_OK;
     });
@@ -2705,7 +2714,7 @@ int cipc_set_search_dir(cipc_ctx* ctx, const double* p)
 {
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
-        upload_vec3(ctx, ctx->P, p, 24);
+        upload_vec3(ctx, ctx->P, p, 24, &ctx->tagP);
         ctx->haveP = true;
         return (int)CIPC_OK;
     });
@@ -2793,6 +2802,7 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             }
             c->info.reserve((size_t)nC + 1, c->st);
             if (nC) CIPC_LAUNCH(k_fill_info, div_up(nC, TB), TB, 0, c->st, c->info.p, nC, 1.0, dHat2o);
+            c->infoUniform = true; c->infoW = 1.0; c->infoD = dHat2o;
         }
         c->nC = nC;
         c->ctr["constraints"] = nC;
@@ -2800,31 +2810,71 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
         return (int)CIPC_OK;
     });
 }
-int cipc_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info)
+int cipc_get_constraints_strided(cipc_ctx* ctx, int32_t* cs, double* info, int info_stride_bytes)
 {
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
+        if (info && (info_stride_bytes < 16 || info_stride_bytes % 8)) return (int)CIPC_ERR_ARG;
         if (c->nC == 0) return (int)CIPC_OK;
-        if (cs) CIPC_CUDA(cudaMemcpyAsync(cs, c->cs.p, (size_t)c->nC * 16, cudaMemcpyDeviceToHost, c->st));
-        if (info) CIPC_CUDA(cudaMemcpyAsync(info, c->info.p, (size_t)c->nC * 16, cudaMemcpyDeviceToHost, c->st));
-        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        const size_t n = c->nC;
+        if (cs) staged_d2h(c->ring, c->st, cs, c->cs.p, n * 16);
+        if (info) {
+            const size_t sd = (size_t)info_stride_bytes / 8;
+            const size_t CH = 1 << 15;
+            if (c->infoUniform) { // (w, dHat2) is the same for every constraint of a non-elastic set: nothing crosses PCIe
+                const double w = c->infoW, d = c->infoD;
+                HostPool::get().for_each((n + CH - 1) / CH, [&](size_t k) {
+                    if (sd == 4 && ((uintptr_t)info & 15) == 0) { // the reference's VECTOR<T,2>: T data[4], the unused half zero like its constructor leaves it
+                        const __m128d lo = _mm_set_pd(d, w), z = _mm_setzero_pd();
+                        for (size_t i = k * CH, e = std::min(n, i + CH); i < e; ++i) { _mm_stream_pd(info + 4 * i, lo); _mm_stream_pd(info + 4 * i + 2, z); }
+                        _mm_sfence();
+                    }
+                    else if (sd == 4)
+                        for (size_t i = k * CH, e = std::min(n, i + CH); i < e; ++i) { info[4 * i] = w; info[4 * i + 1] = d; info[4 * i + 2] = 0; info[4 * i + 3] = 0; }
+                    else
+                        for (size_t i = k * CH, e = std::min(n, i + CH); i < e; ++i) { info[i * sd] = w; info[i * sd + 1] = d; }
+                });
+            }
+            else if (sd == 2) staged_d2h(c->ring, c->st, info, c->info.p, n * 16);
+            else {
+                const double* h = (const double*)c->pin.reserve(n * 16);
+                CIPC_CUDA(cudaMemcpyAsync((void*)h, c->info.p, n * 16, cudaMemcpyDeviceToHost, c->st));
+                CIPC_CUDA(cudaStreamSynchronize(c->st));
+                HostPool::get().for_each((n + CH - 1) / CH, [&](size_t k) {
+                    for (size_t i = k * CH, e = std::min(n, i + CH); i < e; ++i) { info[i * sd] = h[2 * i]; info[i * sd + 1] = h[2 * i + 1]; }
+                });
+            }
+        }
         return (int)CIPC_OK;
     });
 }
-int cipc_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int nC)
+int cipc_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info) { return cipc_get_constraints_strided(ctx, cs, info, 16); }
+int cipc_set_constraints_strided(cipc_ctx* ctx, const int32_t* cs, const double* info, int info_stride_bytes, int nC)
 {
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
-        if (nC < 0) return (int)CIPC_ERR_ARG;
-        c->cs.reserve((size_t)nC + 1, c->st); c->info.reserve((size_t)nC + 1, c->st);
-        if (nC) {
-            CIPC_CUDA(cudaMemcpyAsync(c->cs.p, cs, (size_t)nC * 16, cudaMemcpyHostToDevice, c->st));
-            CIPC_CUDA(cudaMemcpyAsync(c->info.p, info, (size_t)nC * 16, cudaMemcpyHostToDevice, c->st));
+        if (nC < 0 || info_stride_bytes < 16 || info_stride_bytes % 8) return (int)CIPC_ERR_ARG;
+        const size_t n = (size_t)nC;
+        c->cs.reserve(n + 1, c->st); c->info.reserve(n + 1, c->st);
+        c->infoUniform = false;
+        if (n) {
+            staged_h2d(c->ring, c->st, c->cs.p, cs, n * 16);
+            if (info_stride_bytes == 16) staged_h2d(c->ring, c->st, c->info.p, info, n * 16);
+            else {
+                const size_t sd = (size_t)info_stride_bytes / 8, CH = 1 << 15;
+                double* h = (double*)c->pin.reserve(n * 16);
+                HostPool::get().for_each((n + CH - 1) / CH, [&](size_t k) {
+                    for (size_t i = k * CH, e = std::min(n, i + CH); i < e; ++i) { h[2 * i] = info[i * sd]; h[2 * i + 1] = info[i * sd + 1]; }
+                });
+                CIPC_CUDA(cudaMemcpyAsync(c->info.p, h, n * 16, cudaMemcpyHostToDevice, c->st));
+            }
+            CIPC_CUDA(cudaStreamSynchronize(c->st)); // the caller's arrays and the staging buffers may be reused
         }
         c->nC = (u32)nC;
         return (int)CIPC_OK;
     });
 }
+int cipc_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int nC) { return cipc_set_constraints_strided(ctx, cs, info, 16, nC); }
 
 int cipc_barrier_energy_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness)
 {
@@ -2860,10 +2910,10 @@ int cipc_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double
         double* h = (double*)c->pin.reserve(n * 24);
         CIPC_CUDA(cudaMemcpyAsync(h, c->g.p, n * 24, cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
-        const size_t sd = stride / 8;
-        for (size_t v = 0; v < n; ++v) { // nodeAttr.g += (IPC.h:1034-1042)
-            g[v * sd] += h[3 * v]; g[v * sd + 1] += h[3 * v + 1]; g[v * sd + 2] += h[3 * v + 2];
-        }
+        const size_t sd = stride / 8, CH = 1 << 14;
+        HostPool::get().for_each((n + CH - 1) / CH, [&](size_t k) { // nodeAttr.g += (IPC.h:1034-1042)
+            for (size_t v = k * CH, e = std::min(n, v + CH); v < e; ++v) { g[v * sd] += h[3 * v]; g[v * sd + 1] += h[3 * v + 1]; g[v * sd + 2] += h[3 * v + 2]; }
+        });
         return (int)CIPC_OK;
     });
 }
@@ -3067,8 +3117,8 @@ int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDi
         if (r) return r;
         long long bits;
         CIPC_CUDA(cudaMemcpyAsync(&bits, c->scal.p + 2, 8, cudaMemcpyDeviceToHost, c->st));
-        if (dist2) CIPC_CUDA(cudaMemcpyAsync(dist2, c->dist2.p, (size_t)c->nC * 8, cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
+        if (dist2) { advise_huge(dist2, (size_t)c->nC * 8); staged_d2h(c->ring, c->st, dist2, c->dist2.p, (size_t)c->nC * 8); }
         bits = bits >= 0 ? bits : (bits ^ 0x7fffffffffffffffLL);
         double m;
         memcpy(&m, &bits, 8);
@@ -3082,7 +3132,7 @@ int cipc_set_prev_positions(cipc_ctx* ctx, const double* Xn, int stride_bytes)
 {
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
-        upload_vec3(ctx, ctx->Xn, Xn, stride_bytes);
+        upload_vec3(ctx, ctx->Xn, Xn, stride_bytes, &ctx->tagXn);
         ctx->haveXn = true;
         return (int)CIPC_OK;
     });
@@ -3102,10 +3152,10 @@ int cipc_get_friction_basis(cipc_ctx* ctx, int32_t* fcs, double* closestPoint, d
         cipc_ctx* c = ctx;
         const size_t n = c->nF;
         if (!n) return (int)CIPC_OK;
-        if (fcs) CIPC_CUDA(cudaMemcpyAsync(fcs, c->fcs.p, n * 16, cudaMemcpyDeviceToHost, c->st));
-        if (closestPoint) CIPC_CUDA(cudaMemcpyAsync(closestPoint, c->fcp.p, n * 16, cudaMemcpyDeviceToHost, c->st));
-        if (tanBasis) CIPC_CUDA(cudaMemcpyAsync(tanBasis, c->fB.p, n * 48, cudaMemcpyDeviceToHost, c->st));
-        if (normalForce) CIPC_CUDA(cudaMemcpyAsync(normalForce, c->fnf.p, n * 8, cudaMemcpyDeviceToHost, c->st));
+        if (fcs) staged_d2h(c->ring, c->st, fcs, c->fcs.p, n * 16);
+        if (closestPoint) staged_d2h(c->ring, c->st, closestPoint, c->fcp.p, n * 16);
+        if (tanBasis) staged_d2h(c->ring, c->st, tanBasis, c->fB.p, n * 48);
+        if (normalForce) staged_d2h(c->ring, c->st, normalForce, c->fnf.p, n * 8);
         CIPC_CUDA(cudaStreamSynchronize(c->st));
         return (int)CIPC_OK;
     });
@@ -3119,10 +3169,10 @@ int cipc_set_friction_basis(cipc_ctx* ctx, const int32_t* fcs, const double* clo
         const size_t n = (size_t)nF;
         c->fcs.reserve(n + 1, c->st); c->fcp.reserve(n + 1, c->st); c->fB.reserve(n * 6 + 2, c->st); c->fnf.reserve(n + 1, c->st);
         if (n) {
-            CIPC_CUDA(cudaMemcpyAsync(c->fcs.p, fcs, n * 16, cudaMemcpyHostToDevice, c->st));
-            if (closestPoint) CIPC_CUDA(cudaMemcpyAsync(c->fcp.p, closestPoint, n * 16, cudaMemcpyHostToDevice, c->st));
-            if (tanBasis) CIPC_CUDA(cudaMemcpyAsync(c->fB.p, tanBasis, n * 48, cudaMemcpyHostToDevice, c->st));
-            CIPC_CUDA(cudaMemcpyAsync(c->fnf.p, normalForce, n * 8, cudaMemcpyHostToDevice, c->st));
+            staged_h2d(c->ring, c->st, c->fcs.p, fcs, n * 16);
+            if (closestPoint) staged_h2d(c->ring, c->st, c->fcp.p, closestPoint, n * 16);
+            if (tanBasis) staged_h2d(c->ring, c->st, c->fB.p, tanBasis, n * 48);
+            staged_h2d(c->ring, c->st, c->fnf.p, normalForce, n * 8);
             CIPC_CUDA(cudaStreamSynchronize(c->st));
         }
         c->nF = (u32)nF;
@@ -3180,10 +3230,10 @@ int cipc_friction_gradient(cipc_ctx* ctx, double epsvh2, double mu, double* g, i
         double* h = (double*)c->pin.reserve(n * 24);
         CIPC_CUDA(cudaMemcpyAsync(h, c->g.p, n * 24, cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
-        const size_t sd = stride / 8;
-        for (size_t v = 0; v < n; ++v) { // nodeAttr.g += (FRICTION.h:294-297)
-            g[v * sd] += h[3 * v]; g[v * sd + 1] += h[3 * v + 1]; g[v * sd + 2] += h[3 * v + 2];
-        }
+        const size_t sd = stride / 8, CH = 1 << 14;
+        HostPool::get().for_each((n + CH - 1) / CH, [&](size_t k) { // nodeAttr.g += (FRICTION.h:294-297)
+            for (size_t v = k * CH, e = std::min(n, v + CH); v < e; ++v) { g[v * sd] += h[3 * v]; g[v * sd + 1] += h[3 * v + 1]; g[v * sd + 2] += h[3 * v + 2]; }
+        });
         return (int)CIPC_OK;
     });
 }
@@ -3237,6 +3287,7 @@ int cipc_step_positions(cipc_ctx* ctx, double alpha)
         cipc_ctx* c = ctx;
         need(c->haveXprev && c->haveP, "saved positions / search direction not set");
         CIPC_LAUNCH(k_step_positions, div_up(c->T.nV, TB), TB, 0, c->st, c->Xprev.p, c->P.p, alpha, c->T.nV, c->X.p);
+        c->tagX = 0; // the resident positions no longer mirror any host array
         c->haveX = true;
         ++c->xVersion;
         return (int)CIPC_OK;

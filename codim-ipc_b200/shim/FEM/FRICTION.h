@@ -159,10 +159,11 @@ void Compute_Friction_Gradient(MESH_NODE<T, dim>& X, MESH_NODE<T, dim>& Xn, cons
         const size_t n = X.size;
         s.stage3.assign(3 * n, 0.0);
         cipc_shim::die(s.ctx, cipc_friction_gradient(s.ctx, epsvh2, mu, s.stage3.data(), 24), "cipc_friction_gradient");
-        for (size_t i = 0; i < n; ++i) { // nodeAttr.g += (FRICTION.h:294-297)
+        const double* st = s.stage3.data();
+        cipc_shim::parallel_nodes(n, [&nodeAttr, st](size_t i) { // nodeAttr.g += (FRICTION.h:294-297)
             VECTOR<T, dim>& g = std::get<FIELDS<MESH_NODE_ATTR<T, dim>>::g>(nodeAttr.Get_Unchecked(i));
-            g[0] += s.stage3[3 * i]; g[1] += s.stage3[3 * i + 1]; g[2] += s.stage3[3 * i + 2];
-        }
+            g[0] += st[3 * i]; g[1] += st[3 * i + 1]; g[2] += st[3 * i + 2];
+        });
     }
 }
 

@@ -155,6 +155,21 @@ inline typename V::value_type* grow_uninitialized(V& v, size_t n)
 #endif
     return v.data() + old;
 }
+// size n with unspecified contents (every element is overwritten by the delivery that follows)
+template <class V>
+inline void resize_uninitialized(V& v, size_t n)
+{
+    v.clear();
+    grow_uninitialized(v, n);
+}
+
+// runs body(i) for i in [0, n) on the library's host thread pool (element accessors of the AoSoA storage are pure address
+// arithmetic, distinct i touch distinct records)
+template <class F>
+inline void parallel_nodes(size_t n, F body)
+{
+    cipc_host_parallel_for(n, 8192, [](size_t b, size_t e, void* u) { F& f = *static_cast<F*>(u); for (size_t i = b; i < e; ++i) f(i); }, &body);
+}
 
 // positions: MESH_NODE<T,3> = BASE_STORAGE<VECTOR<T,3>>; element i is 4 contiguous doubles.  When the
 // elements are contiguous (32-byte stride, the Cabana AoSoA of a single VECTOR member) upload in place,
@@ -170,10 +185,11 @@ inline void upload_positions(State& s, NODES& X, int (*setter)(cipc_ctx*, const 
         if (k < n && std::get<0>(X.Get_Unchecked(k)).data != p0 + 4 * k) contiguous = false;
     if (contiguous) { die(s.ctx, setter(s.ctx, p0, 32), what); return; }
     s.stage3.resize(3 * n);
-    for (size_t i = 0; i < n; ++i) {
+    double* st = s.stage3.data();
+    parallel_nodes(n, [&X, st](size_t i) {
         const double* d = std::get<0>(X.Get_Unchecked(i)).data;
-        s.stage3[3 * i] = d[0]; s.stage3[3 * i + 1] = d[1]; s.stage3[3 * i + 2] = d[2];
-    }
+        st[3 * i] = d[0]; st[3 * i + 1] = d[1]; st[3 * i + 2] = d[2];
+    });
     die(s.ctx, setter(s.ctx, s.stage3.data(), 24), what);
 }
 template <class ATTR>
@@ -181,10 +197,11 @@ inline void upload_rest(State& s, ATTR& nodeAttr)
 {
     const size_t n = nodeAttr.size;
     s.stage3.resize(3 * n);
-    for (size_t i = 0; i < n; ++i) {
+    double* st = s.stage3.data();
+    parallel_nodes(n, [&nodeAttr, st](size_t i) {
         const double* d = std::get<FIELDS<ATTR>::x0>(nodeAttr.Get_Unchecked(i)).data;
-        s.stage3[3 * i] = d[0]; s.stage3[3 * i + 1] = d[1]; s.stage3[3 * i + 2] = d[2];
-    }
+        st[3 * i] = d[0]; st[3 * i + 1] = d[1]; st[3 * i + 2] = d[2];
+    });
     die(s.ctx, cipc_set_rest_positions(s.ctx, s.stage3.data(), 24), "cipc_set_rest_positions");
 }
 inline void upload_topology(State& s, size_t nV, const std::vector<int>& boundaryNode, const std::vector<VECTOR<int, 2>>& boundaryEdge,
@@ -217,9 +234,9 @@ inline void remember_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs
 inline void ensure_constraints(State& s, const std::vector<VECTOR<int, 4>>& cs, const std::vector<VECTOR<double, 2>>& info)
 {
     if (constraints_resident(s, cs)) return;
-    s.stage2.resize(2 * cs.size());
-    for (size_t i = 0; i < cs.size(); ++i) { s.stage2[2 * i] = info[i][0]; s.stage2[2 * i + 1] = info[i][1]; }
-    die(s.ctx, cipc_set_constraints(s.ctx, cs.empty() ? nullptr : cs[0].data, s.stage2.data(), (int)cs.size()), "cipc_set_constraints");
+    static_assert(sizeof(VECTOR<double, 2>) == 32 && sizeof(VECTOR<int, 4>) == 16, "VECTOR<T,dim> stores T data[4]");
+    die(s.ctx, cipc_set_constraints_strided(s.ctx, cs.empty() ? nullptr : cs[0].data, info.empty() ? nullptr : info[0].data, 32, (int)cs.size()),
+        "cipc_set_constraints");
     remember_constraints(s, cs); // the caller's set is the resident one now
 }
 
@@ -254,11 +271,12 @@ void Compute_Constraint_Set(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeAt
         cipc_shim::upload_rest(s, nodeAttr);
         int n = 0;
         cipc_shim::die(s.ctx, cipc_constraint_set(s.ctx, 0, dHat2, thickness, &n), "cipc_constraint_set");
-        constraintSet.resize(n); // the reference resize(0)s and refills (IPC.h:587-590)
-        stencilInfo.resize(n);
-        s.stage2.resize(2 * (size_t)n);
-        cipc_shim::die(s.ctx, cipc_get_constraints(s.ctx, n ? constraintSet[0].data : nullptr, s.stage2.data()), "cipc_get_constraints");
-        for (int i = 0; i < n; ++i) { stencilInfo[i][0] = s.stage2[2 * i]; stencilInfo[i][1] = s.stage2[2 * i + 1]; }
+        // the reference resize(0)s and refills both containers (IPC.h:587-590); here every element is written by the delivery
+        static_assert(sizeof(VECTOR<T, 2>) == 32, "VECTOR<T,dim> stores T data[4]");
+        cipc_shim::resize_uninitialized(constraintSet, (size_t)n);
+        cipc_shim::resize_uninitialized(stencilInfo, (size_t)n);
+        cipc_shim::die(s.ctx, cipc_get_constraints_strided(s.ctx, n ? constraintSet[0].data : nullptr, n ? stencilInfo[0].data : nullptr, 32),
+            "cipc_get_constraints");
         cipc_shim::remember_constraints(s, constraintSet);
         cipc_shim::report_scopes(s, "Compute_Constraint_Set", "ccs_hash_build", "ccs_pairs", "ccs_narrow_pt", "ccs_narrow_ee", "ccs_merge",
             (double)(cipc_counter(s.ctx, "candidates_pt") + cipc_counter(s.ctx, "candidates_pe") + cipc_counter(s.ctx, "candidates_pp")),
@@ -299,10 +317,11 @@ void Compute_Barrier_Gradient(MESH_NODE<T, dim>& X, const std::vector<VECTOR<int
         const size_t n = X.size;
         s.stage3.assign(3 * n, 0.0);
         cipc_shim::die(s.ctx, cipc_barrier_gradient(s.ctx, 0, dHat2, kappa, thickness, s.stage3.data(), 24), "cipc_barrier_gradient");
-        for (size_t i = 0; i < n; ++i) { // nodeAttr.g += (IPC.h:1034-1042); g lives inside the AoSoA record of node i
+        const double* st = s.stage3.data();
+        cipc_shim::parallel_nodes(n, [&nodeAttr, st](size_t i) { // nodeAttr.g += (IPC.h:1034-1042); g lives inside the AoSoA record of node i
             VECTOR<T, dim>& g = std::get<FIELDS<MESH_NODE_ATTR<T, dim>>::g>(nodeAttr.Get_Unchecked(i));
-            g[0] += s.stage3[3 * i]; g[1] += s.stage3[3 * i + 1]; g[2] += s.stage3[3 * i + 2];
-        }
+            g[0] += st[3 * i]; g[1] += st[3 * i + 1]; g[2] += st[3 * i + 2];
+        });
     }
 }
 
@@ -369,7 +388,7 @@ void Compute_Min_Dist2(MESH_NODE<T, dim>& X, const std::vector<VECTOR<int, dim +
             cipc_shim::die(s.ctx, cipc_set_constraints(s.ctx, constraintSet[0].data, s.stage2.data(), (int)constraintSet.size()), "cipc_set_constraints");
             s.csPtr = nullptr; // the resident weights are placeholders: the next barrier call uploads its own
         }
-        dist2.resize(constraintSet.size());
+        cipc_shim::resize_uninitialized(dist2, constraintSet.size());
         cipc_shim::die(s.ctx, cipc_min_dist2(s.ctx, thickness, dist2.data(), &minDist2), "cipc_min_dist2");
     }
 }

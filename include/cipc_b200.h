@@ -60,7 +60,9 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
                       int nBT, const int32_t* BT, int bt_stride, int nRod, const int32_t codimBNStartInd[2],
                       const uint8_t* dbc, int nNnxPairs, const int32_t* nnxPairs,
                       const double* BNArea, const double* BEArea, const double* BTArea);
-/* stride_bytes: 32 for the reference's VECTOR<double,3> storage, 24 for packed xyz */
+/* stride_bytes: 32 for the reference's VECTOR<double,3> storage, 24 for packed xyz.  The four uploads below keep a 64-bit
+ * content tag of what is resident: an array whose bytes equal the previous upload's is not sent again (the contact stage passes
+ * the same X to up to eight consecutive calls). */
 int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes);
 int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes);
 int cipc_set_search_dir(cipc_ctx* ctx, const double* p /* 3*nV packed, like std::vector<T> searchDir */);
@@ -73,6 +75,10 @@ int cipc_constraint_set(cipc_ctx* ctx, int elasticIPC, double dHat2, double thic
 int cipc_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info);
 /* makes a caller-owned set resident (used when the caller's vectors are not the last ones produced) */
 int cipc_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int nC);
+/* the same two calls for the reference's std::vector<VECTOR<T,2>> stencilInfo, whose records are 32 bytes apart (VECTOR<T,dim>
+ * always stores T data[4], Math/VECTOR.h:38-42): info_stride_bytes between consecutive (weight, dHat2) pairs */
+int cipc_get_constraints_strided(cipc_ctx* ctx, int32_t* cs, double* info, int info_stride_bytes);
+int cipc_set_constraints_strided(cipc_ctx* ctx, const int32_t* cs, const double* info, int info_stride_bytes, int nC);
 
 /* ---- barrier terms on the resident constraint set and positions --------------------------- */
 /* E_inout += sum_c w_c m_c b(d_c) e_c          (accumulates like the reference, IPC.h:940) */
@@ -208,6 +214,11 @@ int64_t cipc_kernel_launches(void);  /* kernels launched by this library since l
 /* 64-bit content hash of a host array, computed by a few host threads (~50 GB/s): the shim's change detector for the
  * caller-owned containers (constraint set, friction set) it keeps resident on the device between calls */
 uint64_t cipc_hash_bytes(const void* p, size_t n);
+/* runs fn(begin, end, user) over [0, n) in pieces of `grain` on the library's persistent host thread pool (CIPC_HOST_THREADS,
+ * default all cores) and returns when all pieces are done: the shim's loops over the reference's AoSoA node storage
+ * (gradient accumulation nodeAttr.g +=, rest-position gather) use it.  Not re-entrant from inside fn. */
+typedef void (*cipc_range_fn)(size_t begin, size_t end, void* user);
+int cipc_host_parallel_for(size_t n, size_t grain, cipc_range_fn fn, void* user);
 const char* cipc_version(void);
 
 /* ---- test hooks (device primitives, exercised by tests/) ----------------------------------- */
