@@ -327,6 +327,28 @@ class ContactContext:
     def friction_gradient_dev(self, epsvh2, mu, accumulate=True):
         self._ck(self.L.cipc_friction_gradient_dev(self.h, C.c_double(epsvh2), C.c_double(mu), int(accumulate)))
 
+    # ---- boundary-primitive construction: Utils/MESHIO.h:768-834 + Shell/IMPLICIT_EULER.h:245-277
+    def build_boundary(self, X, tri, seg=None, rod=None, rodRadius=None, particle=None):
+        """-> dict(BN, BE (n,2), BT (n,3), BNArea, BEArea, BTArea, codim (2,)) in the reference's exact order"""
+        X = np.ascontiguousarray(X, np.float64)
+        if X.ndim != 2 or X.shape[1] not in (3, 4):
+            raise ValueError("X must be (nV,3) or (nV,4) float64")
+
+        def ia(a, k):
+            a = np.zeros((0, k), np.int32) if a is None else np.ascontiguousarray(a, np.int32)
+            return a.reshape(-1, a.shape[-1] if a.ndim == 2 else k) if k > 1 else a.reshape(-1)
+        tri, seg, rod, particle = ia(tri, 3), ia(seg, 2), ia(rod, 2), ia(particle, 1)
+        rr = np.ascontiguousarray(np.zeros(len(rod)) if rodRadius is None else rodRadius, np.float64)
+        cnt = (C.c_int32 * 6)()
+        self._ck(self.L.cipc_build_boundary(self.h, len(X), _p(X, C.c_double), X.shape[1] * 8, len(tri), _p(tri, C.c_int32), tri.shape[1] if len(tri) else 3,
+                                            len(seg), _p(seg, C.c_int32), seg.shape[1] if len(seg) else 2, len(rod), _p(rod, C.c_int32),
+                                            rod.shape[1] if len(rod) else 2, _p(rr, C.c_double), len(particle), _p(particle, C.c_int32), cnt))
+        BN = np.zeros(cnt[0], np.int32); BE = np.zeros((cnt[1], 2), np.int32); BT = np.zeros((cnt[2], 3), np.int32)
+        BNA = np.zeros(cnt[5]); BEA = np.zeros(cnt[1] - len(seg)); BTA = np.zeros(cnt[2])  # seg edges carry no BEArea entry (IMPLICIT_EULER.h:245)
+        self._ck(self.L.cipc_get_boundary(self.h, _p(BN, C.c_int32), _p(BE, C.c_int32), 2, _p(BT, C.c_int32), 3, _p(BNA, C.c_double), _p(BEA, C.c_double),
+                                          _p(BTA, C.c_double)))
+        return dict(BN=BN, BE=BE, BT=BT, BNArea=BNA, BEArea=BEA, BTArea=BTA, codim=np.array([cnt[3], cnt[4]], np.int32))
+
     # ---- Hessian triplets -> CSR on the device (SURVEY 8(f)-2)
     def csr_begin(self):
         self._ck(self.L.cipc_csr_begin(self.h))

@@ -1536,6 +1536,7 @@ __global__ void k_fill_u32(u32* p, size_t n, u32 v)
 
 #include "friction.cuh"
 #include "csr.cuh"
+#include "boundary.cuh"
 
 // ========================================================================================= context
 using namespace cipc;
@@ -1620,6 +1621,18 @@ struct cipc_ctx {
     u32 nBlkLast = 0, nUm = 0, nDiag = 0;
     bool mergedValid = false;
     PinnedBuf pinMK, pinMV;
+    // boundary-primitive construction (boundary.cuh): device scratch + the assembled host lists of the last build
+    DevBuf<int4> bdTri;
+    DevBuf<double> bdThird, bdBTArea, bdUeVal, bdBEArea, bdNodeSum, bdBNArea;
+    DevBuf<u32> bdLo, bdHi, bdV, bdIds, bdKey, bdHeads, bdScan, bdUeA, bdUeB, bdIds2, bdNodeV, bdKeep, bdKeepScan;
+    DevBuf<int2> bdBE;
+    DevBuf<int> bdBN;
+    std::vector<int> hBN;
+    std::vector<int2> hBE;
+    std::vector<double> hBNArea, hBEArea, hBTArea;
+    std::vector<int> hTri; // 3 per triangle
+    u64 bdHash = 0;
+    int bdCodim[2] = {0, 0};
     StageRing ring;              // staging for transfers from / to pageable host memory (hostpool.h)
     bool infoUniform = false;    // stencilInfo of the resident set is (infoW, infoD) for every constraint (non-elastic sets)
     double infoW = 1.0, infoD = 0.0;
@@ -3401,6 +3414,163 @@ int cipc_get_csr(cipc_ctx* ctx, int32_t* rowPtr, int32_t* colIdx, double* val)
         if (colIdx && nnz) CIPC_CUDA(cudaMemcpyAsync(colIdx, c->csrColIdx.p, nnz * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         if (val && nnz) CIPC_CUDA(cudaMemcpyAsync(val, c->csrVal.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         CIPC_CUDA(cudaStreamSynchronize(c->st));
+        return (int)CIPC_OK;
+    });
+}
+
+// ---- boundary-primitive construction: Utils/MESHIO.h:768-834 + Shell/IMPLICIT_EULER.h:245-276
+int cipc_build_boundary(cipc_ctx* ctx, int nV, const double* X, int x_stride_bytes, int nTri, const int32_t* tri, int tri_stride, int nSeg,
+    const int32_t* seg, int seg_stride, int nRod, const int32_t* rod, int rod_stride, const double* rodRadius, int nParticle,
+    const int32_t* particle, int32_t counts_out[6])
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        if (nV <= 0 || nTri < 0 || nSeg < 0 || nRod < 0 || nParticle < 0 || !X || (x_stride_bytes != 24 && x_stride_bytes != 32) ||
+            (nTri && (tri_stride != 3 && tri_stride != 4)) || (nSeg && seg_stride != 2 && seg_stride != 4) || (nRod && rod_stride != 2 && rod_stride != 4) ||
+            (nRod && !rodRadius))
+            return (int)CIPC_ERR_ARG;
+        c->begin_call();
+        // content hash of every input: an unchanged call returns the lists of the previous build
+        u64 h = 0x9AD0C0DEULL;
+        const int hdr[8] = {nV, nTri, nSeg, nRod, nParticle, tri_stride, seg_stride, rod_stride};
+        h = fnv(hdr, sizeof(hdr), h);
+        const HashSeg segs[6] = {{(const unsigned char*)tri, (size_t)nTri * tri_stride * 4}, {(const unsigned char*)seg, (size_t)nSeg * seg_stride * 4},
+            {(const unsigned char*)rod, (size_t)nRod * rod_stride * 4}, {(const unsigned char*)rodRadius, (size_t)nRod * 8},
+            {(const unsigned char*)particle, (size_t)nParticle * 4}, {(const unsigned char*)X, (size_t)nV * x_stride_bytes}};
+        h = hash_segments(segs, 6, h) | 1ULL;
+        auto counts = [&]() {
+            if (!counts_out) return;
+            counts_out[0] = (int)c->hBN.size(); counts_out[1] = (int)c->hBE.size(); counts_out[2] = (int)(c->hTri.size() / 3);
+            counts_out[3] = c->bdCodim[0]; counts_out[4] = c->bdCodim[1]; counts_out[5] = (int)c->hBNArea.size();
+        };
+        if (h == c->bdHash) { counts(); return (int)CIPC_OK; }
+        cipc_ctx::Scope sc(c, "build_boundary");
+        // node positions: a private upload (the context's resident X belongs to the contact calls and needs a topology)
+        DevBuf<double4> Xd;
+        Xd.reserve(nV, c->st);
+        {
+            const int keepNV = c->T.nV;
+            c->T.nV = nV; // upload_vec3 sizes by T.nV
+            try { upload_vec3(c, Xd, X, x_stride_bytes, nullptr); } catch (...) { c->T.nV = keepNV; throw; }
+            c->T.nV = keepNV;
+        }
+        int bits = 1;
+        while ((1ll << bits) < (long long)nV) ++bits;
+        u32 nUE = 0, nNode = 0, nKeep = 0;
+        c->hTri.resize((size_t)3 * nTri);
+        if (nTri) {
+            for (int t = 0; t < nTri; ++t) for (int k = 0; k < 3; ++k) {
+                const int v = tri[(size_t)t * tri_stride + k];
+                if (v < 0 || v >= nV) return (int)CIPC_ERR_ARG;
+                c->hTri[(size_t)3 * t + k] = v;
+            }
+            const size_t nE = (size_t)3 * nTri;
+            if (nE >= 0xfffffff0ull) return (int)CIPC_ERR_ARG;
+            c->bdTri.reserve(nTri, c->st); c->bdThird.reserve(nTri, c->st); c->bdBTArea.reserve(nTri, c->st);
+            c->stageI.reserve((size_t)nTri * tri_stride, c->st);
+            staged_h2d(c->ring, c->st, c->stageI.p, tri, (size_t)nTri * tri_stride * 4);
+            CIPC_LAUNCH(k_pack_tris, div_up(nTri, TB), TB, 0, c->st, c->stageI.p, tri_stride, nTri, c->bdTri.p);
+            CIPC_LAUNCH(k_bd_tri_area, div_up(nTri, TB), TB, 0, c->st, Xd.p, c->bdTri.p, nTri, c->bdBTArea.p, c->bdThird.p);
+            c->bdLo.reserve(nE, c->st); c->bdHi.reserve(nE, c->st); c->bdV.reserve(nE, c->st); c->bdIds.reserve(nE, c->st); c->bdKey.reserve(nE, c->st);
+            c->bdHeads.reserve(nE, c->st); c->bdScan.reserve(nE, c->st);
+            CIPC_LAUNCH(k_bd_events, div_up(nE, TB), TB, 0, c->st, c->bdTri.p, nTri, c->bdLo.p, c->bdHi.p, c->bdV.p);
+            // ---- edges: events ordered by (min vertex, max vertex, visiting order)
+            CIPC_LAUNCH(k_iota_copy, div_up(nE, TB), TB, 0, c->st, c->bdHi.p, c->bdKey.p, c->bdIds.p, nE);
+            device_radix_sort(c->bdKey.p, c->bdIds.p, nE, bits, c->sortwk, c->st);
+            CIPC_LAUNCH(k_gather_u32, div_up(nE, TB), TB, 0, c->st, c->bdLo.p, c->bdIds.p, c->bdKey.p, nE);
+            device_radix_sort(c->bdKey.p, c->bdIds.p, nE, bits, c->sortwk, c->st);
+            CIPC_LAUNCH(k_bd_heads, div_up(nE, TB), TB, 0, c->st, c->bdLo.p, c->bdHi.p, c->bdIds.p, (u32)nE, c->bdHeads.p);
+            device_excl_scan(c->bdHeads.p, c->bdScan.p, nE, c->scanwk, c->st);
+            CIPC_CUDA(cudaMemcpyAsync(&nUE, c->scanwk.total.p, 4, cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+            c->bdUeA.reserve((size_t)nUE + 1, c->st); c->bdUeB.reserve((size_t)nUE + 1, c->st); c->bdUeVal.reserve((size_t)nUE + 1, c->st);
+            c->bdIds2.reserve((size_t)nUE + 1, c->st); c->bdBE.reserve((size_t)nUE + 1, c->st); c->bdBEArea.reserve((size_t)nUE + 1, c->st);
+            CIPC_LAUNCH(k_bd_edge_fold, div_up(nE, TB), TB, 0, c->st, c->bdTri.p, c->bdThird.p, c->bdLo.p, c->bdHi.p, c->bdIds.p, c->bdHeads.p, c->bdScan.p,
+                (u32)nE, c->bdUeA.p, c->bdUeB.p, c->bdUeVal.p);
+            // oriented edges in lexicographic (a, b) order -- the iteration order of the reference's std::map
+            CIPC_LAUNCH(k_iota_copy, div_up(nUE, TB), TB, 0, c->st, c->bdUeB.p, c->bdKey.p, c->bdIds2.p, (size_t)nUE);
+            device_radix_sort(c->bdKey.p, c->bdIds2.p, nUE, bits, c->sortwk, c->st);
+            CIPC_LAUNCH(k_gather_u32, div_up(nUE, TB), TB, 0, c->st, c->bdUeA.p, c->bdIds2.p, c->bdKey.p, (size_t)nUE);
+            device_radix_sort(c->bdKey.p, c->bdIds2.p, nUE, bits, c->sortwk, c->st);
+            CIPC_LAUNCH(k_bd_edge_emit, div_up(nUE, TB), TB, 0, c->st, c->bdUeA.p, c->bdUeB.p, c->bdUeVal.p, c->bdIds2.p, nUE, c->bdBE.p, c->bdBEArea.p);
+            // ---- nodes: events ordered by (vertex, visiting order)
+            CIPC_LAUNCH(k_iota_copy, div_up(nE, TB), TB, 0, c->st, c->bdV.p, c->bdKey.p, c->bdIds.p, nE);
+            device_radix_sort(c->bdKey.p, c->bdIds.p, nE, bits, c->sortwk, c->st);
+            CIPC_LAUNCH(k_bd_heads, div_up(nE, TB), TB, 0, c->st, c->bdV.p, (const u32*)nullptr, c->bdIds.p, (u32)nE, c->bdHeads.p);
+            device_excl_scan(c->bdHeads.p, c->bdScan.p, nE, c->scanwk, c->st);
+            CIPC_CUDA(cudaMemcpyAsync(&nNode, c->scanwk.total.p, 4, cudaMemcpyDeviceToHost, c->st));
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+            c->bdNodeV.reserve((size_t)nNode + 1, c->st); c->bdNodeSum.reserve((size_t)nNode + 1, c->st); c->bdKeep.reserve((size_t)nNode + 1, c->st);
+            c->bdKeepScan.reserve((size_t)nNode + 1, c->st); c->bdBN.reserve((size_t)nNode + 1, c->st); c->bdBNArea.reserve((size_t)nNode + 1, c->st);
+            CIPC_LAUNCH(k_bd_node_fold, div_up(nE, TB), TB, 0, c->st, c->bdThird.p, c->bdV.p, c->bdIds.p, c->bdHeads.p, c->bdScan.p, (u32)nE, c->bdNodeV.p,
+                c->bdNodeSum.p, c->bdKeep.p);
+            device_excl_scan(c->bdKeep.p, c->bdKeepScan.p, nNode, c->scanwk, c->st);
+            CIPC_CUDA(cudaMemcpyAsync(&nKeep, c->scanwk.total.p, 4, cudaMemcpyDeviceToHost, c->st));
+            CIPC_LAUNCH(k_bd_node_emit, div_up(nNode, TB), TB, 0, c->st, c->bdNodeV.p, c->bdNodeSum.p, c->bdKeep.p, c->bdKeepScan.p, nNode, c->bdBN.p, c->bdBNArea.p);
+            CIPC_CUDA(cudaStreamSynchronize(c->st));
+        }
+        // ---- host lists: surface primitives from the device, then the appends of Shell/IMPLICIT_EULER.h:245-276
+        c->hBN.resize(nKeep); c->hBNArea.resize(nKeep); c->hBE.resize(nUE); c->hBEArea.resize(nUE); c->hBTArea.resize(nTri);
+        if (nKeep) { staged_d2h(c->ring, c->st, c->hBN.data(), c->bdBN.p, (size_t)nKeep * 4); staged_d2h(c->ring, c->st, c->hBNArea.data(), c->bdBNArea.p, (size_t)nKeep * 8); }
+        if (nUE) { staged_d2h(c->ring, c->st, c->hBE.data(), c->bdBE.p, (size_t)nUE * 8); staged_d2h(c->ring, c->st, c->hBEArea.data(), c->bdBEArea.p, (size_t)nUE * 8); }
+        if (nTri) staged_d2h(c->ring, c->st, c->hBTArea.data(), c->bdBTArea.p, (size_t)nTri * 8);
+        auto xyz = [&](int v, double* o) { const double* p = (const double*)((const char*)X + (size_t)v * x_stride_bytes); o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; };
+        for (int i = 0; i < nSeg; ++i) { // :245-250 -- edges appended, both end nodes appended (duplicates kept, no BNArea entry)
+            const int a = seg[(size_t)i * seg_stride], b = seg[(size_t)i * seg_stride + 1];
+            if (a < 0 || a >= nV || b < 0 || b >= nV) return (int)CIPC_ERR_ARG;
+            c->hBE.push_back(make_int2(a, b));
+        }
+        for (int i = 0; i < nSeg; ++i) { c->hBN.push_back(seg[(size_t)i * seg_stride]); c->hBN.push_back(seg[(size_t)i * seg_stride + 1]); }
+        std::vector<std::pair<int, double>> rodNode; // (node, half edge area) in rod order; folded per node in that order like std::map<int,T>::operator[] +=
+        for (int i = 0; i < nRod; ++i) { // :252-266
+            const int a = rod[(size_t)i * rod_stride], b = rod[(size_t)i * rod_stride + 1];
+            if (a < 0 || a >= nV || b < 0 || b >= nV) return (int)CIPC_ERR_ARG;
+            c->hBE.push_back(make_int2(a, b));
+            double p0[3], p1[3];
+            xyz(a, p0); xyz(b, p1);
+            const double dx = p0[0] - p1[0], dy = p0[1] - p1[1], dz = p0[2] - p1[2];
+            const double len = std::sqrt((dx * dx + dy * dy) + dz * dz);
+            const double area = len * M_PI * rodRadius[i] / 6; // 1/6 of the cylinder surface participates in one contact
+            rodNode.emplace_back(a, area / 2); rodNode.emplace_back(b, area / 2);
+            c->hBEArea.push_back(area / 2);
+        }
+        c->bdCodim[0] = (int)c->hBN.size();
+        std::stable_sort(rodNode.begin(), rodNode.end(), [](const std::pair<int, double>& x, const std::pair<int, double>& y) { return x.first < y.first; });
+        for (size_t i = 0; i < rodNode.size();) { // :267-273 -- ascending node ids, areas summed in rod order
+            size_t j = i;
+            double s = 0.0;
+            for (; j < rodNode.size() && rodNode[j].first == rodNode[i].first; ++j) s += rodNode[j].second;
+            c->hBN.push_back(rodNode[i].first); c->hBNArea.push_back(s);
+            i = j;
+        }
+        c->bdCodim[1] = (int)c->hBN.size();
+        for (int i = 0; i < nParticle; ++i) { // :275-277
+            if (particle[i] < 0 || particle[i] >= nV) return (int)CIPC_ERR_ARG;
+            c->hBN.push_back(particle[i]);
+        }
+        c->bdHash = h;
+        counts();
+        return (int)CIPC_OK;
+    });
+}
+int cipc_get_boundary(cipc_ctx* ctx, int32_t* BN, int32_t* BE, int be_stride, int32_t* BT, int bt_stride, double* BNArea, double* BEArea, double* BTArea)
+{
+    return guarded(ctx, [&]() {
+        cipc_ctx* c = ctx;
+        if (!c->bdHash) return (int)CIPC_ERR_ARG;
+        if ((BE && be_stride != 2 && be_stride != 4) || (BT && bt_stride != 3 && bt_stride != 4)) return (int)CIPC_ERR_ARG;
+        if (BN && !c->hBN.empty()) memcpy(BN, c->hBN.data(), c->hBN.size() * 4);
+        if (BE) for (size_t i = 0; i < c->hBE.size(); ++i) {
+            BE[i * be_stride] = c->hBE[i].x; BE[i * be_stride + 1] = c->hBE[i].y;
+            for (int k = 2; k < be_stride; ++k) BE[i * be_stride + k] = 0;
+        }
+        if (BT) for (size_t t = 0; t < c->hTri.size() / 3; ++t) {
+            for (int k = 0; k < 3; ++k) BT[t * bt_stride + k] = c->hTri[3 * t + k];
+            for (int k = 3; k < bt_stride; ++k) BT[t * bt_stride + k] = 0;
+        }
+        if (BNArea && !c->hBNArea.empty()) memcpy(BNArea, c->hBNArea.data(), c->hBNArea.size() * 8);
+        if (BEArea && !c->hBEArea.empty()) memcpy(BEArea, c->hBEArea.data(), c->hBEArea.size() * 8);
+        if (BTArea && !c->hBTArea.empty()) memcpy(BTArea, c->hBTArea.data(), c->hBTArea.size() * 8);
         return (int)CIPC_OK;
     });
 }

@@ -157,7 +157,9 @@ def assemble(parts, rods=(), particles=None, dHat=1e-3, xi=0.0, seed=2, p_scale=
     sc = dict(X=X, X0=X.copy(), BN=BN, BE=BE.astype(np.int32), BT=BT, nRod=nRod, codim=(codim0, codim1),
               DBC=np.concatenate(dbc), NNX=(np.zeros((0, 2), np.int32) if nnx is None else np.asarray(nnx, np.int32)),
               BNArea=BNA, BEArea=BEA, BTArea=BTA, dHat2=dHat * dHat, xi=xi, kappa=oipc_kappa(dHat * dHat),
-              p=rng.normal(0.0, 0.2 * p_scale, size=X.shape))
+              p=rng.normal(0.0, 0.2 * p_scale, size=X.shape),
+              # raw element lists the boundary primitives were built from (inputs of cipc_build_boundary)
+              F=F, rodE=(np.concatenate(rod_edges, 0).astype(np.int32) if rod_edges else np.zeros((0, 2), np.int32)), particles=part_ids)
     return sc
 
 

@@ -173,6 +173,24 @@ int cipc_csr_add(cipc_ctx* ctx);
 int cipc_csr_finish(cipc_ctx* ctx, int64_t* nnz_out);
 int cipc_get_csr(cipc_ctx* ctx, int32_t* rowPtr, int32_t* colIdx, double* val);
 
+/* ---- boundary-primitive construction --------------------------------------------------------
+ * Find_Surface_Primitives_And_Compute_Area (Utils/MESHIO.h:768-834: a std::map over the 3T directed triangle edges, rebuilt
+ * every time step by Shell/IMPLICIT_EULER.h:224-243) plus the seg / rod / particle appends of Shell/IMPLICIT_EULER.h:245-277,
+ * on the device, with the reference's exact output order:
+ *   boundaryTri = tri in order; boundaryEdge = undirected edges oriented like their first mention, in lexicographic order of
+ *   the oriented pair, then seg, then rod; boundaryNode = ascending surface vertices of non-zero area, then both ends of
+ *   every seg, [codim0] rod nodes ascending, [codim1] particles; BNArea (surface + rod nodes only: nBNArea values), BEArea
+ *   (surface + rod edges only: nBE - nSeg values, like the reference's vector), BTArea.
+ * X: nV node positions (stride 32 or 24 bytes); tri / seg / rod: int records with the given stride in ints (3|4, 2|4, 2|4);
+ * rodRadius[i] = rodInfo[i][2].  counts_out = {nBN, nBE, nBT, codimBNStartInd[0], codimBNStartInd[1], nBNArea}.
+ * The result is cached on a content hash of every input: an unchanged call costs the hash only.
+ * cipc_get_boundary copies the lists out (any pointer may be NULL; be_stride / bt_stride as in cipc_set_topology). */
+int cipc_build_boundary(cipc_ctx* ctx, int nV, const double* X, int x_stride_bytes, int nTri, const int32_t* tri, int tri_stride,
+                        int nSeg, const int32_t* seg, int seg_stride, int nRod, const int32_t* rod, int rod_stride,
+                        const double* rodRadius, int nParticle, const int32_t* particle, int32_t counts_out[6]);
+int cipc_get_boundary(cipc_ctx* ctx, int32_t* BN, int32_t* BE, int be_stride, int32_t* BT, int bt_stride, double* BNArea,
+                      double* BEArea, double* BTArea);
+
 /* ---- device-resident access (multi-GPU reductions, benchmarking) ----------------------------- */
 double* cipc_dev_positions(cipc_ctx* ctx);      /* nV x 4 doubles (x,y,z,pad) */
 double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient_dev */

@@ -1291,6 +1291,67 @@ void oracle_compare_triplet_blocks(const void* a_, const void* b_, const int* cs
     }
     out[0] = worst; out[1] = (double)mism; out[2] = worstQ; out[3] = (double)nC; out[4] = (double)off[nC];
 }
+// ---- boundary-primitive construction, restated literally (checker of cipc_build_boundary):
+// Find_Surface_Primitives_And_Compute_Area (Utils/MESHIO.h:768-834) followed by the seg / rod / particle appends of
+// Shell/IMPLICIT_EULER.h:245-277.  Same containers as the reference: std::map keyed by the oriented vertex pair (lexicographic
+// operator<, Math/VECTOR.h:124-134), a dense per-vertex area accumulator, std::map<int, T> for the rod nodes.
+namespace {
+std::vector<int> g_bBN, g_bBE, g_bBT;
+std::vector<double> g_bBNArea, g_bBEArea, g_bBTArea;
+int g_bCodim[2];
+}
+void oracle_build_boundary(int nV, const double* X, int nTri, const int* tri, int nSeg, const int* seg, int nRod, const int* rod,
+    const double* rodRadius, int nParticle, const int* particle, int* counts6)
+{
+    g_bBN.clear(); g_bBE.clear(); g_bBT.clear(); g_bBNArea.clear(); g_bBEArea.clear(); g_bBTArea.clear();
+    typedef std::pair<int, int> E2;
+    std::map<E2, double> boundaryEdgeSet;
+    std::vector<double> isBoundaryNode(nV, 0.0);
+    for (int t = 0; t < nTri; ++t) { // MESHIO.h:781-812
+        const int* v = tri + 3 * (size_t)t;
+        const V3 v0(X + 3 * (size_t)v[0]), v1(X + 3 * (size_t)v[1]), v2(X + 3 * (size_t)v[2]);
+        g_bBTArea.push_back(0.5 * std::sqrt(norm2(cross(v1 - v0, v2 - v0))));
+        g_bBT.push_back(v[0]); g_bBT.push_back(v[1]); g_bBT.push_back(v[2]);
+        const int ea[3] = {v[0], v[1], v[2]}, eb[3] = {v[1], v[2], v[0]};
+        for (int k = 0; k < 3; ++k) {
+            auto finder = boundaryEdgeSet.find(E2(eb[k], ea[k]));
+            if (finder == boundaryEdgeSet.end()) boundaryEdgeSet[E2(ea[k], eb[k])] = g_bBTArea.back() / 3;
+            else finder->second += g_bBTArea.back() / 3;
+        }
+        for (int k = 0; k < 3; ++k) isBoundaryNode[v[k]] += g_bBTArea.back() / 3;
+        g_bBTArea.back() /= 2;
+    }
+    for (const auto& i : boundaryEdgeSet) { // :816-819
+        g_bBE.push_back(i.first.first); g_bBE.push_back(i.first.second);
+        g_bBEArea.push_back(i.second / 2);
+    }
+    for (int vI = 0; vI < nV; ++vI) // :821-826
+        if (isBoundaryNode[vI]) { g_bBN.push_back(vI); g_bBNArea.push_back(isBoundaryNode[vI]); }
+    // Shell/IMPLICIT_EULER.h:245-277
+    for (int i = 0; i < nSeg; ++i) { g_bBE.push_back(seg[2 * i]); g_bBE.push_back(seg[2 * i + 1]); }
+    for (int i = 0; i < nSeg; ++i) { g_bBN.push_back(seg[2 * i]); g_bBN.push_back(seg[2 * i + 1]); }
+    std::map<int, double> rodNodeArea;
+    for (int i = 0; i < nRod; ++i) {
+        g_bBE.push_back(rod[2 * i]); g_bBE.push_back(rod[2 * i + 1]);
+        const V3 v0(X + 3 * (size_t)rod[2 * i]), v1(X + 3 * (size_t)rod[2 * i + 1]);
+        g_bBEArea.push_back(std::sqrt(norm2(v0 - v1)) * M_PI * rodRadius[i] / 6);
+        rodNodeArea[rod[2 * i]] += g_bBEArea.back() / 2;
+        rodNodeArea[rod[2 * i + 1]] += g_bBEArea.back() / 2;
+        g_bBEArea.back() /= 2;
+    }
+    g_bCodim[0] = (int)g_bBN.size();
+    for (const auto& n : rodNodeArea) { g_bBN.push_back(n.first); g_bBNArea.push_back(n.second); }
+    g_bCodim[1] = (int)g_bBN.size();
+    for (int i = 0; i < nParticle; ++i) g_bBN.push_back(particle[i]);
+    counts6[0] = (int)g_bBN.size(); counts6[1] = (int)(g_bBE.size() / 2); counts6[2] = (int)(g_bBT.size() / 3);
+    counts6[3] = g_bCodim[0]; counts6[4] = g_bCodim[1]; counts6[5] = (int)g_bBNArea.size();
+}
+void oracle_fetch_boundary(int* BN, int* BE, int* BT, double* BNArea, double* BEArea, double* BTArea)
+{
+    std::copy(g_bBN.begin(), g_bBN.end(), BN); std::copy(g_bBE.begin(), g_bBE.end(), BE); std::copy(g_bBT.begin(), g_bBT.end(), BT);
+    std::copy(g_bBNArea.begin(), g_bBNArea.end(), BNArea); std::copy(g_bBEArea.begin(), g_bBEArea.end(), BEArea);
+    std::copy(g_bBTArea.begin(), g_bBTArea.end(), BTArea);
+}
 int oracle_step_size(void* h, int elastic, const double* searchDir, double thickness, int use_hash, double* stepSize,
     double* timers3, long* nPairs)
 {

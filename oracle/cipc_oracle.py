@@ -322,6 +322,22 @@ def compare_triplet_blocks(ptr_a, ptr_b, cs):
                 triplets=int(out[4]))
 
 
+def build_boundary(X, tri, seg=None, rod=None, rodRadius=None, particle=None):
+    """literal restatement of Find_Surface_Primitives_And_Compute_Area (Utils/MESHIO.h:768-834) + the seg / rod / particle
+    appends of Shell/IMPLICIT_EULER.h:245-277 -> dict(BN, BE (n,2), BT (n,3), BNArea, BEArea, BTArea, codim (2,))"""
+    X = np.ascontiguousarray(X, np.float64)
+    ia = lambda a, k: np.ascontiguousarray(a if a is not None else np.zeros((0, k)), np.int32).reshape(-1, k) if k > 1 else \
+        np.ascontiguousarray(a if a is not None else np.zeros(0), np.int32).reshape(-1)
+    tri, seg, rod, particle = ia(tri, 3), ia(seg, 2), ia(rod, 2), ia(particle, 1)
+    rr = np.ascontiguousarray(rodRadius if rodRadius is not None else np.zeros(len(rod)), np.float64)
+    cnt = np.zeros(6, np.int32)
+    lib().oracle_build_boundary(len(X), _dp(X), len(tri), _ip(tri), len(seg), _ip(seg), len(rod), _ip(rod), _dp(rr), len(particle), _ip(particle), _ip(cnt))
+    BN = np.zeros(cnt[0], np.int32); BE = np.zeros((cnt[1], 2), np.int32); BT = np.zeros((cnt[2], 3), np.int32)
+    BNA = np.zeros(cnt[5]); BEA = np.zeros(cnt[1] - len(seg)); BTA = np.zeros(cnt[2])  # seg edges carry no BEArea entry (IMPLICIT_EULER.h:245)
+    lib().oracle_fetch_boundary(_ip(BN), _ip(BE), _ip(BT), _dp(BNA), _dp(BEA), _dp(BTA))
+    return dict(BN=BN, BE=BE, BT=BT, BNArea=BNA, BEArea=BEA, BTArea=BTA, codim=cnt[3:5].copy())
+
+
 # ---- per-stencil probes (kind: 0 PP, 1 PE, 2 PT, 3 EE, 4 EE cross-norm^2)
 _NDOF = {0: 6, 1: 9, 2: 12, 3: 12, 4: 12}
 
