@@ -87,11 +87,18 @@ class ContactContext:
     """One device context (one per process / GPU).  rank/world select this process' share of the
     candidate pairs (multi-GPU)."""
 
-    def __init__(self, device=0, rank=0, world=1):
+    def __init__(self, device=0, rank=0, world=1, devices=None):
+        """devices: list of CUDA ordinals -> ONE context over several GPUs of this box driven by this thread (cipc_create_multi:
+        slab-partitioned pairs, NVLink peer exchanges inside the library); otherwise a single-device context (rank/world select
+        this process' share when one process per GPU is used)."""
         L = load_library()
         self.L = L
         h = C.c_void_p()
-        st = L.cipc_create(int(device), int(rank), int(world), C.byref(h))
+        if devices is not None:
+            d = (C.c_int * len(devices))(*[int(x) for x in devices])
+            st = L.cipc_create_multi(len(devices), d, C.byref(h))
+        else:
+            st = L.cipc_create(int(device), int(rank), int(world), C.byref(h))
         if st != CIPC_OK:
             raise CipcError(st, "cipc_create failed (no CUDA device?) -- there is no CPU fallback")
         self.h = h

@@ -1538,6 +1538,9 @@ __global__ void k_fill_u32(u32* p, size_t n, u32 v)
 #include "csr.cuh"
 #include "boundary.cuh"
 
+struct cipc_ctx;
+#include "multidev.h"
+
 // ========================================================================================= context
 using namespace cipc;
 
@@ -1548,6 +1551,8 @@ struct StageEv {
 
 struct cipc_ctx {
     int dev = 0, rank = 0, world = 1;
+    std::unique_ptr<cipc_multi> multi; // cipc_create_multi: this context only fans calls out to multi->sub (multidev.h)
+    u32 nPassLast = 0;                 // stencils of the last constraint set that needed no de-duplication (PT / EE / mollified)
     cudaStream_t st = nullptr, ownSt = nullptr;
     cudaEvent_t userEv[64] = {};
     std::string err;
@@ -2523,6 +2528,22 @@ void deliver_merged_host(cipc_ctx* c, cipc_triplet* out)
     if (failed) throw CudaError("device-to-host copy of the merged Hessian blocks failed");
 }
 
+// ---- multi-device fan-out (defined behind the C ABI, multidev.h)
+static int multi_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE, const int32_t* BE, int be_stride, int nBT, const int32_t* BT,
+    int bt_stride, int nRod, const int32_t codim[2], const uint8_t* dbc, int nNnx, const int32_t* nnxPairs, const double* BNArea, const double* BEArea,
+    const double* BTArea);
+static int multi_upload(cipc_ctx* ctx, int which, const double* src, int stride_bytes);
+static int multi_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickness, int* nC_out);
+static int multi_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info, int info_stride_bytes);
+static int multi_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int info_stride_bytes, int nC);
+static int multi_barrier_energy(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* E);
+static int multi_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* g, int stride);
+static int multi_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD, int64_t* nTrip, bool merged);
+static int multi_get_triplets(cipc_ctx* ctx, cipc_triplet* out);
+static int multi_step_size(cipc_ctx* ctx, int elastic, double thickness, double* step);
+static int multi_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2);
+#define CIPC_MULTI_UNSUPPORTED(ctx) do { if ((ctx) && (ctx)->multi) { (ctx)->err = "not available on a multi-device context"; return CIPC_ERR_UNSUPPORTED; } } while (0)
+
 // ========================================================================================= C ABI
 extern "C" {
 
@@ -2590,6 +2611,14 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
 void cipc_destroy(cipc_ctx* ctx)
 {
     if (!ctx) return;
+    if (ctx->multi) {
+        ctx->multi->thr.clear(); // joins the helper threads
+        for (cipc_ctx* s : ctx->multi->sub) cipc_destroy(s);
+        cudaSetDevice(ctx->dev);
+        ctx->multi.reset();
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->dev);
     cudaStreamSynchronize(ctx->st);
     for (auto e : ctx->evPool) cudaEventDestroy(e);
@@ -2600,11 +2629,13 @@ void cipc_destroy(cipc_ctx* ctx)
 const char* cipc_last_error(cipc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int cipc_sync(cipc_ctx* ctx)
 {
+    if (ctx && ctx->multi) { int st = CIPC_OK; for (cipc_ctx* s : ctx->multi->sub) { const int r = cipc_sync(s); if (r) st = r; } return st; }
     return guarded(ctx, [&]() { CIPC_CUDA(cudaStreamSynchronize(ctx->st)); return (int)CIPC_OK; });
 }
 
 int cipc_set_stream(cipc_ctx* ctx, void* stream)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         CIPC_CUDA(cudaStreamSynchronize(ctx->st));
         ctx->st = stream ? (cudaStream_t)stream : ctx->ownSt;
@@ -2613,6 +2644,7 @@ int cipc_set_stream(cipc_ctx* ctx, void* stream)
 }
 int cipc_event_record(cipc_ctx* ctx, int slot)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         if (slot < 0 || slot >= 64) return (int)CIPC_ERR_ARG;
         if (!ctx->userEv[slot]) CIPC_CUDA(cudaEventCreate(&ctx->userEv[slot]));
@@ -2634,6 +2666,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
     const int32_t* BT, int bt_stride, int nRod, const int32_t codim[2], const uint8_t* dbc, int nNnx, const int32_t* nnxPairs,
     const double* BNArea, const double* BEArea, const double* BTArea)
 {
+    if (ctx && ctx->multi) return multi_set_topology(ctx, nV, nBN, BN, nBE, BE, be_stride, nBT, BT, bt_stride, nRod, codim, dbc, nNnx, nnxPairs, BNArea, BEArea, BTArea);
     return guarded(ctx, [&]() {
         if (nV <= 0 || nBN < 0 || nBE < 0 || nBT < 0 || (be_stride != 2 && be_stride != 4) || (bt_stride != 3 && bt_stride != 4) || !dbc)
             return (int)CIPC_ERR_ARG;
@@ -2704,6 +2737,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
 }
 int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes)
 {
+    if (ctx && ctx->multi) return multi_upload(ctx, 0, X, stride_bytes);
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
         if (upload_vec3(ctx, ctx->X, X, stride_bytes, &ctx->tagX)) ++ctx->xVersion;
@@ -2713,6 +2747,7 @@ int cipc_set_positions(cipc_ctx* ctx, const double* X, int stride_bytes)
 }
 int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes)
 {
+    if (ctx && ctx->multi) return multi_upload(ctx, 1, X0, stride_bytes);
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
         if (upload_vec3(ctx, ctx->X0, X0, stride_bytes, &ctx->tagX0) || !ctx->haveX0) {
@@ -2725,6 +2760,7 @@ int cipc_set_rest_positions(cipc_ctx* ctx, const double* X0, int stride_bytes)
 }
 int cipc_set_search_dir(cipc_ctx* ctx, const double* p)
 {
+    if (ctx && ctx->multi) return multi_upload(ctx, 2, p, 24);
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
         upload_vec3(ctx, ctx->P, p, 24, &ctx->tagP);
@@ -2735,6 +2771,7 @@ int cipc_set_search_dir(cipc_ctx* ctx, const double* p)
 
 int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickness, int* nC_out)
 {
+    if (ctx && ctx->multi) return multi_constraint_set(ctx, elastic, dHat2, thickness, nC_out);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->haveX && c->haveX0, "positions / rest positions not set");
@@ -2798,6 +2835,7 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             CIPC_CUDA(cudaStreamSynchronize(c->st));
         }
         u32 nC = hc[0];
+        c->nPassLast = hc[0];
         {
             cipc_ctx::Scope sc(c, "ccs_merge");
             const u32 nRaw = hc[1];
@@ -2825,6 +2863,7 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
 }
 int cipc_get_constraints_strided(cipc_ctx* ctx, int32_t* cs, double* info, int info_stride_bytes)
 {
+    if (ctx && ctx->multi) return multi_get_constraints(ctx, cs, info, info_stride_bytes);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (info && (info_stride_bytes < 16 || info_stride_bytes % 8)) return (int)CIPC_ERR_ARG;
@@ -2864,6 +2903,7 @@ int cipc_get_constraints_strided(cipc_ctx* ctx, int32_t* cs, double* info, int i
 int cipc_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info) { return cipc_get_constraints_strided(ctx, cs, info, 16); }
 int cipc_set_constraints_strided(cipc_ctx* ctx, const int32_t* cs, const double* info, int info_stride_bytes, int nC)
 {
+    if (ctx && ctx->multi) return multi_set_constraints(ctx, cs, info, info_stride_bytes, nC);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (nC < 0 || info_stride_bytes < 16 || info_stride_bytes % 8) return (int)CIPC_ERR_ARG;
@@ -2891,10 +2931,12 @@ int cipc_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, i
 
 int cipc_barrier_energy_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() { ctx->begin_call(); return do_barrier_energy(ctx, elastic, dHat2, kappa, thickness); });
 }
 int cipc_barrier_energy(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* E)
 {
+    if (ctx && ctx->multi) return multi_barrier_energy(ctx, elastic, dHat2, kappa, thickness, E);
     return guarded(ctx, [&]() {
         ctx->begin_call();
         int r = do_barrier_energy(ctx, elastic, dHat2, kappa, thickness);
@@ -2909,10 +2951,12 @@ int cipc_barrier_energy(cipc_ctx* ctx, int elastic, double dHat2, const double k
 }
 int cipc_barrier_gradient_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() { ctx->begin_call(); return do_barrier_gradient(ctx, elastic, dHat2, kappa, thickness); });
 }
 int cipc_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* g, int stride)
 {
+    if (ctx && ctx->multi) return multi_barrier_gradient(ctx, elastic, dHat2, kappa, thickness, g, stride);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (stride < 24 || stride % 8) return (int)CIPC_ERR_ARG;
@@ -3055,24 +3099,29 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
 int cipc_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
     int64_t* nTrip)
 {
+    if (ctx && ctx->multi) return multi_barrier_hessian(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, false);
     return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, H_HOST);
 }
 int cipc_barrier_hessian_merged(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
     int64_t* nTrip)
 {
+    if (ctx && ctx->multi) return multi_barrier_hessian(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, true);
     return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, H_BLK);
 }
 int cipc_barrier_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD,
     int64_t* nTrip)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, projectSPD, nTrip, H_DEV);
 }
 int cipc_barrier_gradient_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int64_t* nTrip)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return barrier_hessian_impl(ctx, elastic, dHat2, kappa, thickness, 1, nTrip, H_DEV, true);
 }
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 {
+    if (ctx && ctx->multi) return multi_get_triplets(ctx, out);
     return guarded(ctx, [&]() {
         if (!ctx->nTrip) return (int)CIPC_OK;
         if (ctx->mergedValid) { deliver_merged_host(ctx, out); return (int)CIPC_OK; }
@@ -3088,7 +3137,7 @@ int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 }
 cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx)
 {
-    if (!ctx) return nullptr;
+    if (!ctx || ctx->multi) return nullptr;
     int r = guarded(ctx, [&]() {
         ctx->begin_call();
         ctx->trip.reserve(1, ctx->st); // an empty stream (no constraints) still has a valid address
@@ -3099,10 +3148,12 @@ cipc_triplet* cipc_dev_triplets(cipc_ctx* ctx)
 }
 int cipc_step_size_dev(cipc_ctx* ctx, int elastic, double thickness, double stepIn)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() { ctx->begin_call(); return do_step_size(ctx, elastic, thickness, stepIn); });
 }
 int cipc_step_size(cipc_ctx* ctx, int elastic, double thickness, double* step)
 {
+    if (ctx && ctx->multi) return multi_step_size(ctx, elastic, thickness, step);
     return guarded(ctx, [&]() {
         ctx->begin_call();
         int r = do_step_size(ctx, elastic, thickness, *step);
@@ -3117,11 +3168,13 @@ int cipc_step_size(cipc_ctx* ctx, int elastic, double thickness, double* step)
 }
 int cipc_min_dist2_dev(cipc_ctx* ctx, double thickness)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     (void)thickness;
     return guarded(ctx, [&]() { ctx->begin_call(); return do_min_dist(ctx, false); });
 }
 int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2)
 {
+    if (ctx && ctx->multi) return multi_min_dist2(ctx, thickness, dist2, minDist2);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         c->begin_call();
@@ -3143,6 +3196,7 @@ int cipc_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDi
 // ---- friction (FEM/FRICTION.h)
 int cipc_set_prev_positions(cipc_ctx* ctx, const double* Xn, int stride_bytes)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         need(ctx->T.nV > 0, "topology not set");
         upload_vec3(ctx, ctx->Xn, Xn, stride_bytes, &ctx->tagXn);
@@ -3152,6 +3206,7 @@ int cipc_set_prev_positions(cipc_ctx* ctx, const double* Xn, int stride_bytes)
 }
 int cipc_friction_basis(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int* nF_out)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         ctx->begin_call();
         int r = do_friction_basis(ctx, elastic, dHat2, kappa, thickness);
@@ -3161,6 +3216,7 @@ int cipc_friction_basis(cipc_ctx* ctx, int elastic, double dHat2, const double k
 }
 int cipc_get_friction_basis(cipc_ctx* ctx, int32_t* fcs, double* closestPoint, double* tanBasis, double* normalForce)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         const size_t n = c->nF;
@@ -3176,6 +3232,7 @@ int cipc_get_friction_basis(cipc_ctx* ctx, int32_t* fcs, double* closestPoint, d
 int cipc_set_friction_basis(cipc_ctx* ctx, const int32_t* fcs, const double* closestPoint, const double* tanBasis, const double* normalForce,
     int nF)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (nF < 0 || (nF && (!fcs || !normalForce))) return (int)CIPC_ERR_ARG;
@@ -3194,6 +3251,7 @@ int cipc_set_friction_basis(cipc_ctx* ctx, const int32_t* fcs, const double* clo
 }
 int cipc_friction_coef(cipc_ctx* ctx, int nComp, const int32_t* compNodeRange, const double* muComp, double* mu_out)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (nComp <= 0 || !compNodeRange || !muComp) return (int)CIPC_ERR_ARG;
@@ -3212,10 +3270,12 @@ int cipc_friction_coef(cipc_ctx* ctx, int nComp, const int32_t* compNodeRange, c
 }
 int cipc_friction_energy_dev(cipc_ctx* ctx, double epsvh2, double mu)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() { ctx->begin_call(); return do_friction_energy(ctx, epsvh2, mu); });
 }
 int cipc_friction_energy(cipc_ctx* ctx, double epsvh2, double mu, double* E)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         ctx->begin_call();
         int r = do_friction_energy(ctx, epsvh2, mu);
@@ -3229,10 +3289,12 @@ int cipc_friction_energy(cipc_ctx* ctx, double epsvh2, double mu, double* E)
 }
 int cipc_friction_gradient_dev(cipc_ctx* ctx, double epsvh2, double mu, int accumulate)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() { ctx->begin_call(); return do_friction_gradient(ctx, epsvh2, mu, accumulate != 0); });
 }
 int cipc_friction_gradient(cipc_ctx* ctx, double epsvh2, double mu, double* g, int stride)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (stride < 24 || stride % 8) return (int)CIPC_ERR_ARG;
@@ -3252,6 +3314,7 @@ int cipc_friction_gradient(cipc_ctx* ctx, double epsvh2, double mu, double* g, i
 }
 int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTrip)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     (void)projectSPD; // the inner 2x2 matrix is positive semi-definite in closed form: makePD is the identity (friction.cuh)
     return guarded(ctx, [&]() {
         ctx->begin_call();
@@ -3262,6 +3325,7 @@ int cipc_friction_hessian(cipc_ctx* ctx, double epsvh2, double mu, int projectSP
 }
 int cipc_friction_hessian_dev(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTrip)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     (void)projectSPD;
     return guarded(ctx, [&]() {
         ctx->begin_call();
@@ -3273,6 +3337,7 @@ int cipc_friction_hessian_dev(cipc_ctx* ctx, double epsvh2, double mu, int proje
 
 int cipc_friction_hessian_merged(cipc_ctx* ctx, double epsvh2, double mu, int projectSPD, int64_t* nTrip)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     (void)projectSPD;
     return guarded(ctx, [&]() {
         ctx->begin_call();
@@ -3285,6 +3350,7 @@ int cipc_friction_hessian_merged(cipc_ctx* ctx, double epsvh2, double mu, int pr
 // ---- device-resident line search: Shell/IMPLICIT_EULER.h:102-131 without a position upload per trial
 int cipc_save_positions(cipc_ctx* ctx)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->haveX, "positions not set");
@@ -3296,6 +3362,7 @@ int cipc_save_positions(cipc_ctx* ctx)
 }
 int cipc_step_positions(cipc_ctx* ctx, double alpha)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->haveXprev && c->haveP, "saved positions / search direction not set");
@@ -3308,6 +3375,7 @@ int cipc_step_positions(cipc_ctx* ctx, double alpha)
 }
 int cipc_get_positions(cipc_ctx* ctx, double* X, int stride_bytes)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->haveX, "positions not set");
@@ -3329,10 +3397,12 @@ int cipc_get_positions(cipc_ctx* ctx, double* X, int stride_bytes)
 // ---- triplets -> CSR (Math/CSR_MATRIX.h:49-56)
 int cipc_csr_begin(cipc_ctx* ctx)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() { ctx->nBlk = 0; ctx->nU = 0; ctx->csrValid = false; return (int)CIPC_OK; });
 }
 int cipc_csr_add(cipc_ctx* ctx)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         c->begin_call();
@@ -3351,6 +3421,7 @@ int cipc_csr_add(cipc_ctx* ctx)
 }
 int cipc_csr_finish(cipc_ctx* ctx, int64_t* nnz_out)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->T.nV > 0, "topology not set");
@@ -3406,6 +3477,7 @@ int cipc_csr_finish(cipc_ctx* ctx, int64_t* nnz_out)
 }
 int cipc_get_csr(cipc_ctx* ctx, int32_t* rowPtr, int32_t* colIdx, double* val)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         need(c->csrValid, "no assembled CSR matrix (call cipc_csr_finish)");
@@ -3423,6 +3495,7 @@ int cipc_build_boundary(cipc_ctx* ctx, int nV, const double* X, int x_stride_byt
     const int32_t* seg, int seg_stride, int nRod, const int32_t* rod, int rod_stride, const double* rodRadius, int nParticle,
     const int32_t* particle, int32_t counts_out[6])
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (nV <= 0 || nTri < 0 || nSeg < 0 || nRod < 0 || nParticle < 0 || !X || (x_stride_bytes != 24 && x_stride_bytes != 32) ||
@@ -3555,6 +3628,7 @@ int cipc_build_boundary(cipc_ctx* ctx, int nV, const double* X, int x_stride_byt
 }
 int cipc_get_boundary(cipc_ctx* ctx, int32_t* BN, int32_t* BE, int be_stride, int32_t* BT, int bt_stride, double* BNArea, double* BEArea, double* BTArea)
 {
+    CIPC_MULTI_UNSUPPORTED(ctx);
     return guarded(ctx, [&]() {
         cipc_ctx* c = ctx;
         if (!c->bdHash) return (int)CIPC_ERR_ARG;
@@ -3575,13 +3649,18 @@ int cipc_get_boundary(cipc_ctx* ctx, int32_t* BN, int32_t* BE, int be_stride, in
     });
 }
 
-double* cipc_dev_positions(cipc_ctx* ctx) { return ctx ? (double*)ctx->X.p : nullptr; }
-double* cipc_dev_gradient(cipc_ctx* ctx) { return ctx ? ctx->g.p : nullptr; }
-double* cipc_dev_scalars(cipc_ctx* ctx) { return ctx ? ctx->scal.p : nullptr; }
+double* cipc_dev_positions(cipc_ctx* ctx) { return ctx && !ctx->multi ? (double*)ctx->X.p : nullptr; }
+double* cipc_dev_gradient(cipc_ctx* ctx) { return ctx && !ctx->multi ? ctx->g.p : nullptr; }
+double* cipc_dev_scalars(cipc_ctx* ctx) { return ctx && !ctx->multi ? ctx->scal.p : nullptr; }
 
 double cipc_stage_ms(cipc_ctx* ctx, const char* stage)
 {
     if (!ctx) return -1;
+    if (ctx->multi) { // the slowest rank
+        double m = -1;
+        for (cipc_ctx* s : ctx->multi->sub) m = std::max(m, cipc_stage_ms(s, stage));
+        return m;
+    }
     cudaSetDevice(ctx->dev);
     cudaStreamSynchronize(ctx->st);
     double tot = -1;
@@ -3595,6 +3674,11 @@ double cipc_stage_ms(cipc_ctx* ctx, const char* stage)
 int64_t cipc_counter(cipc_ctx* ctx, const char* name)
 {
     if (!ctx) return -1;
+    if (ctx->multi) { // summed over the ranks
+        int64_t t = -1;
+        for (cipc_ctx* s : ctx->multi->sub) { const int64_t v = cipc_counter(s, name); if (v >= 0) t = (t < 0 ? 0 : t) + v; }
+        return t;
+    }
     auto it = ctx->ctr.find(name);
     return it == ctx->ctr.end() ? -1 : it->second;
 }
@@ -3645,3 +3729,306 @@ int cipc_test_make_pd(cipc_ctx* ctx, double* H, int n, int count)
 }
 
 } // extern "C"
+
+// ========================================================================================= multi-device context (multidev.h)
+namespace {
+// copies n int4 records between devices on the destination's stream
+void peer_copy(cipc_ctx* dst, int4* d, cipc_ctx* src, const int4* sp, size_t n)
+{
+    if (!n) return;
+    CIPC_CUDA(cudaSetDevice(dst->dev));
+    if (dst->dev == src->dev) CIPC_CUDA(cudaMemcpyAsync(d, sp, n * 16, cudaMemcpyDeviceToDevice, dst->st));
+    else CIPC_CUDA(cudaMemcpyPeerAsync(d, dst->dev, sp, src->dev, n * 16, dst->st));
+}
+template <class F>
+int multi_guard(cipc_ctx* ctx, F f)
+{
+    try { return f(); }
+    catch (const std::exception& e) { ctx->err = e.what(); return CIPC_ERR_CUDA; }
+}
+int sub_err(cipc_ctx* ctx, cipc_ctx* s, int st)
+{
+    if (st) ctx->err = s->err;
+    return st;
+}
+} // namespace
+
+extern "C" int cipc_create_multi(int ndev, const int* devices, cipc_ctx** out)
+{
+    if (!out || ndev < 1 || ndev > MAX_RANKS || !devices) return CIPC_ERR_ARG;
+    *out = nullptr;
+    std::unique_ptr<cipc_ctx> c(new cipc_ctx());
+    c->dev = devices[0];
+    c->multi.reset(new cipc_multi());
+    cipc_multi& m = *c->multi;
+    m.n = ndev;
+    for (int r = 0; r < ndev; ++r) {
+        cipc_ctx* sub = nullptr;
+        const int st = cipc_create(devices[r], r, ndev, &sub);
+        if (st != CIPC_OK) { for (cipc_ctx* q : m.sub) cipc_destroy(q); return st; }
+        m.sub.push_back(sub);
+    }
+    for (int a = 0; a < ndev; ++a) // peer access for the NVLink copies / loads between the ranks
+        for (int b = 0; b < ndev; ++b) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            if (!can) { for (cipc_ctx* q : m.sub) cipc_destroy(q); fprintf(stderr, "cipc_b200: devices %d and %d have no peer access\n", devices[a], devices[b]); return CIPC_ERR_CUDA; }
+            cudaSetDevice(devices[a]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { for (cipc_ctx* q : m.sub) cipc_destroy(q); return CIPC_ERR_CUDA; }
+            cudaGetLastError();
+        }
+    for (int r = 1; r < ndev; ++r) m.thr.emplace_back(new RankThread());
+    m.chunk.assign(ndev + 1, 0);
+    m.tripCount.assign(ndev, 0);
+    cudaSetDevice(devices[0]);
+    *out = c.release();
+    return CIPC_OK;
+}
+
+static int multi_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE, const int32_t* BE, int be_stride, int nBT, const int32_t* BT,
+    int bt_stride, int nRod, const int32_t codim[2], const uint8_t* dbc, int nNnx, const int32_t* nnxPairs, const double* BNArea, const double* BEArea,
+    const double* BTArea)
+{
+    cipc_multi& m = *ctx->multi;
+    // the content check is the same on every rank: ask rank 0 first, fan the upload out only when something changed
+    const u64 before = m.sub[0]->topoHash;
+    int st = cipc_set_topology(m.sub[0], nV, nBN, BN, nBE, BE, be_stride, nBT, BT, bt_stride, nRod, codim, dbc, nNnx, nnxPairs, BNArea, BEArea, BTArea);
+    if (st) return sub_err(ctx, m.sub[0], st);
+    bool same = m.sub[0]->topoHash == before;
+    for (int r = 1; r < m.n && same; ++r) same = m.sub[r]->topoHash == before && m.sub[r]->T.nV == nV;
+    if (same) return CIPC_OK;
+    for (int r = 1; r < m.n; ++r) {
+        st = cipc_set_topology(m.sub[r], nV, nBN, BN, nBE, BE, be_stride, nBT, BT, bt_stride, nRod, codim, dbc, nNnx, nnxPairs, BNArea, BEArea, BTArea);
+        if (st) return sub_err(ctx, m.sub[r], st);
+    }
+    ctx->T.nV = nV;
+    return CIPC_OK;
+}
+// which: 0 positions, 1 rest positions, 2 search direction.  Rank 0 takes the host array (content-tagged: an unchanged array is
+// not sent), the other ranks receive it over NVLink.
+static int multi_upload(cipc_ctx* ctx, int which, const double* src, int stride_bytes)
+{
+    cipc_multi& m = *ctx->multi;
+    return multi_guard(ctx, [&]() {
+        cipc_ctx* c0 = m.sub[0];
+        const u64 v0 = c0->xVersion, t0 = which == 0 ? c0->tagX : (which == 1 ? c0->tagX0 : c0->tagP);
+        int st = which == 0 ? cipc_set_positions(c0, src, stride_bytes) : (which == 1 ? cipc_set_rest_positions(c0, src, stride_bytes) : cipc_set_search_dir(c0, src));
+        if (st) return sub_err(ctx, c0, st);
+        const u64 t1 = which == 0 ? c0->tagX : (which == 1 ? c0->tagX0 : c0->tagP);
+        bool changed = t1 != t0 || t1 == 0 || c0->xVersion != v0;
+        for (int r = 1; r < m.n && !changed; ++r) {
+            cipc_ctx* c = m.sub[r];
+            changed = (which == 0 ? c->tagX : (which == 1 ? c->tagX0 : c->tagP)) != t1;
+        }
+        if (!changed) return (int)CIPC_OK;
+        CIPC_CUDA(cudaSetDevice(c0->dev));
+        CIPC_CUDA(cudaStreamSynchronize(c0->st));
+        const size_t bytes = (size_t)c0->T.nV * 32;
+        for (int r = 1; r < m.n; ++r) {
+            cipc_ctx* c = m.sub[r];
+            need(c->T.nV == c0->T.nV && c->T.nV > 0, "topology not set");
+            CIPC_CUDA(cudaSetDevice(c->dev));
+            DevBuf<double4>& d = which == 0 ? c->X : (which == 1 ? c->X0 : c->P);
+            const DevBuf<double4>& s0 = which == 0 ? c0->X : (which == 1 ? c0->X0 : c0->P);
+            d.reserve(c->T.nV, c->st);
+            CIPC_CUDA(cudaMemcpyPeerAsync(d.p, c->dev, s0.p, c0->dev, bytes, c->st));
+            if (which == 0) { c->haveX = true; c->tagX = t1; ++c->xVersion; }
+            else if (which == 1) {
+                c->restLen2.reserve(std::max(c->T.nBE, 1), c->st);
+                if (c->T.nBE) CIPC_LAUNCH(k_rest_len2, div_up(c->T.nBE, TB), TB, 0, c->st, c->X0.p, c->BE.p, c->T.nBE, c->restLen2.p);
+                c->haveX0 = true; c->tagX0 = t1;
+            }
+            else { c->haveP = true; c->tagP = t1; }
+        }
+        CIPC_CUDA(cudaSetDevice(c0->dev));
+        return (int)CIPC_OK;
+    });
+}
+static int multi_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickness, int* nC_out)
+{
+    cipc_multi& m = *ctx->multi;
+    return multi_guard(ctx, [&]() {
+        const int N = m.n;
+        std::vector<int> nr(N, 0);
+        int st = m.run_all([&](int r) {
+            const int e = cipc_constraint_set(m.sub[r], elastic, dHat2, thickness, &nr[r]);
+            if (e == CIPC_OK) { cudaSetDevice(m.sub[r]->dev); cudaStreamSynchronize(m.sub[r]->st); }
+            return e;
+        });
+        if (st) { for (cipc_ctx* s : m.sub) if (!s->err.empty()) ctx->err = s->err; return st; }
+        cipc_ctx* c0 = m.sub[0];
+        // ---- PP / PE stencils of all ranks -> device 0 -> merged with their multiplicities
+        size_t nPP = 0, nPass = 0;
+        for (int r = 0; r < N; ++r) { nPP += (size_t)nr[r] - m.sub[r]->nPassLast; nPass += m.sub[r]->nPassLast; }
+        u32 nM = 0;
+        CIPC_CUDA(cudaSetDevice(c0->dev));
+        if (nPP) {
+            c0->raw.reserve(nPP + 1, c0->st);
+            size_t o = 0;
+            for (int r = 0; r < N; ++r) {
+                const size_t k = (size_t)nr[r] - m.sub[r]->nPassLast;
+                peer_copy(c0, c0->raw.p + o, m.sub[r], m.sub[r]->cs.p + m.sub[r]->nPassLast, k);
+                o += k;
+            }
+            CIPC_CUDA(cudaSetDevice(c0->dev));
+            u32 nSlots = 1024;
+            while (nSlots < 2 * nPP) nSlots <<= 1;
+            c0->slots.reserve(nSlots, c0->st); c0->slotCnt.reserve(nSlots, c0->st);
+            m.mergeTmp.reserve(nPP + 1, c0->st);
+            CIPC_CUDA(cudaMemsetAsync(c0->slots.p, 0xff, (size_t)nSlots * 4, c0->st));
+            CIPC_CUDA(cudaMemsetAsync(c0->slotCnt.p, 0, (size_t)nSlots * 4, c0->st));
+            CIPC_CUDA(cudaMemsetAsync(c0->counters.p + 6, 0, 4, c0->st));
+            CIPC_LAUNCH(k_dedup_insert_w, div_up(nPP, TB), TB, 0, c0->st, c0->raw.p, (u32)nPP, c0->slots.p, c0->slotCnt.p, nSlots - 1);
+            CIPC_LAUNCH(k_dedup_emit, div_up(nSlots, TB), TB, 0, c0->st, c0->raw.p, c0->slots.p, c0->slotCnt.p, nSlots, m.mergeTmp.p, c0->counters.p + 6);
+            CIPC_CUDA(cudaMemcpyAsync(&nM, c0->counters.p + 6, 4, cudaMemcpyDeviceToHost, c0->st));
+            CIPC_CUDA(cudaStreamSynchronize(c0->st));
+        }
+        // ---- global list G = [pass_0 | ... | pass_{N-1} | merged PP/PE], re-cut into N contiguous chunks
+        const size_t nG = nPass + nM;
+        if (nG > 0x7fffffffull) throw std::runtime_error("constraint set exceeds the reference's 32-bit container sizes");
+        struct Seg { cipc_ctx* c; const int4* p; size_t n, off; };
+        std::vector<Seg> segs;
+        size_t off = 0;
+        for (int r = 0; r < N; ++r) { segs.push_back({m.sub[r], m.sub[r]->cs.p, m.sub[r]->nPassLast, off}); off += m.sub[r]->nPassLast; }
+        segs.push_back({c0, m.mergeTmp.p, nM, off});
+        for (int r = 0; r <= N; ++r) m.chunk[r] = nG * (size_t)r / (size_t)N;
+        for (int r = 0; r < N; ++r) {
+            cipc_ctx* c = m.sub[r];
+            const size_t a = m.chunk[r], b = m.chunk[r + 1];
+            CIPC_CUDA(cudaSetDevice(c->dev));
+            c->raw.reserve(b - a + 1, c->st); // the chunk is assembled in `raw` and swapped in below
+            for (const Seg& sg : segs) {
+                const size_t lo = std::max(a, sg.off), hi = std::min(b, sg.off + sg.n);
+                if (hi > lo) peer_copy(c, c->raw.p + (lo - a), sg.c, sg.p + (lo - sg.off), hi - lo);
+            }
+        }
+        for (int r = 0; r < N; ++r) { CIPC_CUDA(cudaSetDevice(m.sub[r]->dev)); CIPC_CUDA(cudaStreamSynchronize(m.sub[r]->st)); }
+        const double dHat = std::sqrt(dHat2) + thickness, dHat2o = dHat * dHat;
+        for (int r = 0; r < N; ++r) {
+            cipc_ctx* c = m.sub[r];
+            const u32 n = (u32)(m.chunk[r + 1] - m.chunk[r]);
+            CIPC_CUDA(cudaSetDevice(c->dev));
+            std::swap(c->cs.p, c->raw.p); std::swap(c->cs.cap, c->raw.cap);
+            c->nC = n;
+            c->info.reserve((size_t)n + 1, c->st);
+            if (n) CIPC_LAUNCH(k_fill_info, div_up(n, TB), TB, 0, c->st, c->info.p, n, 1.0, dHat2o);
+            c->infoUniform = true; c->infoW = 1.0; c->infoD = dHat2o;
+            c->ctr["constraints"] = n;
+        }
+        CIPC_CUDA(cudaSetDevice(c0->dev));
+        if (nC_out) *nC_out = (int)nG;
+        return (int)CIPC_OK;
+    });
+}
+static int multi_get_constraints(cipc_ctx* ctx, int32_t* cs, double* info, int info_stride_bytes)
+{
+    cipc_multi& m = *ctx->multi;
+    return m.run_all([&](int r) {
+        const size_t a = m.chunk[r];
+        return sub_err(ctx, m.sub[r], cipc_get_constraints_strided(m.sub[r], cs ? cs + 4 * a : nullptr,
+            info ? (double*)((char*)info + a * (size_t)info_stride_bytes) : nullptr, info_stride_bytes));
+    });
+}
+static int multi_set_constraints(cipc_ctx* ctx, const int32_t* cs, const double* info, int info_stride_bytes, int nC)
+{
+    cipc_multi& m = *ctx->multi;
+    if (nC < 0) return CIPC_ERR_ARG;
+    for (int r = 0; r <= m.n; ++r) m.chunk[r] = (size_t)nC * (size_t)r / (size_t)m.n;
+    return m.run_all([&](int r) {
+        const size_t a = m.chunk[r], n = m.chunk[r + 1] - a;
+        return sub_err(ctx, m.sub[r], cipc_set_constraints_strided(m.sub[r], cs ? cs + 4 * a : nullptr,
+            info ? (const double*)((const char*)info + a * (size_t)info_stride_bytes) : nullptr, info_stride_bytes, (int)n));
+    });
+}
+static int multi_barrier_energy(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* E)
+{
+    cipc_multi& m = *ctx->multi;
+    std::vector<double> e(m.n, 0.0);
+    const int st = m.run_all([&](int r) { return sub_err(ctx, m.sub[r], cipc_barrier_energy(m.sub[r], elastic, dHat2, kappa, thickness, &e[r])); });
+    if (st) return st;
+    double s = 0;
+    for (int r = 0; r < m.n; ++r) s += e[r]; // rank order: reproducible
+    *E += s;
+    return CIPC_OK;
+}
+static int multi_barrier_gradient(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, double* g, int stride)
+{
+    cipc_multi& m = *ctx->multi;
+    if (stride < 24 || stride % 8) return CIPC_ERR_ARG;
+    return multi_guard(ctx, [&]() {
+        int st = m.run_all([&](int r) {
+            const int e = cipc_barrier_gradient_dev(m.sub[r], elastic, dHat2, kappa, thickness);
+            if (e == CIPC_OK) { cudaSetDevice(m.sub[r]->dev); cudaStreamSynchronize(m.sub[r]->st); }
+            return sub_err(ctx, m.sub[r], e);
+        });
+        if (st) return st;
+        cipc_ctx* c = m.sub[0];
+        CIPC_CUDA(cudaSetDevice(c->dev));
+        const size_t n = (size_t)c->T.nV;
+        if (m.n > 1) { // device 0 sums the ranks' vectors with peer loads over NVLink
+            PeerPtrs pp;
+            pp.n = m.n - 1;
+            for (int r = 1; r < m.n; ++r) pp.p[r - 1] = m.sub[r]->g.p;
+            CIPC_LAUNCH(k_sum_peers, 592, 256, 0, c->st, c->g.p, pp, 3 * n);
+        }
+        double* h = (double*)c->pin.reserve(n * 24);
+        CIPC_CUDA(cudaMemcpyAsync(h, c->g.p, n * 24, cudaMemcpyDeviceToHost, c->st));
+        CIPC_CUDA(cudaStreamSynchronize(c->st));
+        const size_t sd = stride / 8, CH = 1 << 14;
+        HostPool::get().for_each((n + CH - 1) / CH, [&](size_t k) { // nodeAttr.g += (IPC.h:1034-1042)
+            for (size_t v = k * CH, e = std::min(n, v + CH); v < e; ++v) { g[v * sd] += h[3 * v]; g[v * sd + 1] += h[3 * v + 1]; g[v * sd + 2] += h[3 * v + 2]; }
+        });
+        return (int)CIPC_OK;
+    });
+}
+static int multi_barrier_hessian(cipc_ctx* ctx, int elastic, double dHat2, const double kappa[3], double thickness, int projectSPD, int64_t* nTrip, bool merged)
+{
+    cipc_multi& m = *ctx->multi;
+    const int st = m.run_all([&](int r) {
+        int64_t n = 0;
+        const int e = merged ? cipc_barrier_hessian_merged(m.sub[r], elastic, dHat2, kappa, thickness, projectSPD, &n)
+                             : cipc_barrier_hessian(m.sub[r], elastic, dHat2, kappa, thickness, projectSPD, &n);
+        m.tripCount[r] = n;
+        return sub_err(ctx, m.sub[r], e);
+    });
+    if (st) return st;
+    int64_t tot = 0;
+    for (int r = 0; r < m.n; ++r) tot += m.tripCount[r];
+    if (nTrip) *nTrip = tot;
+    return CIPC_OK;
+}
+static int multi_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
+{
+    cipc_multi& m = *ctx->multi;
+    std::vector<int64_t> off(m.n + 1, 0);
+    for (int r = 0; r < m.n; ++r) off[r + 1] = off[r] + m.tripCount[r];
+    return m.run_all([&](int r) { return m.tripCount[r] ? sub_err(ctx, m.sub[r], cipc_get_triplets(m.sub[r], out + off[r])) : (int)CIPC_OK; });
+}
+static int multi_step_size(cipc_ctx* ctx, int elastic, double thickness, double* step)
+{
+    cipc_multi& m = *ctx->multi;
+    std::vector<double> a(m.n, *step);
+    const int st = m.run_all([&](int r) { return sub_err(ctx, m.sub[r], cipc_step_size(m.sub[r], elastic, thickness, &a[r])); });
+    if (st) return st;
+    double v = a[0];
+    for (int r = 1; r < m.n; ++r) v = std::min(v, a[r]);
+    *step = v;
+    return CIPC_OK;
+}
+static int multi_min_dist2(cipc_ctx* ctx, double thickness, double* dist2, double* minDist2)
+{
+    cipc_multi& m = *ctx->multi;
+    if (m.chunk[m.n] == 0) return CIPC_OK; // empty set: outputs untouched (IPC.h:2253)
+    std::vector<double> v(m.n, 1e300);
+    const int st = m.run_all([&](int r) {
+        if (m.chunk[r + 1] == m.chunk[r]) return (int)CIPC_OK;
+        return sub_err(ctx, m.sub[r], cipc_min_dist2(m.sub[r], thickness, dist2 ? dist2 + m.chunk[r] : nullptr, &v[r]));
+    });
+    if (st) return st;
+    double mn = v[0];
+    for (int r = 1; r < m.n; ++r) mn = std::min(mn, v[r]);
+    *minDist2 = mn;
+    return CIPC_OK;
+}

@@ -19,7 +19,8 @@
 //
 // Reference signatures: FEM/IPC.h:19-36, 742-748, 943-948, 1258-1265, 1879-1890, 2246-2249.
 //
-// Environment knobs (read once): CIPC_DEVICE (CUDA ordinal, default 0); CIPC_TRIPLETS = merged (default) | raw.
+// Environment knobs (read once): CIPC_DEVICE (CUDA ordinal, default 0) or CIPC_DEVICES (comma-separated ordinals: all of them
+// behind this one calling thread, cipc_create_multi); CIPC_TRIPLETS = merged (default) | raw.
 //   merged: Compute_Barrier_Hessian / Compute_Friction_Hessian append ONE triplet per distinct (row, col) of their matrix --
 //           the duplicates that the only consumer of the vector, sysMtr.Construct_From_Triplet = Eigen setFromTriplets
 //           (Shell/INC_POTENTIAL.h:382, Math/CSR_MATRIX.h:49-56), would sum anyway are summed on the device (cipc_*_hessian_merged).
@@ -86,7 +87,18 @@ inline State& state()
     static State s;
     if (!s.ctx) {
         const char* dev = getenv("CIPC_DEVICE");
-        int st = cipc_create(dev ? atoi(dev) : 0, 0, 1, &s.ctx);
+        const char* devs = getenv("CIPC_DEVICES"); // "0,1,2,3": one context over several GPUs of this box (cipc_create_multi)
+        int st;
+        if (devs && *devs) {
+            std::vector<int> list;
+            for (const char* p = devs; *p;) {
+                list.push_back(atoi(p));
+                while (*p && *p != ',') ++p;
+                if (*p == ',') ++p;
+            }
+            st = cipc_create_multi((int)list.size(), list.data(), &s.ctx);
+        }
+        else st = cipc_create(dev ? atoi(dev) : 0, 0, 1, &s.ctx);
         if (st != CIPC_OK) { printf("cipc_b200: no CUDA device; the contact path has no CPU fallback\n"); exit(-1); }
         const char* tm = getenv("CIPC_TRIPLETS");
         s.merged = !(tm && std::string(tm) == "raw");

@@ -48,6 +48,16 @@ typedef struct { int32_t row, col; double val; } cipc_triplet;
 /* device: CUDA ordinal.  rank/world: this process' share of the candidate-pair work (multi-GPU:
  * one process per GPU); rank=0, world=1 for a single GPU. */
 int cipc_create(int device, int rank, int world, cipc_ctx** out);
+/* One context over ndev GPUs of one box, driven by ONE calling thread (the reference calls the path from a single thread,
+ * Shell/IMPLICIT_EULER.h:418-428): candidate pairs are partitioned by voxel slabs across the devices, helper threads overlap
+ * the ranks' host round trips, exchanges go over NVLink peer copies / peer loads (gather + merge of the PP/PE stencils,
+ * re-balancing of the constraint list into contiguous per-rank chunks, gradient sum); energy / step size / min distance are
+ * combined on the host in rank order.  Supported on such a context: cipc_set_topology, the position / rest / search-direction
+ * uploads, cipc_constraint_set, cipc_get/set_constraints[_strided], cipc_barrier_energy / _gradient / _hessian[_merged],
+ * cipc_get_triplets, cipc_step_size, cipc_min_dist2, cipc_stage_ms (slowest rank), cipc_counter (sum), cipc_sync; every other
+ * call returns CIPC_ERR_UNSUPPORTED.  Results equal the single-device context's (same constraint set as a sorted set; sums
+ * in a different but fixed order). */
+int cipc_create_multi(int ndev, const int* devices, cipc_ctx** out);
 void cipc_destroy(cipc_ctx* ctx);
 const char* cipc_last_error(cipc_ctx* ctx);
 
