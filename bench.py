@@ -47,7 +47,8 @@ WORKLOADS = {  # name -> (n, layers)
 # the CPU arms run the requested workload itself; only cfg5_4m is sampled (see the module docstring) and flagged as such
 CPU_SAMPLE = {"cfg5_4m": ("cfg5_1m", None)}
 L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB write), working set >> L2"
-PAR_NOTE = "GPU arm: candidate pairs partitioned by hash-cell ranges across n_gpus ranks; reference arm: all host cores of rank 0"
+PAR_NOTE = ("GPU arm: candidate pairs partitioned by voxel slabs across n_gpus ranks, per stage one NCCL all-reduce (gradient) and one all-gather "
+            "(energy / step / min-distance scalars); reference arm: all host cores of rank 0")
 
 
 def scene_config(name, sc):
@@ -301,28 +302,26 @@ def main():
     dHat2, xi, kappa = sc["dHat2"], sc["xi"], sc["kappa"]
     scal = multi.wrap_device_f64(ctx.dev_ptrs()["scalars"], 16, local)
 
-    def allreduce(t, op):
-        if dc is not None:
-            dc.dist.all_reduce(t, op=op)
+    gathered = torch.zeros((world, 4), dtype=torch.float64, device="cuda") if world > 1 else None
 
     def device_step():
-        """inputs resident; results stay on the device"""
+        """inputs resident; results stay on the device.  N > 1: two collectives per stage -- one all-reduce(sum) of the 3 nV
+        gradient and one all-gather of the ranks' scalars (energy partial, step, min distance), from which every rank forms
+        the complete energy (sum) and step / min distance (min)"""
         nC = ctx.constraint_set(dHat2, xi, fetch=False)
         ctx.barrier_energy_dev(dHat2, kappa, xi)
-        if dc is not None:
-            allreduce(scal[0:1], dc.dist.ReduceOp.SUM)
         # gradient and PSD-projected Hessian in one pass over the stencils (the Newton iteration evaluates them back to back);
         # the triplet stream is materialised in HBM (what a device-side solver / CSR assembly consumes)
         nTrip = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
         if dc is not None:
-            allreduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, local), dc.dist.ReduceOp.SUM)
+            dc.dist.all_reduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, local), op=dc.dist.ReduceOp.SUM)
         ctx.step_size_dev(xi, 1.0)
-        if dc is not None:
-            allreduce(scal[1:2], dc.dist.ReduceOp.MIN)
         for _ in range(2):
             ctx.min_dist2_dev(xi)
-            if dc is not None:
-                allreduce(scal[2:3], dc.dist.ReduceOp.MIN)
+        if dc is not None:
+            dc.dist.all_gather_into_tensor(gathered, scal[0:4])
+            red = torch.stack([gathered[:, 0].sum(), gathered[:, 1].min(), gathered[:, 2].min()])  # E, step, min dist2 (ordered bit pattern)
+            scal[0:3].copy_(red)
         return nC, nTrip
 
     def sync_all():
@@ -513,13 +512,29 @@ def main():
         # std::vector containers (pageable, the triplet vector and dist2 fresh per call as in INC_POTENTIAL.h:321 /
         # IMPLICIT_EULER.h:122), built through codim-ipc_b200/shim (tests/shim_harness).  When the harness travelled here its
         # number is the headline e2e; the ctypes-mirror figure stays beside it.
-        if world == 1:
+        # N > 1: the shim is ONE calling thread over all N GPUs (CIPC_DEVICES -> cipc_create_multi: slab-partitioned pairs, NVLink peer
+        # exchanges inside the library); rank 0 runs it while the other ranks have released their device buffers and wait.
+        n4_keep = ctx.counter("hessian_4pt")
+        if True:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             try:
                 import shim_scene
                 have_shim = shim_scene.present()
             except Exception:
                 have_shim = False
+            if world > 1:
+                hs = torch.tensor([1 if have_shim else 0], device="cuda")
+                dist.all_reduce(hs, op=dist.ReduceOp.MIN)
+                have_shim = bool(hs.item())
+                if have_shim:
+                    ctx.close()  # every rank frees its contact context; rank 0 re-enters through the shim on all devices
+                    del flush
+                    torch.cuda.empty_cache()
+                    sync_all()
+                    if rank == 0:
+                        os.environ["CIPC_DEVICES"] = ",".join(str(i) for i in range(world))
+                    else:
+                        have_shim = False
             if have_shim:
                 ctx.sync()
                 S = shim_scene.ShimScene(sc)
@@ -538,7 +553,8 @@ def main():
                             "min_ms": 1e3 * min(tot), "max_ms": 1e3 * max(tot),
                             "via": "compiled shim harness (tests/shim_harness/_build/libcipc_shimdrv.so): the reference's six templates called in the "
                                    "reference's own call pattern on MESH_NODE / AoSoA / std::vector containers (pageable; triplet vector and dist2 "
-                                   "freshly allocated per call), CIPC_TRIPLETS=merged",
+                                   "freshly allocated per call), CIPC_TRIPLETS=merged" + ("" if world == 1 else
+                                   ", CIPC_DEVICES=0..%d: one calling thread over all %d GPUs (cipc_create_multi)" % (world - 1, world)),
                             "calls_ms": {k: round(1e3 * v / args.steps, 3) for k, v in per.items()}})
                 # The fresh std::vector<Eigen::Triplet> of every Hessian evaluation (INC_POTENTIAL.h:321) costs ~30 ms of page faults
                 # at this size under glibc's default policy (allocations > 32 MB are mmap'ed and returned on free).  A process that
@@ -575,6 +591,8 @@ def main():
             e2e["hessian_as_csr_bytes"] = int(nnz * 12 + (3 * nV + 1) * 4)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    if dist is not None:
+        dist.barrier()
 
     if rank != 0:
         if dist is not None:
@@ -589,7 +607,7 @@ def main():
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    n4 = ctx.counter("hessian_4pt")
+    n4 = n4_keep if not args.no_e2e else ctx.counter("hessian_4pt")
     per_unit = 144 * 16 + 16 + 16 + 4 + 4 + 4 * 32
     alg_bytes = n4 * per_unit
     achieved = alg_bytes / (kH * 1e-3) / 1e9 if kH and kH > 0 else None

@@ -1569,6 +1569,8 @@ struct cipc_ctx {
     DevBuf<double4> X, X0, P, Xprev;
     bool haveX = false, haveX0 = false, haveP = false, haveXprev = false;
     u64 tagX = 0, tagX0 = 0, tagP = 0, tagXn = 0; // content tags of the resident uploads (upload_vec3); 0 = unknown
+    struct SlabCache { bool valid = false; int age = 0, gx = 0, gy = 0, gz = 0, nP = 0; Slab sl{0, 0, 1 << 30}; };
+    SlabCache slabCache[2]; // [0] constraint-set grid, [1] swept step-size grid (multi-GPU slab bounds, build_cell_lists)
     u64 xVersion = 1, edgeLenVersion = 0; // bumped whenever the resident positions or the topology change
     double edgeLenCached = 0.0;
     bool edgeLenPending = false;
@@ -1771,15 +1773,6 @@ struct HashInfo {
     u32 nEntries = 0, nCells = 0, maxTasks = 0, qch = 16;
 };
 
-// sum of partials helper: returns value on host
-double reduce_to_host(cipc_ctx* c, double scale)
-{
-    CIPC_LAUNCH(k_final_sum, 1, RED_BT, 0, c->st, c->partial.p, RED_GRID, c->scal.p + 3, scale);
-    double v;
-    CIPC_CUDA(cudaMemcpyAsync(&v, c->scal.p + 3, sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    CIPC_CUDA(cudaStreamSynchronize(c->st));
-    return v;
-}
 // mean boundary-edge length of the resident positions; cached until the positions (or the topology) change, so the
 // step-size pass that follows a constraint-set pass on the same X saves the reduction and its host round trip.
 // edge_len_begin launches the reduction and its copy without waiting; the value is valid after the next stream sync.
@@ -1819,12 +1812,21 @@ void bbox_to_host(cipc_ctx* c, const double4* P, double alpha, double* mn, doubl
     }
 }
 // after boxes + counts are in place: scan, emit, sort, cell table
-void build_cell_lists(cipc_ctx* c, HashInfo& H)
+void build_cell_lists(cipc_ctx* c, HashInfo& H, int which)
 {
     const Topo& T = c->T;
     const int nP = T.nBN + T.nBE + T.nBT;
     Slab sl{0, 0, 1 << 30};
-    if (c->world > 1) {
+    cipc_ctx::SlabCache& sc = c->slabCache[which];
+    if (c->world > 1 && sc.valid && sc.gx == H.G.gx && sc.gy == H.G.gy && sc.gz == H.G.gz && sc.nP == nP && sc.age < 8) {
+        // The slab bounds only balance the load (any bounds give the same global candidate set, every rank uses the same
+        // ones because every rank sees the same inputs); positions move little between Newton iterations, so the bounds of
+        // the previous build on the same grid are kept for a few calls: no histogram pass, no host round trip.
+        ++sc.age;
+        sl = sc.sl;
+        CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
+    }
+    else if (c->world > 1) {
         // this rank's slab along the axis with the most voxel layers, balanced on the number of hash entries
         const int gd[3] = {H.G.gx, H.G.gy, H.G.gz};
         sl.axis = (gd[0] >= gd[1] && gd[0] >= gd[2]) ? 0 : (gd[1] >= gd[2] ? 1 : 2);
@@ -1848,6 +1850,7 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H)
         sl.s0 = bound(c->rank);
         sl.s1 = bound(c->rank + 1);
         CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
+        sc.valid = true; sc.age = 0; sc.gx = H.G.gx; sc.gy = H.G.gy; sc.gz = H.G.gz; sc.nP = nP; sc.sl = sl;
     }
     const long gridCells = (long)H.G.gx * H.G.gy * H.G.gz;
     static const bool forceSort = getenv("CIPC_HASH_SORT") != nullptr; // cross-check switch: radix-sort path for every grid
@@ -2046,14 +2049,22 @@ int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
         // span rule (SPATIAL_HASH.h:466-482).  The sum is a fixed-tree reduction; when the rule
         // fires the step is biased down by 4e-13 relative so that it never exceeds the sequential
         // CPU sum's result.
+        // one host round trip for the search-direction reduction AND the swept bounding box: the box is launched for the
+        // unshrunk step before the span rule is known and redone only when the rule fires (rare)
         CIPC_LAUNCH(k_psize_partial, RED_GRID, RED_BT, 0, c->st, c->P.p, c->BN.p, T.nBN, c->partial.p);
-        const double pSize = reduce_to_host(c, 1.0 / ((double)T.nBN * 3.0));
+        CIPC_LAUNCH(k_final_sum, 1, RED_BT, 0, c->st, c->partial.p, RED_GRID, c->scal.p + 3, 1.0 / ((double)T.nBN * 3.0));
+        double* hp = (double*)((char*)c->pinScal.reserve(128) + 64);
+        CIPC_CUDA(cudaMemcpyAsync(hp, c->scal.p + 3, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        double mn[3], mx[3];
+        bbox_to_host(c, c->P.p, alpha, mn, mx); // synchronises the stream
+        const double pSize = *hp;
         double voxelSize = 1.0;
         if (T.nBE) voxelSize *= edge_len_end(c);
         const double spanSize = alpha * pSize / voxelSize;
-        if (spanSize > 1) alpha = (alpha / spanSize) * (1.0 - 4e-13);
-        double mn[3], mx[3];
-        bbox_to_host(c, c->P.p, alpha, mn, mx);
+        if (spanSize > 1) {
+            alpha = (alpha / spanSize) * (1.0 - 4e-13);
+            bbox_to_host(c, c->P.p, alpha, mn, mx);
+        }
         for (int d = 0; d < 3; ++d) { mn[d] -= thickness / 2; mx[d] += thickness / 2; }
         if (!size_grid(mn, mx, voxelSize, H.G, true)) return CIPC_ERR_GRID;
         const int nP = T.nBN + T.nBE + T.nBT;
@@ -2066,7 +2077,7 @@ int do_step_size(cipc_ctx* c, int elastic, double thickness, double stepIn)
             c->nodeFine.p);
         CIPC_LAUNCH(k_prim_boxes_ccd, div_up(nP, TB), TB, 0, c->st, T, c->nodeLo.p, c->nodeHi.p, c->nodeFine.p, c->boxLo.p, c->boxHi.p, c->fine.p,
             c->cnt.p);
-        build_cell_lists(c, H);
+        build_cell_lists(c, H, 1);
     }
     u32 counts[4];
     {
@@ -2729,6 +2740,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         c->topoHash = h;
         c->haveX = c->haveX0 = c->haveP = c->haveXn = c->haveXprev = false;
         c->tagX = c->tagX0 = c->tagP = c->tagXn = 0;
+        c->slabCache[0].valid = c->slabCache[1].valid = false;
         ++c->xVersion;
         c->nC = 0;
         c->nF = 0;
@@ -2804,7 +2816,7 @@ int cipc_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double thickne
             const int nP = T.nBN + T.nBE + T.nBT;
             c->boxLo.reserve(nP, c->st); c->boxHi.reserve(nP, c->st); c->cnt.reserve(nP, c->st); c->fine.reserve(nP, c->st);
             CIPC_LAUNCH(k_boxes_ccs, div_up(nP, TB), TB, 0, c->st, T, c->X.p, H.G, r, c->boxLo.p, c->boxHi.p, c->fine.p, c->cnt.p);
-            build_cell_lists(c, H);
+            build_cell_lists(c, H, 0);
         }
         u32 counts[4];
         {
@@ -3863,36 +3875,54 @@ static int multi_constraint_set(cipc_ctx* ctx, int elastic, double dHat2, double
         size_t nPP = 0, nPass = 0;
         for (int r = 0; r < N; ++r) { nPP += (size_t)nr[r] - m.sub[r]->nPassLast; nPass += m.sub[r]->nPassLast; }
         u32 nM = 0;
+        std::vector<u32> ownCnt(N, 0), ownBase(N + 1, 0);
         CIPC_CUDA(cudaSetDevice(c0->dev));
         if (nPP) {
             c0->raw.reserve(nPP + 1, c0->st);
+            RankOffsets ro;
+            ro.n = N;
             size_t o = 0;
             for (int r = 0; r < N; ++r) {
                 const size_t k = (size_t)nr[r] - m.sub[r]->nPassLast;
+                ro.off[r] = (u32)o;
                 peer_copy(c0, c0->raw.p + o, m.sub[r], m.sub[r]->cs.p + m.sub[r]->nPassLast, k);
                 o += k;
             }
+            ro.off[N] = (u32)o;
             CIPC_CUDA(cudaSetDevice(c0->dev));
             u32 nSlots = 1024;
             while (nSlots < 2 * nPP) nSlots <<= 1;
             c0->slots.reserve(nSlots, c0->st); c0->slotCnt.reserve(nSlots, c0->st);
             m.mergeTmp.reserve(nPP + 1, c0->st);
+            m.ownerDev.reserve(2 * MAX_RANKS + 2, c0->st);
             CIPC_CUDA(cudaMemsetAsync(c0->slots.p, 0xff, (size_t)nSlots * 4, c0->st));
             CIPC_CUDA(cudaMemsetAsync(c0->slotCnt.p, 0, (size_t)nSlots * 4, c0->st));
-            CIPC_CUDA(cudaMemsetAsync(c0->counters.p + 6, 0, 4, c0->st));
+            CIPC_CUDA(cudaMemsetAsync(m.ownerDev.p, 0, (2 * MAX_RANKS + 2) * 4, c0->st));
             CIPC_LAUNCH(k_dedup_insert_w, div_up(nPP, TB), TB, 0, c0->st, c0->raw.p, (u32)nPP, c0->slots.p, c0->slotCnt.p, nSlots - 1);
-            CIPC_LAUNCH(k_dedup_emit, div_up(nSlots, TB), TB, 0, c0->st, c0->raw.p, c0->slots.p, c0->slotCnt.p, nSlots, m.mergeTmp.p, c0->counters.p + 6);
-            CIPC_CUDA(cudaMemcpyAsync(&nM, c0->counters.p + 6, 4, cudaMemcpyDeviceToHost, c0->st));
+            // merged stencils grouped by owner rank: count, then emit at the owners' bases
+            CIPC_LAUNCH(k_dedup_emit_owned<0>, div_up(nSlots, TB), TB, 0, c0->st, c0->raw.p, c0->slots.p, c0->slotCnt.p, nSlots, ro, (const u32*)nullptr,
+                m.ownerDev.p, (int4*)nullptr);
+            CIPC_CUDA(cudaMemcpyAsync(ownCnt.data(), m.ownerDev.p, (size_t)N * 4, cudaMemcpyDeviceToHost, c0->st));
+            CIPC_CUDA(cudaStreamSynchronize(c0->st));
+            for (int r = 0; r < N; ++r) ownBase[r + 1] = ownBase[r] + ownCnt[r];
+            nM = ownBase[N];
+            CIPC_CUDA(cudaMemcpyAsync(m.ownerDev.p + MAX_RANKS + 1, ownBase.data(), (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, c0->st));
+            CIPC_CUDA(cudaMemsetAsync(m.ownerDev.p, 0, (size_t)N * 4, c0->st));
+            CIPC_LAUNCH(k_dedup_emit_owned<1>, div_up(nSlots, TB), TB, 0, c0->st, c0->raw.p, c0->slots.p, c0->slotCnt.p, nSlots, ro,
+                (const u32*)(m.ownerDev.p + MAX_RANKS + 1), m.ownerDev.p, m.mergeTmp.p);
             CIPC_CUDA(cudaStreamSynchronize(c0->st));
         }
-        // ---- global list G = [pass_0 | ... | pass_{N-1} | merged PP/PE], re-cut into N contiguous chunks
+        // ---- global list G = [pass_0 | merged_0 | pass_1 | merged_1 | ...] (merged_r: the merged PP/PE stencils rank r owns),
+        // re-cut into N contiguous chunks
         const size_t nG = nPass + nM;
         if (nG > 0x7fffffffull) throw std::runtime_error("constraint set exceeds the reference's 32-bit container sizes");
         struct Seg { cipc_ctx* c; const int4* p; size_t n, off; };
         std::vector<Seg> segs;
         size_t off = 0;
-        for (int r = 0; r < N; ++r) { segs.push_back({m.sub[r], m.sub[r]->cs.p, m.sub[r]->nPassLast, off}); off += m.sub[r]->nPassLast; }
-        segs.push_back({c0, m.mergeTmp.p, nM, off});
+        for (int r = 0; r < N; ++r) {
+            segs.push_back({m.sub[r], m.sub[r]->cs.p, m.sub[r]->nPassLast, off}); off += m.sub[r]->nPassLast;
+            segs.push_back({c0, m.mergeTmp.p + ownBase[r], ownCnt[r], off}); off += ownCnt[r];
+        }
         for (int r = 0; r <= N; ++r) m.chunk[r] = nG * (size_t)r / (size_t)N;
         for (int r = 0; r < N; ++r) {
             cipc_ctx* c = m.sub[r];

@@ -8,10 +8,11 @@
 // Exchanges stay on NVLink (peer copies / peer loads, no host staging):
 //   constraint set : PT / EE / mollified stencils are unique to the rank that enumerated the pair.  The PP / PE stencils every
 //                    rank de-duplicated locally are gathered on device 0 and merged with their multiplicities (IPC.h:599-654
-//                    keys on the raw tuple, the same key can come from pairs of different slabs).  The global list
-//                    G = [rank 0's | rank 1's | ... | merged PP/PE] is then re-cut into N equal CONTIGUOUS chunks, one
-//                    per rank (peer copies), so the barrier terms are balanced and every rank's outputs (constraints,
-//                    dist2, triplets) are one contiguous slice of the caller's containers.
+//                    keys on the raw tuple, the same key can come from pairs of different slabs); a merged stencil is owned by
+//                    the rank whose record claimed it.  The global list G = [rank 0's | rank 0's merged PP/PE | rank 1's | ...]
+//                    is then re-cut into N equal CONTIGUOUS chunks, one per rank (peer copies), so the barrier terms are
+//                    balanced, every rank's outputs (constraints, dist2, triplets) are one contiguous slice of the caller's
+//                    containers, and the chunks stay aligned with the voxel slabs (few Hessian blocks shared between ranks).
 //   energy / step / min distance : one scalar per rank, combined on the host in rank order.
 //   gradient       : rank 0 sums the ranks' 3 nV vectors with peer loads (k_sum_peers), one D2H.
 //   Hessian        : every rank delivers the (merged) triplets of its chunk into its slice of the caller's vector; entries
@@ -49,6 +50,28 @@ __global__ void k_dedup_insert_w(const int4* __restrict__ raw, u32 n, u32* slots
         const int4 o = raw[prev];
         if (o.x == k.x && o.y == k.y && o.z == k.z) { atomicAdd(&slotCnt[h], w); return; }
         h = (h + 1) & mask;
+    }
+}
+
+// Emission of the merged PP / PE stencils grouped by OWNER rank = the rank whose record claimed the hash slot (rankOff: offsets
+// of the ranks' records in the gathered list).  PASS 0 counts per owner, PASS 1 writes at ownerBase[o] + running counter: the
+// global list then reads [rank 0's stencils | rank 0's merged PP/PE | rank 1's ... ], so the re-cut chunks stay aligned with the
+// ranks' voxel slabs and few 3x3 Hessian blocks are shared between ranks.
+struct RankOffsets { u32 off[MAX_RANKS + 1]; int n; };
+template <int PASS>
+__global__ void k_dedup_emit_owned(const int4* __restrict__ raw, const u32* __restrict__ slots, const u32* __restrict__ slotCnt, u32 nSlots,
+    RankOffsets ro, const u32* __restrict__ ownerBase, u32* __restrict__ ownerCnt, int4* __restrict__ out)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSlots) return;
+    const u32 r = slots[s];
+    if (r == 0xffffffffu) return;
+    int o = 0;
+    while (o + 1 < ro.n && r >= ro.off[o + 1]) ++o;
+    const u32 k = atomicAdd(&ownerCnt[o], 1u);
+    if (PASS == 1) {
+        const int4 q = raw[r];
+        out[ownerBase[o] + k] = make_int4(q.x, q.y, q.z, -(int)slotCnt[s]);
     }
 }
 
@@ -104,6 +127,7 @@ struct cipc_multi {
     std::vector<size_t> chunk;                          // n + 1 offsets of the ranks' chunks in the global constraint list
     std::vector<int64_t> tripCount;                     // triplets of the last Hessian per rank
     cipc::DevBuf<int4> mergeTmp;                        // device 0: merged PP / PE stencils
+    cipc::DevBuf<cipc::u32> ownerDev;                   // device 0: per-owner counters [0, MAX_RANKS] and bases [MAX_RANKS + 1, ...]
     // runs f(r) for every rank (rank 0 on the calling thread) and returns the first non-OK status
     int run_all(const std::function<int(int)>& f)
     {
