@@ -287,6 +287,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_pg = dist.new_group(backend="gloo")  # host-side waits that must not occupy the GPUs (a NCCL barrier spins in a kernel)
     dc = multi.DistContact() if world > 1 else None
 
     sc = make_scene(args.workload)
@@ -508,6 +509,21 @@ def main():
                "raw_triplets": {"value": raw_ms, "unit": "ms", "d2h_bytes_per_step": raw_d2h, "calls_ms": raw_calls,
                                 "note": "the reference's exact 144/81/36 triplets per stencil (%d triplets = %d B), crossing PCIe as %d B of factors "
                                         "and expanded by the host cores (CIPC_TRIPLETS=raw in the shim)" % (raw_n, raw_n * 16, raw_pcie)}}
+        # the same Hessian delivered as CSR assembled on the device (SURVEY 8(f)-2) instead of 16-byte triplets: what an
+        # integration that feeds the solver's A->p/i/x directly would pay (reported beside e2e, not part of it)
+        if csr:
+            rp_h = pin((3 * nV + 1,), torch.int32); ci_h = pin((csr["nnz"] + 1024,), torch.int32); cv_h = pin((csr["nnz"] + 1024,), torch.float64)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ctx.set_positions(X4)
+                ctx.csr_begin(); ctx.barrier_hessian_dev(dHat2, kappa, xi, True); ctx.csr_add()
+                nnz = ctx.csr_finish(fetch=False)
+                ctx._ck(ctx.L.cipc_get_csr(ctx.h, rp_h.ctypes.data_as(C.POINTER(C.c_int32)), ci_h.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           cv_h.ctypes.data_as(C.POINTER(C.c_double))))
+                ts.append(1e3 * (time.perf_counter() - t0))
+            e2e["hessian_as_csr_ms"] = round(min(ts), 3)
+            e2e["hessian_as_csr_bytes"] = int(nnz * 12 + (3 * nV + 1) * 4)
         # ---- the same stage through the COMPILED shim: the reference's driver translation unit on its real MESH_NODE / AoSoA /
         # std::vector containers (pageable, the triplet vector and dist2 fresh per call as in INC_POTENTIAL.h:321 /
         # IMPLICIT_EULER.h:122), built through codim-ipc_b200/shim (tests/shim_harness).  When the harness travelled here its
@@ -536,7 +552,8 @@ def main():
                     else:
                         have_shim = False
             if have_shim:
-                ctx.sync()
+                if world == 1:
+                    ctx.sync()
                 S = shim_scene.ShimScene(sc)
                 tot, per = [], {}
                 for i in range(max(1, args.warmup - 1) + args.steps):
@@ -574,25 +591,10 @@ def main():
                 except Exception as ex:  # noqa: BLE001 -- a side measurement must not take the bench line down
                     e2e["with_malloc_reuse"] = {"error": str(ex)}
                 del S
-        # the same Hessian delivered as CSR assembled on the device (SURVEY 8(f)-2) instead of 16-byte triplets: what an
-        # integration that feeds the solver's A->p/i/x directly would pay (reported beside e2e, not part of it)
-        if csr:
-            rp_h = pin((3 * nV + 1,), torch.int32); ci_h = pin((csr["nnz"] + 1024,), torch.int32); cv_h = pin((csr["nnz"] + 1024,), torch.float64)
-            ts = []
-            for _ in range(3):
-                t0 = time.perf_counter()
-                ctx.set_positions(X4)
-                ctx.csr_begin(); ctx.barrier_hessian_dev(dHat2, kappa, xi, True); ctx.csr_add()
-                nnz = ctx.csr_finish(fetch=False)
-                ctx._ck(ctx.L.cipc_get_csr(ctx.h, rp_h.ctypes.data_as(C.POINTER(C.c_int32)), ci_h.ctypes.data_as(C.POINTER(C.c_int32)),
-                                           cv_h.ctypes.data_as(C.POINTER(C.c_double))))
-                ts.append(1e3 * (time.perf_counter() - t0))
-            e2e["hessian_as_csr_ms"] = round(min(ts), 3)
-            e2e["hessian_as_csr_bytes"] = int(nnz * 12 + (3 * nV + 1) * 4)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=host_pg)  # the ranks that released their GPU for rank 0's multi-device shim run wait here on the host
 
     if rank != 0:
         if dist is not None:
