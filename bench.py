@@ -619,6 +619,27 @@ def main():
             "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
             "note": "write-dominated stream co-limited by the FP64 pipe: the same launch runs the 5x5 Jacobi PSD projection of every stencil "
                     "(~6K fp64 instructions each); the expansion-only kernel it replaces runs at 0.98 of the copy peak (stages_ms.barrier_H_expand_only)"}
+    # FP64 side of the same kernel (it is co-limited): fp64 thread instructions per PT/EE stencil counted by ncu on this build
+    # (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r2_fp64_ops_k_hessian_fused.csv) against the
+    # non-tensor FP64 FMA rate measured on THIS box by tools/fp64_fma_probe (dependent DFMA chains, CUDA events)
+    FP64_OPS_4PT = {"dfma": 1756, "dmul": 1283, "dadd": 372}
+    fp64_peak, fp64_src = 34.2, "recorded on this pool's B200 (tools/fp64_fma_probe, 2026-10-17)"
+    probe = os.path.join(ROOT, "tools", "fp64_fma_probe")
+    if os.path.exists(probe) and world == 1:
+        try:
+            pj = json.loads(subprocess.run([probe, str(local)], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1])
+            fp64_peak, fp64_src = float(pj["fp64_tflops"]), "tools/fp64_fma_probe run in this process' job: %s" % pj["how"]
+        except Exception:
+            pass
+    if kH and kH > 0:
+        flops = n4 * (2 * FP64_OPS_4PT["dfma"] + FP64_OPS_4PT["dmul"] + FP64_OPS_4PT["dadd"])
+        slots = n4 * sum(FP64_OPS_4PT.values())
+        roof_fp64 = {"bound": "fp64", "kernel": "k_hessian_fused<0>", "achieved": flops / (kH * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": flops / (kH * 1e-3) / 1e12 / fp64_peak,
+                     "pipe_frac": 2.0 * slots / (kH * 1e-3) / 1e12 / fp64_peak,  # every fp64 instruction occupies one FMA issue slot
+                     "fp64_thread_instructions_per_unit": FP64_OPS_4PT, "peak_source": fp64_src}
+    else:
+        roof_fp64 = None
     tr_path = os.path.join(ROOT, "profiles", "traffic_k_hessian_fused.json")
     if os.path.exists(tr_path):
         try:
@@ -649,7 +670,7 @@ def main():
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": scene_config(args.workload, sc),
             "counts": {"constraints_rank0": int(nC), "triplets_rank0": int(nTrip), "world": world},
-            "roofline": roof, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": roof, "roofline_fp64": roof_fp64, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters,
             "friction_stages_ms": friction, "csr_stages_ms": csr}
     if args.stage_report:

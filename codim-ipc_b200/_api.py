@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcipc_b200.so")
+LIB_PATH = os.environ.get("CIPC_LIB") or os.path.join(_HERE, "libcipc_b200.so")  # CIPC_LIB: an experimental build of the same library
 
 CIPC_OK, CIPC_ERR_CUDA, CIPC_ERR_NONPOSITIVE_DIST, CIPC_ERR_ZERO_STEP, CIPC_ERR_ARG, CIPC_ERR_GRID, CIPC_ERR_UNSUPPORTED = range(7)
 

@@ -1316,6 +1316,9 @@ constexpr int FUSED_BD = 128;
 #ifndef FUSED_MINB
 #define FUSED_MINB 4
 #endif
+#ifndef FUSED_STASH
+#define FUSED_STASH 1
+#endif
 template <int CLS> struct FusedShape {
     static constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, YD = NY * NN;
     static constexpr int YS = (YD % 2 == 0) ? YD + 1 : YD; // odd stride: conflict-free 8-byte accesses, one stencil per lane
@@ -1365,7 +1368,7 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
             double* Y = sY + threadIdx.x * YS; // the factor routines write every entry exactly once: straight into the thread's slot
             if (CLS == 0) {
                 const dv3 x[4] = {ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), ldd(X, s.v[3])};
-                hess4_factor(s.kind == K_EE, x, alpha, beta, Y);
+                hess4_factor<FUSED_STASH != 0>(s.kind == K_EE, x, alpha, beta, Y); // the slot doubles as the parking space of the iteration
             }
             else if (CLS == 1) hess_pe_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), ldd(X, s.v[2]), alpha, beta, Y);
             else hess_pp_factor(ldd(X, s.v[0]), ldd(X, s.v[1]), alpha, beta, Y);
@@ -3060,8 +3063,15 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     }
 #undef CIPC_FUSED
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
-                    CIPC_LAUNCH(k_barrier_hessian, 1184, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u,
-                        (const u32*)dn, bp, projectSPD, outT, bm);
+                    // mollified stencils + the ones the fused kernels rejected: dense eigen path.  Its launch costs ~0.25 ms even
+                    // for an empty list (63 KB of shared memory per CTA: the SMs re-partition L1 / shared memory around it), a
+                    // host round trip for the list length costs a tenth of that.
+                    u32 nDense = 0;
+                    CIPC_CUDA(cudaMemcpyAsync(&nDense, dn, 4, cudaMemcpyDeviceToHost, c->st));
+                    CIPC_CUDA(cudaStreamSynchronize(c->st));
+                    if (nDense) CIPC_LAUNCH(k_barrier_hessian, std::min<u32>(1184u, div_up(nDense, DENSE_BD)), DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p,
+                        c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u, (const u32*)dn, bp, projectSPD, outT, bm);
+                    c->ctr["hessian_dense"] = nDense;
                 }
                 else if (projectSPD) {
                     // (A) factor, (B) expand; stencils the factor kernels reject are appended to the dense list

@@ -295,6 +295,11 @@ CIPC_HD void hess4_lowrank(bool ee, const dv3* x, double alpha, double beta, boo
 // the Gram matrix (3x3 + two equal scalars) and the closed forms of eta_1, eta_2 written out by hand so that the
 // whole computation stays in registers:
 //     eta_1 = (0, -1/|u|, 0),  eta_2 = (0, (u^.v)/|n|, -|u|/|n|)        (t1 = u^, t2 = n^ x u^)
+// STASH: the values that are only needed again after the eigen-iteration (basis coefficients, frame vectors, Cholesky
+// factors: 28 doubles) are parked in the output slot Y (volatile accesses: no forwarding through registers) while the 5x5
+// Jacobi runs and are read back before Y is written.  With Y in shared memory (k_hessian_fused) this takes ~56 registers
+// off the iteration's live set: the kernel fits five CTAs per SM without spilling.
+template <bool STASH = false>
 CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, double* Y /*36*/)
 {
     dv3 w, u, v;
@@ -348,6 +353,13 @@ CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, doub
     A[1][3] = gg * l11; A[1][4] = gg * l21;
     A[2][3] = 0.0; A[2][4] = gg * l22;
     A[3][3] = 0.0; A[3][4] = 0.0; A[4][4] = 0.0;
+    if (STASH) {
+        volatile double* st = Y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { st[k] = cz[k]; st[4 + k] = c1[k]; st[8 + k] = c2[k]; }
+        st[12] = nh.x; st[13] = nh.y; st[14] = nh.z; st[15] = t1.x; st[16] = t1.y; st[17] = t1.z; st[18] = t2.x; st[19] = t2.y; st[20] = t2.z;
+        st[21] = l10; st[22] = l20; st[23] = l11; st[24] = l21; st[25] = il00; st[26] = il11; st[27] = il22;
+    }
     double V[5][5];
 #pragma unroll
     for (int i = 0; i < 5; ++i)
@@ -427,21 +439,40 @@ CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, doub
                 V[k][j] = sw ? tv : V[k][j];
             }
         }
+    // the parked values come back before the slot is overwritten with the factors
+    double zc[4], oc[4], tc[4], nx, ny, nz, ax, ay, az, bx, by, bz, m10, m20, m21, j00, j11, j22;
+    if (STASH) {
+        volatile double* st = Y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { zc[k] = st[k]; oc[k] = st[4 + k]; tc[k] = st[8 + k]; }
+        nx = st[12]; ny = st[13]; nz = st[14]; ax = st[15]; ay = st[16]; az = st[17]; bx = st[18]; by = st[19]; bz = st[20];
+        m10 = st[21]; m20 = st[22]; m21 = st[24]; j00 = st[25]; j11 = st[26]; j22 = st[27];
+    }
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { zc[k] = cz[k]; oc[k] = c1[k]; tc[k] = c2[k]; }
+        nx = nh.x; ny = nh.y; nz = nh.z; ax = t1.x; ay = t1.y; az = t1.z; bx = t2.x; by = t2.y; bz = t2.z;
+        m10 = l10; m20 = l20; m21 = l21; j00 = il00; j11 = il11; j22 = il22;
+    }
+    double F[3][5];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double sc = lam[k] > 0.0 ? sqrt(lam[k]) : 0.0;
         // f = L~^-T (sc v): back substitution with L~ = blockdiag(L_N, l00, l00)
-        const double f4 = sc * V[4][k] * il00, f3 = sc * V[3][k] * il00;
-        const double f2 = sc * V[2][k] * il22;
-        const double f1 = (sc * V[1][k] - l21 * f2) * il11;
-        const double f0 = (sc * V[0][k] - l10 * f1 - l20 * f2) * il00;
-        const dv3 tt(f3 * t1.x + f4 * t2.x, f3 * t1.y + f4 * t2.y, f3 * t1.z + f4 * t2.z);
+        F[k][4] = sc * V[4][k] * j00; F[k][3] = sc * V[3][k] * j00;
+        F[k][2] = sc * V[2][k] * j22;
+        F[k][1] = (sc * V[1][k] - m21 * F[k][2]) * j11;
+        F[k][0] = (sc * V[0][k] - m10 * F[k][1] - m20 * F[k][2]) * j00;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double ttx = F[k][3] * ax + F[k][4] * bx, tty = F[k][3] * ay + F[k][4] * by, ttz = F[k][3] * az + F[k][4] * bz;
 #pragma unroll
         for (int I = 0; I < 4; ++I) {
-            const double cn = f0 * cz[I] + f1 * c1[I] + f2 * c2[I];
-            Y[12 * k + 3 * I + 0] = cn * nh.x + cz[I] * tt.x;
-            Y[12 * k + 3 * I + 1] = cn * nh.y + cz[I] * tt.y;
-            Y[12 * k + 3 * I + 2] = cn * nh.z + cz[I] * tt.z;
+            const double cn = F[k][0] * zc[I] + F[k][1] * oc[I] + F[k][2] * tc[I];
+            Y[12 * k + 3 * I + 0] = cn * nx + zc[I] * ttx;
+            Y[12 * k + 3 * I + 1] = cn * ny + zc[I] * tty;
+            Y[12 * k + 3 * I + 2] = cn * nz + zc[I] * ttz;
         }
     }
 }
