@@ -47,8 +47,8 @@ WORKLOADS = {  # name -> (n, layers)
 # the CPU arms run the requested workload itself; only cfg5_4m is sampled (see the module docstring) and flagged as such
 CPU_SAMPLE = {"cfg5_4m": ("cfg5_1m", None)}
 L2_NOTE = "GPU arm: L2 flushed between timed steps (256 MiB write), working set >> L2"
-PAR_NOTE = ("GPU arm: candidate pairs partitioned by voxel slabs across n_gpus ranks, per stage one NCCL all-reduce (gradient) and one all-gather "
-            "(energy / step / min-distance scalars); reference arm: all host cores of rank 0")
+PAR_NOTE = ("GPU arm: candidate pairs partitioned by voxel slabs across n_gpus ranks, per stage two NCCL all-reduces (sum: gradient + energy; "
+            "min: step size + min distance); reference arm: all host cores of rank 0")
 
 
 def scene_config(name, sc):
@@ -303,26 +303,21 @@ def main():
     dHat2, xi, kappa = sc["dHat2"], sc["xi"], sc["kappa"]
     scal = multi.wrap_device_f64(ctx.dev_ptrs()["scalars"], 16, local)
 
-    gathered = torch.zeros((world, 4), dtype=torch.float64, device="cuda") if world > 1 else None
-
     def device_step():
-        """inputs resident; results stay on the device.  N > 1: two collectives per stage -- one all-reduce(sum) of the 3 nV
-        gradient and one all-gather of the ranks' scalars (energy partial, step, min distance), from which every rank forms
-        the complete energy (sum) and step / min distance (min)"""
+        """inputs resident; results stay on the device.  N > 1: two collectives per stage -- one all-reduce(sum) over the 3 nV
+        gradient with the energy in slot 3 nV (cipc_dev_gradient) and one all-reduce(min) over (step, min distance)"""
         nC = ctx.constraint_set(dHat2, xi, fetch=False)
         ctx.barrier_energy_dev(dHat2, kappa, xi)
         # gradient and PSD-projected Hessian in one pass over the stencils (the Newton iteration evaluates them back to back);
         # the triplet stream is materialised in HBM (what a device-side solver / CSR assembly consumes)
         nTrip = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
         if dc is not None:
-            dc.dist.all_reduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV, local), op=dc.dist.ReduceOp.SUM)
+            dc.dist.all_reduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV + 1, local), op=dc.dist.ReduceOp.SUM)
         ctx.step_size_dev(xi, 1.0)
         for _ in range(2):
             ctx.min_dist2_dev(xi)
         if dc is not None:
-            dc.dist.all_gather_into_tensor(gathered, scal[0:4])
-            red = torch.stack([gathered[:, 0].sum(), gathered[:, 1].min(), gathered[:, 2].min()])  # E, step, min dist2 (ordered bit pattern)
-            scal[0:3].copy_(red)
+            dc.dist.all_reduce(scal[1:3], op=dc.dist.ReduceOp.MIN)  # step size, min dist2 (bit pattern of a positive double: same order)
         return nC, nTrip
 
     def sync_all():
@@ -341,6 +336,7 @@ def main():
     stage_names = ["ccs_hash_build", "ccs_pairs", "ccs_narrow", "ccs_merge", "barrier_E", "barrier_g", "barrier_H", "k_barrier_hessian",
                    "ccd_hash_build", "ccd_pairs", "ccd_accd", "min_dist"]
     launches0 = cipc.kernel_launches()
+    ctx.set_timing(False)  # the per-stage event scopes are instrumentation: off inside the timed loop, on again for the stage report
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kH_ms = []
     for i in range(args.steps):
@@ -350,6 +346,7 @@ def main():
         ev[i][1].record(stream)
     sync_all()
     launches = cipc.kernel_launches() - launches0
+    ctx.set_timing(True)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     # the dominant kernel, timed live with CUDA events on its own stream (stage timers of the last step)
     ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
@@ -380,6 +377,8 @@ def main():
 
     # lagged friction (FEM/FRICTION.h) on the same constraint set: reported beside the metric, not inside `value`
     friction = {}
+    if args.workload == "cfg5_4m":
+        args.no_friction = True  # the side measurements (friction, CSR assembly) need a second 68 GB triplet stream
     if not args.no_friction:
         rng = np.random.default_rng(17)
         Xn = sc["X"] - rng.normal(size=sc["X"].shape) * np.where(rng.random(nV) < 0.5, 2e-6, 5e-5)[:, None]  # both sides of eps_v h = 1e-5
@@ -415,7 +414,10 @@ def main():
         X04 = pin((nV, 4), torch.float64); X04[:, :3] = sc["X0"]; X04[:, 3] = 0
         p_h = pin((nV * 3,), torch.float64); p_h[:] = sc["p"].ravel()
         g_h = pin((nV, 4), torch.float64)
-        nC_cap, nT_cap = int(nC * 1.05) + 1024, int(nTrip * 1.05) + 1024
+        big = args.workload == "cfg5_4m"  # 4.28G raw triplets = 68 GB: only the merged delivery is timed end to end, side measurements off
+        ctx.set_positions(sc["X"])
+        nMerged = ctx.barrier_hessian_merged(dHat2, kappa, xi, True, fetch=False)
+        nC_cap, nT_cap = int(nC * 1.05) + 1024, int((nMerged if big else nTrip) * 1.05) + 1024
         cs_h = pin((nC_cap, 4), torch.int32); info_h = pin((nC_cap, 2), torch.float64); d_h = pin((nC_cap,), torch.float64)
         trip_raw = torch.empty((nT_cap, 2), dtype=torch.float64).pin_memory().numpy()
         trip_h = trip_raw.view(cipc.TRIPLET_DTYPE).reshape(-1)
@@ -497,7 +499,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item()), int(h2d), int(d2h), {k: round(1e3 * v / args.steps, 3) for k, v in calls.items()}, ntr[0], pcie[0]
 
-        raw_ms, raw_h2d, raw_d2h, raw_calls, raw_n, raw_pcie = e2e_run(False)
+        raw_ms, raw_h2d, raw_d2h, raw_calls, raw_n, raw_pcie = e2e_run(False) if not big else (None, 0, 0, {}, int(nTrip), 0)
         mg_ms, mg_h2d, mg_d2h, mg_calls, mg_n, mg_pcie = e2e_run(True)
         e2e = {"value": mg_ms, "unit": "ms", "h2d_bytes_per_step": mg_h2d, "d2h_bytes_per_step": mg_d2h,
                "via": "C ABI through the ctypes mirror of the shim's call pattern, pinned host buffers, merged-triplet Hessian delivery",

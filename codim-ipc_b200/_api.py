@@ -435,6 +435,10 @@ class ContactContext:
         """run on the caller's CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream"""
         self._ck(self.L.cipc_set_stream(self.h, C.c_void_p(cuda_stream_handle or None)))
 
+    def set_timing(self, on):
+        """stage timers (stage_ms) on / off: two CUDA event records per stage scope"""
+        self._ck(self.L.cipc_set_timing(self.h, int(bool(on))))
+
     def event_record(self, slot):
         self._ck(self.L.cipc_event_record(self.h, int(slot)))
 

@@ -1671,18 +1671,20 @@ struct cipc_ctx {
         return evPool[evUsed++];
     }
     void begin_call() { stages.clear(); evUsed = 0; }
+    bool timing = true; // cipc_set_timing: stage scopes record CUDA events only while on
     struct Scope {
         cipc_ctx* c;
         size_t idx;
-        Scope(cipc_ctx* c_, const char* name) : c(c_)
+        Scope(cipc_ctx* c_, const char* name) : c(c_), idx((size_t)-1)
         {
+            if (!c->timing) return;
             StageEv s;
             s.name = name; s.a = c->ev(); s.b = c->ev();
             CIPC_CUDA(cudaEventRecord(s.a, c->st));
             c->stages.push_back(s);
             idx = c->stages.size() - 1;
         }
-        ~Scope() { cudaEventRecord(c->stages[idx].b, c->st); }
+        ~Scope() { if (idx != (size_t)-1) cudaEventRecord(c->stages[idx].b, c->st); }
     };
 };
 
@@ -2033,7 +2035,7 @@ int do_barrier_gradient(cipc_ctx* c, int elastic, double dHat2, const double* ka
 {
     need(c->haveX, "positions not set");
     const BarrierParams bp = make_bp(elastic, dHat2, kappa, thickness);
-    c->g.reserve((size_t)3 * c->T.nV, c->st);
+    c->g.reserve((size_t)3 * c->T.nV + 8, c->st);
     cipc_ctx::Scope sc(c, "barrier_g");
     CIPC_CUDA(cudaMemsetAsync(c->g.p, 0, (size_t)3 * c->T.nV * sizeof(double), c->st));
     if (c->nC) CIPC_LAUNCH(k_barrier_gradient, div_up(c->nC, 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->nC, bp, c->g.p, (const u32*)nullptr);
@@ -2207,7 +2209,7 @@ int do_friction_energy(cipc_ctx* c, double epsvh2, double mu)
 int do_friction_gradient(cipc_ctx* c, double epsvh2, double mu, bool accumulate)
 {
     need(c->haveX && c->haveXn, "positions / previous positions not set");
-    c->g.reserve((size_t)3 * c->T.nV, c->st, true);
+    c->g.reserve((size_t)3 * c->T.nV + 8, c->st, true);
     cipc_ctx::Scope sc(c, "friction_g");
     if (!accumulate) CIPC_CUDA(cudaMemsetAsync(c->g.p, 0, (size_t)3 * c->T.nV * sizeof(double), c->st));
     if (c->nF) CIPC_LAUNCH(k_friction_gradient, div_up(c->nF, 128), 128, 0, c->st, c->X.p, c->Xn.p, c->fcs.p, c->fcp.p, c->fB.p, c->fnf.p, c->nF,
@@ -2656,6 +2658,13 @@ int cipc_set_stream(cipc_ctx* ctx, void* stream)
         return (int)CIPC_OK;
     });
 }
+int cipc_set_timing(cipc_ctx* ctx, int on)
+{
+    if (!ctx) return CIPC_ERR_ARG;
+    ctx->timing = on != 0;
+    if (ctx->multi) for (cipc_ctx* s : ctx->multi->sub) s->timing = on != 0;
+    return CIPC_OK;
+}
 int cipc_event_record(cipc_ctx* ctx, int slot)
 {
     CIPC_MULTI_UNSUPPORTED(ctx);
@@ -3044,8 +3053,10 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     u32* dl = c->clsIdx[3].p; u32* dn = c->counters.p + 15;
                     double* gOut = nullptr;
                     if (withGradient) { // the barrier gradient of every stencil rides on the same pass
-                        c->g.reserve((size_t)3 * c->T.nV, c->st);
+                        c->g.reserve((size_t)3 * c->T.nV + 8, c->st);
                         CIPC_CUDA(cudaMemsetAsync(c->g.p, 0, (size_t)3 * c->T.nV * sizeof(double), c->st));
+                        // g[3 nV] = the energy of the last cipc_barrier_energy_dev: one all-reduce(sum) covers gradient and energy
+                        CIPC_CUDA(cudaMemcpyAsync(c->g.p + (size_t)3 * c->T.nV, c->scal.p, sizeof(double), cudaMemcpyDeviceToDevice, c->st));
                         gOut = c->g.p;
                         if (nk[3]) CIPC_LAUNCH(k_barrier_gradient, div_up(nk[3], 128), 128, 0, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, nk[3], bp, c->g.p,
                             (const u32*)c->clsIdx[3].p); // mollified stencils (the first nk[3] entries of the dense list)
@@ -3063,15 +3074,9 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     }
 #undef CIPC_FUSED
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
-                    // mollified stencils + the ones the fused kernels rejected: dense eigen path.  Its launch costs ~0.25 ms even
-                    // for an empty list (63 KB of shared memory per CTA: the SMs re-partition L1 / shared memory around it), a
-                    // host round trip for the list length costs a tenth of that.
-                    u32 nDense = 0;
-                    CIPC_CUDA(cudaMemcpyAsync(&nDense, dn, 4, cudaMemcpyDeviceToHost, c->st));
-                    CIPC_CUDA(cudaStreamSynchronize(c->st));
-                    if (nDense) CIPC_LAUNCH(k_barrier_hessian, std::min<u32>(1184u, div_up(nDense, DENSE_BD)), DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p,
-                        c->cs.p, c->info.p, c->tripOff.p, c->clsIdx[3].p, 0u, (const u32*)dn, bp, projectSPD, outT, bm);
-                    c->ctr["hessian_dense"] = nDense;
+                    // mollified stencils + the ones the fused kernels rejected (list length read on the device): dense eigen path
+                    CIPC_LAUNCH(k_barrier_hessian, nk[3] ? 1184 : 148, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                        c->clsIdx[3].p, 0u, (const u32*)dn, bp, projectSPD, outT, bm);
                 }
                 else if (projectSPD) {
                     // (A) factor, (B) expand; stencils the factor kernels reject are appended to the dense list

@@ -203,7 +203,9 @@ int cipc_get_boundary(cipc_ctx* ctx, int32_t* BN, int32_t* BE, int be_stride, in
 
 /* ---- device-resident access (multi-GPU reductions, benchmarking) ----------------------------- */
 double* cipc_dev_positions(cipc_ctx* ctx);      /* nV x 4 doubles (x,y,z,pad) */
-double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient_dev */
+double* cipc_dev_gradient(cipc_ctx* ctx);       /* 3*nV doubles written by the last cipc_barrier_gradient[_hessian]_dev; after
+                                                 * cipc_barrier_gradient_hessian_dev slot [3*nV] holds the energy of the last
+                                                 * cipc_barrier_energy_dev, so one all-reduce(sum) of 3*nV+1 doubles covers both */
 double* cipc_dev_scalars(cipc_ctx* ctx);        /* [0]=barrier energy, [1]=step size, [2]=min dist2, [4]=friction energy of the last *_dev call */
 /* same stages with every result left on the device (no D2H): */
 int cipc_barrier_energy_dev(cipc_ctx* ctx, int elasticIPC, double dHat2, const double kappa[3], double thickness);
@@ -225,6 +227,9 @@ int cipc_sync(cipc_ctx* ctx);
  * the caller's events / NCCL collectives order against it without host synchronisation; NULL restores the
  * library's own stream */
 int cipc_set_stream(cipc_ctx* ctx, void* cuda_stream);
+/* stage timers (cipc_stage_ms) record two CUDA events per stage scope; on = 0 switches them off (cipc_stage_ms then returns -1),
+ * on != 0 (default) back on */
+int cipc_set_timing(cipc_ctx* ctx, int on);
 /* CUDA events on the library's stream: record into slot [0,64) / elapsed milliseconds between two slots */
 int cipc_event_record(cipc_ctx* ctx, int slot);
 double cipc_event_elapsed_ms(cipc_ctx* ctx, int slot_a, int slot_b);
