@@ -20,7 +20,7 @@
 // Reference signatures: FEM/IPC.h:19-36, 742-748, 943-948, 1258-1265, 1879-1890, 2246-2249.
 //
 // Environment knobs (read once): CIPC_DEVICE (CUDA ordinal, default 0) or CIPC_DEVICES (comma-separated ordinals: all of them
-// behind this one calling thread, cipc_create_multi); CIPC_TRIPLETS = merged (default) | raw.
+// behind this one calling thread, cipc_create_multi); CIPC_TRIPLETS = merged (default) | raw; CIPC_MALLOC_REUSE=1 (see state()).
 //   merged: Compute_Barrier_Hessian / Compute_Friction_Hessian append ONE triplet per distinct (row, col) of their matrix --
 //           the duplicates that the only consumer of the vector, sysMtr.Construct_From_Triplet = Eigen setFromTriplets
 //           (Shell/INC_POTENTIAL.h:382, Math/CSR_MATRIX.h:49-56), would sum anyway are summed on the device (cipc_*_hessian_merged).
@@ -48,6 +48,7 @@
 
 #include <cipc_b200.h>
 
+#include <malloc.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,11 @@ inline State& state()
         if (st != CIPC_OK) { printf("cipc_b200: no CUDA device; the contact path has no CPU fallback\n"); exit(-1); }
         const char* tm = getenv("CIPC_TRIPLETS");
         s.merged = !(tm && std::string(tm) == "raw");
+        // CIPC_MALLOC_REUSE=1: keep freed memory in the process (glibc: no mmap for large blocks, no trimming), so that the
+        // triplet vector a Newton iteration allocates (INC_POTENTIAL.h:321, ~2 GB at 1M triangles) lands on pages the
+        // previous iteration already faulted in instead of paying ~30 ms of first-touch page faults again
+        const char* mr = getenv("CIPC_MALLOC_REUSE");
+        if (mr && mr[0] == '1') { mallopt(M_MMAP_MAX, 0); mallopt(M_TRIM_THRESHOLD, 2147483647); }
     }
     return s;
 }
