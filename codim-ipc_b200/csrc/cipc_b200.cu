@@ -2573,6 +2573,11 @@ int cipc_host_parallel_for(size_t n, size_t grain, cipc_range_fn fn, void* user)
     HostPool::get().for_each(items, [&](size_t k) { fn(k * grain, std::min(n, (k + 1) * grain), user); });
     return CIPC_OK;
 }
+int cipc_host_prefault_async(void* p, size_t bytes)
+{
+    try { Prefault::get().start(p, bytes); } catch (...) { return CIPC_ERR_ARG; }
+    return CIPC_OK;
+}
 uint64_t cipc_hash_bytes(const void* p, size_t n)
 {
     const HashSeg sg{(const unsigned char*)p, n};
@@ -3148,6 +3153,7 @@ int cipc_barrier_gradient_hessian_dev(cipc_ctx* ctx, int elastic, double dHat2, 
 }
 int cipc_get_triplets(cipc_ctx* ctx, cipc_triplet* out)
 {
+    Prefault::get().wait(); // a background first touch of the destination (cipc_host_prefault_async) must have finished
     if (ctx && ctx->multi) return multi_get_triplets(ctx, out);
     return guarded(ctx, [&]() {
         if (!ctx->nTrip) return (int)CIPC_OK;

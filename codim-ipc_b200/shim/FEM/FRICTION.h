@@ -157,7 +157,9 @@ void Compute_Friction_Gradient(MESH_NODE<T, dim>& X, MESH_NODE<T, dim>& Xn, cons
         cipc_shim::upload_positions(s, Xn, cipc_set_prev_positions, "cipc_set_prev_positions");
         cipc_shim::ensure_friction(s, constraintSet, closestPoint, tanBasis, normalForce);
         const size_t n = X.size;
-        s.stage3.assign(3 * n, 0.0);
+        s.stage3.resize(3 * n);
+        double* z = s.stage3.data();
+        cipc_shim::parallel_nodes(n, [z](size_t i) { z[3 * i] = 0.0; z[3 * i + 1] = 0.0; z[3 * i + 2] = 0.0; }); // the C ABI accumulates
         cipc_shim::die(s.ctx, cipc_friction_gradient(s.ctx, epsvh2, mu, s.stage3.data(), 24), "cipc_friction_gradient");
         const double* st = s.stage3.data();
         cipc_shim::parallel_nodes(n, [&nodeAttr, st](size_t i) { // nodeAttr.g += (FRICTION.h:294-297)

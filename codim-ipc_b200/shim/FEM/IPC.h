@@ -333,7 +333,9 @@ void Compute_Barrier_Gradient(MESH_NODE<T, dim>& X, const std::vector<VECTOR<int
         cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
         cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
         const size_t n = X.size;
-        s.stage3.assign(3 * n, 0.0);
+        s.stage3.resize(3 * n);
+        double* z = s.stage3.data();
+        cipc_shim::parallel_nodes(n, [z](size_t i) { z[3 * i] = 0.0; z[3 * i + 1] = 0.0; z[3 * i + 2] = 0.0; }); // the C ABI accumulates
         cipc_shim::die(s.ctx, cipc_barrier_gradient(s.ctx, 0, dHat2, kappa, thickness, s.stage3.data(), 24), "cipc_barrier_gradient");
         const double* st = s.stage3.data();
         cipc_shim::parallel_nodes(n, [&nodeAttr, st](size_t i) { // nodeAttr.g += (IPC.h:1034-1042); g lives inside the AoSoA record of node i
@@ -358,10 +360,19 @@ void Compute_Barrier_Hessian(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeA
         cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
         cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
         int64_t n = 0;
+        // the vector is new in every Newton iteration (INC_POTENTIAL.h:321): reserve it from the previous iteration's count and
+        // let its first-touch page faults overlap the device work
+        static size_t lastCount = 0;
+        if (lastCount) {
+            const size_t guess = lastCount + lastCount / 32;
+            triplets.reserve(triplets.size() + guess);
+            cipc_host_prefault_async(triplets.data() + triplets.size(), guess * sizeof(Eigen::Triplet<T>));
+        }
         if (s.merged) cipc_shim::die(s.ctx, cipc_barrier_hessian_merged(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian_merged");
         else cipc_shim::die(s.ctx, cipc_barrier_hessian(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian");
         // the new entries are APPENDED (IPC.h:1371,1388), without the zero-fill of resize()
         if (n) cipc_shim::die(s.ctx, cipc_get_triplets(s.ctx, reinterpret_cast<cipc_triplet*>(cipc_shim::grow_uninitialized(triplets, (size_t)n))), "cipc_get_triplets");
+        lastCount = (size_t)n;
     }
 }
 

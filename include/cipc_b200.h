@@ -247,6 +247,10 @@ int64_t cipc_kernel_launches(void);  /* kernels launched by this library since l
 /* 64-bit content hash of a host array, computed by a few host threads (~50 GB/s): the shim's change detector for the
  * caller-owned containers (constraint set, friction set) it keeps resident on the device between calls */
 uint64_t cipc_hash_bytes(const void* p, size_t n);
+/* starts touching the pages of [p, p + bytes) on the host thread pool in the background and returns at once: a caller that
+ * knows roughly how many triplets the next Hessian delivers (the previous Newton iteration's count) reserves its vector first
+ * and lets the first-touch page faults of the fresh allocation overlap the device work; cipc_get_triplets waits for it. */
+int cipc_host_prefault_async(void* p, size_t bytes);
 /* runs fn(begin, end, user) over [0, n) in pieces of `grain` on the library's persistent host thread pool (CIPC_HOST_THREADS,
  * default all cores) and returns when all pieces are done: the shim's loops over the reference's AoSoA node storage
  * (gradient accumulation nodeAttr.g +=, rest-position gather) use it.  Not re-entrant from inside fn. */
