@@ -134,8 +134,10 @@ def cpu_describe(kind):
             else "oracle port (-O3 -mavx2 -mfma -fopenmp, the reference's parallel structure)")
 
 
-def cpu_samples(workload, n_warm, n_timed):
-    """run n_warm + n_timed full contact stages of `workload` (cfg5_4m: of its sample) on all host cores"""
+def cpu_samples(workload, n_warm, n_timed, budget_s=None):
+    """run n_warm + n_timed full contact stages of `workload` (cfg5_4m: of its sample) on all host cores.  budget_s: wall-clock
+    bound of the whole run -- when the first stage shows that n_warm + n_timed stages would exceed it, fewer stages are run
+    (never fewer than 1 warm-up + 3 timed) and the executed counts are returned"""
     sample, _ = CPU_SAMPLE.get(workload, (workload, 1.0))
     sc = make_scene(sample)
     cores = os.cpu_count()  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
@@ -143,10 +145,16 @@ def cpu_samples(workload, n_warm, n_timed):
     cpu_set_threads(Scene, cores)
     S = Scene(sc)
     times, st, nC = [], {}, 0
-    for i in range(n_warm + n_timed):
+    i = 0
+    while i < n_warm + n_timed:
         t, st, nC = cpu_contact_stage(S, sc)
+        if i == 0 and budget_s is not None and t * (n_warm + n_timed) > budget_s:
+            fit = max(4, int(budget_s / t))
+            n_warm = max(1, min(n_warm, fit - 3)) if n_warm else 0
+            n_timed = max(3, min(n_timed, fit - n_warm))
         if i >= n_warm:
             times.append(t)
+        i += 1
     scale, extrap = 1.0, None
     if sample != workload:
         # cfg5_4m only: scaled by the constraint count of the full workload (known from the scene generator's density) -- an
@@ -155,20 +163,25 @@ def cpu_samples(workload, n_warm, n_timed):
         scale = full / float(len(sc["BT"]))
         extrap = {"extrapolated": True, "sample_workload": sample, "scale": scale,
                   "why": "4.28G triplets overflow the reference's int triplet offsets (FEM/IPC.h:1368) and 68 GB of host triplets"}
-    return dict(kind=kind, cores=cores, times=[t * scale for t in times], stages=st, nC=nC, sample=sample, scene=sc, scale=scale, extrap=extrap)
+    return dict(kind=kind, cores=cores, times=[t * scale for t in times], stages=st, nC=nC, sample=sample, scene=sc, scale=scale, extrap=extrap,
+                n_warm=n_warm, n_timed=len(times))
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_samples(args.workload, args.warmup, args.steps)
+    # every warm-up and timed step is one FULL contact stage of the workload (~13 s at cfg5_1m on 16 cores).  The run is bounded by
+    # CIPC_REF_BUDGET_S seconds of CPU work (default 420): if W + K stages do not fit, fewer are executed and "steps" / "warmup"
+    # report what was executed, with the request beside them.
+    budget = float(os.environ.get("CIPC_REF_BUDGET_S", "420"))
+    r = cpu_samples(args.workload, args.warmup, args.steps, budget)
     ms = 1e3 * float(np.mean(r["times"]))
     sc_full = r["scene"] if r["sample"] == args.workload else make_scene(args.workload)
     desc = "%s: %d warm-up + %d timed full contact stages of %s (%d triangles, %d constraints)%s" % (
-        cpu_describe(r["kind"]), args.warmup, args.steps, r["sample"], len(r["scene"]["BT"]), r["nC"],
+        cpu_describe(r["kind"]), r["n_warm"], r["n_timed"], r["sample"], len(r["scene"]["BT"]), r["nC"],
         "" if r["extrap"] is None else ", scaled x%.2f to %s" % (r["scale"], args.workload))
-    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": r["n_timed"], "warmup": r["n_warm"],
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": scene_config(args.workload, sc_full),
             "cpu_baseline": {"value": ms, "unit": "ms", "cores": r["cores"], "kind": r["kind"], "sample": desc,
@@ -176,6 +189,8 @@ def run_reference_arm(args):
                              "stages_s": {k: round(v, 4) for k, v in r["stages"].items()}},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "counts": {"constraints": int(r["nC"])}}
+    if (r["n_timed"], r["n_warm"]) != (args.steps, args.warmup):
+        line["requested"] = {"steps": args.steps, "warmup": args.warmup, "budget_s": budget}
     if r["extrap"] is not None:
         line.update(r["extrap"])
     print(json.dumps(line))
@@ -556,6 +571,10 @@ def main():
             if have_shim:
                 if world == 1:
                     ctx.sync()
+                    if big:  # 4M triangles: the bench context's 100+ GB of buffers make room for the shim's own context
+                        ctx.close()
+                        del flush
+                        torch.cuda.empty_cache()
                 S = shim_scene.ShimScene(sc)
                 tot, per = [], {}
                 for i in range(max(1, args.warmup - 1) + args.steps):
