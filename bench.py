@@ -326,13 +326,15 @@ def main():
         # gradient and PSD-projected Hessian in one pass over the stencils (the Newton iteration evaluates them back to back);
         # the triplet stream is materialised in HBM (what a device-side solver / CSR assembly consumes)
         nTrip = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
-        if dc is not None:
-            dc.dist.all_reduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV + 1, local), op=dc.dist.ReduceOp.SUM)
+        work = None
+        if dc is not None:  # asynchronous: the sum travels over NVLink while the step-size search (independent of it) runs
+            work = dc.dist.all_reduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV + 1, local), op=dc.dist.ReduceOp.SUM, async_op=True)
         ctx.step_size_dev(xi, 1.0)
         for _ in range(2):
             ctx.min_dist2_dev(xi)
         if dc is not None:
             dc.dist.all_reduce(scal[1:3], op=dc.dist.ReduceOp.MIN)  # step size, min dist2 (bit pattern of a positive double: same order)
+            work.wait()  # the stage ends with every collective complete (stream-ordered: the timing event is recorded after it)
         return nC, nTrip
 
     def sync_all():

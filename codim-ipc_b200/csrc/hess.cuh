@@ -24,6 +24,10 @@
 #pragma once
 #include "geom.cuh"
 
+#ifndef CIPC_JACOBI_RR
+#define CIPC_JACOBI_RR 1
+#endif
+
 namespace cipc {
 
 // ------------------------------------------------------------------ K x K symmetric Jacobi, registers only
@@ -377,6 +381,65 @@ CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, doub
     // not zeroed), so an angle error of 1e-7 only leaves a_pq' ~ 1e-7 a_pq: the sweeps still converge quadratically
     // down to the fp64 tolerance above, which is what bounds the result's accuracy.
     const double iscale = cipc_rsqrt(fro);
+#if CIPC_JACOBI_RR
+    // Round-robin ordering: five rounds of two DISJOINT index pairs.  The two rotations of a round commute and neither
+    // changes the three entries the other's angle is formed from, so both angles are computed first -- two independent
+    // fp32 / rsqrt latency chains the scheduler interleaves -- and then both rotations are applied.  Branch-free: a pair
+    // whose off-diagonal entry is already negligible gets the identity rotation (t = 0).
+    constexpr int RP[10] = {1, 2, 0, 3, 1, 0, 2, 0, 0, 1}, RQ[10] = {4, 3, 2, 4, 3, 4, 4, 1, 3, 2};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 5; ++q) off += A[p][q] * A[p][q];
+        if (off <= tol) break;
+        const double thr = 1e-34 * fro;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            double cr[2], sr[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = RP[2 * r + h], q = RQ[2 * r + h];
+                const double apq = A[p][q], app = A[p][p], aqq = A[q][q];
+                const float df = (float)((aqq - app) * iscale), af = (float)(apq * iscale) * 2.0f;
+#if defined(__CUDA_ARCH__)
+                const float h2 = fmaxf(fmaf(df, df, af * af), 1e-37f);
+                const float tf = __fdividef(df >= 0.0f ? af : -af, fabsf(df) + h2 * rsqrtf(h2));
+#else
+                const float h2 = fmaxf(df * df + af * af, 1e-37f);
+                const float tf = (df >= 0.0f ? af : -af) / (fabsf(df) + sqrtf(h2));
+#endif
+                const double t = (apq * apq > thr) ? (double)tf : 0.0;
+                cr[h] = cipc_rsqrt(t * t + 1.0);
+                sr[h] = t * cr[h];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = RP[2 * r + h], q = RQ[2 * r + h];
+                const double c = cr[h], sn = sr[h];
+                const double apq = A[p][q], app = A[p][p], aqq = A[q][q];
+                const double cc = c * c, ss = sn * sn, cs = c * sn;
+                A[p][p] = cc * app - 2.0 * cs * apq + ss * aqq;
+                A[q][q] = ss * app + 2.0 * cs * apq + cc * aqq;
+                A[p][q] = cs * (app - aqq) + (cc - ss) * apq;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if (k != p && k != q) { // upper-triangle accessors with compile-time indices
+                        double& akp = (k < p) ? A[k][p] : A[p][k];
+                        double& akq = (k < q) ? A[k][q] : A[q][k];
+                        const double vp = akp, vq = akq;
+                        akp = c * vp - sn * vq;
+                        akq = sn * vp + c * vq;
+                    }
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+        }
+    }
+#else
     for (int sweep = 0; sweep < 12; ++sweep) {
         double off = 0.0;
 #pragma unroll
@@ -420,6 +483,7 @@ CIPC_HD void hess4_factor(bool ee, const dv3* x, double alpha, double beta, doub
                 }
             }
     }
+#endif
     // bring the three largest eigenvalues (the only possibly positive ones) to columns 0..2
     double lam[5];
 #pragma unroll
