@@ -645,7 +645,7 @@ def main():
     # FP64 side of the same kernel (it is co-limited): fp64 thread instructions per PT/EE stencil counted by ncu on this build
     # (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r2_fp64_ops_k_hessian_fused.csv) against the
     # non-tensor FP64 FMA rate measured on THIS box by tools/fp64_fma_probe (dependent DFMA chains, CUDA events)
-    FP64_OPS_4PT = {"dfma": 1756, "dmul": 1283, "dadd": 372}
+    FP64_OPS_4PT = {"dfma": 1865, "dmul": 1410, "dadd": 402}
     fp64_peak, fp64_src = 34.2, "recorded on this pool's B200 (tools/fp64_fma_probe, 2026-10-17)"
     probe = os.path.join(ROOT, "tools", "fp64_fma_probe")
     if os.path.exists(probe) and world == 1:
@@ -661,6 +661,13 @@ def main():
                      "frac": flops / (kH * 1e-3) / 1e12 / fp64_peak,
                      "pipe_frac": 2.0 * slots / (kH * 1e-3) / 1e12 / fp64_peak,  # every fp64 instruction occupies one FMA issue slot
                      "fp64_thread_instructions_per_unit": FP64_OPS_4PT, "peak_source": fp64_src}
+        if args.workload == "cfg5_1m" and world == 1 and stages.get("ccd_accd"):
+            # additive CCD (k_accd_pt + k_accd_ee on this workload's 1.17M swept pairs): fp64 thread instructions per call from the
+            # same ncu pass -- dadd 154.6M, dfma 78.7M, dmul 155.1M -- against the live stage time
+            accd_flops = 154.6e6 + 2 * 78.7e6 + 155.1e6
+            roof_fp64["accd"] = {"kernels": "k_accd_pt + k_accd_ee", "achieved": accd_flops / (stages["ccd_accd"] * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                 "frac": accd_flops / (stages["ccd_accd"] * 1e-3) / 1e12 / fp64_peak,
+                                 "note": "divergent per-pair iteration (1-40 ACCD steps), latency-bound: 0.1 ms of the stage"}
     else:
         roof_fp64 = None
     tr_path = os.path.join(ROOT, "profiles", "traffic_k_hessian_fused.json")
