@@ -1270,8 +1270,11 @@ __global__ void __launch_bounds__(256) k_hessian_expand_tiled(const double* __re
 // warps stay decoupled, so one warp's store stream overlaps the others' arithmetic.  Lane l owns the fixed block entries
 // e = l + 32 j of every stencil; (row, col) decoding is hoisted out of the stencil loop and a warp writes 512 contiguous
 // bytes per store instruction.
-template <int NN, int NY, int YS>
-__device__ __forceinline__ void warp_expand_stencils(const double* sY, const int* sH, u32 wq0, u32 g, u32 lane, cipc_triplet* __restrict__ trip)
+// sR: per stencil, the NN global row indices 3 v[r/3] + r%3 (written by the factoring thread).  SIGNED: honour the header's
+// sign flag (friction only; the barrier factors are never negated).
+template <int NN, int NY, int YS, bool SIGNED>
+__device__ __forceinline__ void warp_expand_stencils(const double* sY, const int* sH, const int* sR, u32 wq0, u32 g, u32 lane,
+    cipc_triplet* __restrict__ trip)
 {
     constexpr int PER = NN * NN, NJ = (PER + 31) / 32;
     int rI[NJ], cI[NJ];
@@ -1286,7 +1289,8 @@ __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int
         const u32 o = (u32)h[0];
         if (o == 0xffffffffu) continue;
         const double* y = sY + (wq0 + qq) * YS;
-        const bool neg = h[5] != 0;
+        const int* rows = sR + (wq0 + qq) * NN;
+        const bool neg = SIGNED && h[5] != 0;
         cipc_triplet* dst = trip + (size_t)o * 9;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -1296,10 +1300,9 @@ __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int
                 double v = 0.0;
 #pragma unroll
                 for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
-                if (neg) v = -v;
-                const int ri = r / 3, ci = c / 3;
+                if (SIGNED && neg) v = -v;
                 int4 w;
-                w.x = h[1 + ri] * 3 + (r - 3 * ri); w.y = h[1 + ci] * 3 + (c - 3 * ci);
+                w.x = rows[r]; w.y = rows[c];
                 const long long bb = __double_as_longlong(v);
                 w.z = (int)(bb & 0xffffffffLL); w.w = (int)(bb >> 32);
                 __stcs(reinterpret_cast<int4*>(dst + e), w);
@@ -1322,7 +1325,7 @@ constexpr int FUSED_BD = 128;
 template <int CLS> struct FusedShape {
     static constexpr int NN = 3 * YShape<CLS>::NB, NY = YShape<CLS>::NY, YD = NY * NN;
     static constexpr int YS = (YD % 2 == 0) ? YD + 1 : YD; // odd stride: conflict-free 8-byte accesses, one stencil per lane
-    static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
+    static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32 + FUSED_BD * NN * 4; // factors, headers, row indices
 };
 // BLK: the stencil's upper 3x3 blocks (9 doubles each, merge.cuh) are written instead of 16-byte triplets -- 720 instead of
 // 2304 bytes per PT/EE stencil -- and `off` counts blocks.
@@ -1335,6 +1338,7 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
     extern __shared__ __align__(16) unsigned char fused_sm[];
     double* sY = reinterpret_cast<double*>(fused_sm);
     int* sH = reinterpret_cast<int*>(fused_sm + FUSED_BD * YS * 8);
+    int* sR = sH + FUSED_BD * 8;
     const u32 q0 = blockIdx.x * FUSED_BD;
     const u32 g = min((u32)FUSED_BD, n - q0);
     if (threadIdx.x < g) {
@@ -1346,6 +1350,11 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
         const double beta = wm * barrier_g(bp.elastic, d, bp.dHat2, bp.k0);
         int* h = sH + threadIdx.x * 8;
         h[1] = s.v[0]; h[2] = s.v[1]; h[3] = s.v[2]; h[4] = s.v[3]; h[5] = 0;
+        if (BLK) h[6] = swap_mask<YShape<CLS>::NB>(s.v);
+        else {
+#pragma unroll
+            for (int r = 0; r < NN; ++r) sR[threadIdx.x * NN + r] = 3 * s.v[r / 3] + r % 3;
+        }
         if (gOut) { // barrier gradient of the same stencil (cipc_barrier_gradient_hessian_dev): w m b' grad d, as k_barrier_gradient
             double dg[12];
             const int rows3[3] = {0, 1, 2};
@@ -1375,8 +1384,8 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
         }
     }
     __syncwarp();
-    if (BLK) warp_expand_blocks<YShape<CLS>::NB, NY, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<double*>(outp));
-    else warp_expand_stencils<NN, NY, YS>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<cipc_triplet*>(outp));
+    if (BLK) warp_expand_blocks<YShape<CLS>::NB, NY, YS, false>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<double*>(outp));
+    else warp_expand_stencils<NN, NY, YS, false>(sY, sH, sR, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<cipc_triplet*>(outp));
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 constexpr int DENSE_BD = 64;                              // threads per block of the dense path

@@ -186,17 +186,33 @@ __device__ __forceinline__ void upper_pair_ij(int b, int& I, int& J)
 }
 // Block-mode twin of warp_expand_stencils: lane l owns the doubles e = l + 32 j of every stencil's block run
 // (9 nb(nb+1)/2 doubles, contiguous), so a warp writes 256 contiguous bytes per store instruction.
-template <int NB, int NY, int YS>
+// bit b of the mask: pair b = (I, J) of the upper triangle has v_I > v_J, i.e. its block is stored transposed (for the
+// (min vertex, max vertex) orientation).  Computed once per stencil by the factoring thread, kept in header word 6.
+template <int NB>
+__device__ __forceinline__ int swap_mask(const int* v)
+{
+    int m = 0, b = 0;
+#pragma unroll
+    for (int I = 0; I < NB; ++I)
+#pragma unroll
+        for (int J = I; J < NB; ++J, ++b) m |= (v[I] > v[J]) ? (1 << b) : 0;
+    return m;
+}
+template <int NB, int NY, int YS, bool SIGNED>
 __device__ __forceinline__ void warp_expand_blocks(const double* sY, const int* sH, u32 wq0, u32 g, u32 lane, double* __restrict__ blk)
 {
     constexpr int NN = 3 * NB, PER = 9 * (NB * (NB + 1) / 2), NJ = (PER + 31) / 32;
-    int pI[NJ], pJ[NJ], ra[NJ], rc[NJ];
+    int bI[NJ], r0[NJ], c0[NJ], r1[NJ], c1[NJ]; // pair index; (row, col) inside the stencil, plain and transposed
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int e = (int)lane + 32 * j;
         const int b = (e < PER ? e : 0) / 9, k = (e < PER ? e : 0) - 9 * b;
-        upper_pair_ij<NB>(b, pI[j], pJ[j]);
-        ra[j] = k / 3; rc[j] = k - 3 * ra[j];
+        int I, J;
+        upper_pair_ij<NB>(b, I, J);
+        const int ra = k / 3, rc = k - 3 * ra;
+        bI[j] = b;
+        r0[j] = 3 * I + ra; c0[j] = 3 * J + rc;
+        r1[j] = 3 * J + ra; c1[j] = 3 * I + rc;
     }
     const u32 wn = (wq0 < g) ? min(32u, g - wq0) : 0u;
     for (u32 qq = 0; qq < wn; ++qq) {
@@ -204,18 +220,19 @@ __device__ __forceinline__ void warp_expand_blocks(const double* sY, const int* 
         const u32 o = (u32)h[0];
         if (o == 0xffffffffu) continue;
         const double* y = sY + (wq0 + qq) * YS;
-        const bool neg = h[5] != 0;
+        const bool neg = SIGNED && h[5] != 0;
+        const int mask = h[6];
         double* dst = blk + (size_t)o * 9;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int e = (int)lane + 32 * j;
             if (e < PER) {
-                const bool sw = h[1 + pI[j]] > h[1 + pJ[j]]; // stored for (min vertex, max vertex): transposed when v_I > v_J
-                const int r = 3 * (sw ? pJ[j] : pI[j]) + ra[j], c = 3 * (sw ? pI[j] : pJ[j]) + rc[j];
+                const bool sw = (mask >> bI[j]) & 1;
+                const int r = sw ? r1[j] : r0[j], c = sw ? c1[j] : c0[j];
                 double v = 0.0;
 #pragma unroll
                 for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
-                __stcs(dst + e, neg ? -v : v);
+                __stcs(dst + e, (SIGNED && neg) ? -v : v);
             }
         }
     }
