@@ -318,7 +318,16 @@ def main():
     dHat2, xi, kappa = sc["dHat2"], sc["xi"], sc["kappa"]
     scal = multi.wrap_device_f64(ctx.dev_ptrs()["scalars"], 16, local)
 
-    def device_step():
+    dc_ranks = dc
+    g_views = {}
+
+    def g_view():  # torch view of the library's gradient buffer (3 nV + 1 doubles), cached per device pointer
+        ptr = ctx.L.cipc_dev_gradient(ctx.h)
+        if ptr not in g_views:
+            g_views[ptr] = multi.wrap_device_f64(ptr, 3 * nV + 1, local)
+        return g_views[ptr]
+
+    def device_step(collectives=True):
         """inputs resident; results stay on the device.  N > 1: two collectives per stage -- one all-reduce(sum) over the 3 nV
         gradient with the energy in slot 3 nV (cipc_dev_gradient) and one all-reduce(min) over (step, min distance)"""
         nC = ctx.constraint_set(dHat2, xi, fetch=False)
@@ -327,8 +336,9 @@ def main():
         # the triplet stream is materialised in HBM (what a device-side solver / CSR assembly consumes)
         nTrip = ctx.barrier_gradient_hessian_dev(dHat2, kappa, xi)
         work = None
+        dc = dc_ranks if collectives else None
         if dc is not None:  # asynchronous: the sum travels over NVLink while the step-size search (independent of it) runs
-            work = dc.dist.all_reduce(multi.wrap_device_f64(ctx.dev_ptrs()["g"], 3 * nV + 1, local), op=dc.dist.ReduceOp.SUM, async_op=True)
+            work = dc.dist.all_reduce(g_view(), op=dc.dist.ReduceOp.SUM, async_op=True)
         ctx.step_size_dev(xi, 1.0)
         for _ in range(2):
             ctx.min_dist2_dev(xi)
@@ -372,6 +382,33 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
+
+    # N > 1: where the step goes -- every rank's stage without the collectives, and the collectives alone (untimed extra steps,
+    # L2 not flushed); the gap between max(local) + collectives and `value` is rank skew inside the collectives
+    scaling_breakdown = None
+    if dist is not None:
+        def avg_ms(fn, k):
+            sync_all()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(k):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / k
+
+        def collectives_only():
+            w = dist.all_reduce(g_view(), op=dist.ReduceOp.SUM, async_op=True)
+            dist.all_reduce(scal[1:3], op=dist.ReduceOp.MIN)
+            w.wait()
+
+        ctx.set_timing(False)
+        tl = torch.tensor([avg_ms(lambda: device_step(False), args.steps), avg_ms(collectives_only, args.steps)], dtype=torch.float64, device="cuda")
+        ctx.set_timing(True)
+        tall = [torch.zeros_like(tl) for _ in range(world)]
+        dist.all_gather(tall, tl)
+        scaling_breakdown = {"local_ms_per_rank": [round(float(x[0]), 4) for x in tall],
+                             "collectives_only_ms": round(max(float(x[1]) for x in tall), 4)}
 
     # per-stage report (one extra untimed step)
     stages = {}
@@ -703,6 +740,8 @@ def main():
             "roofline": roof, "roofline_fp64": roof_fp64, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
             "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters,
             "friction_stages_ms": friction, "csr_stages_ms": csr}
+    if scaling_breakdown is not None:
+        line["scaling_breakdown"] = scaling_breakdown
     if args.stage_report:
         print(json.dumps(line["stages_ms"], indent=1), file=sys.stderr)
     print(json.dumps(line))

@@ -139,15 +139,22 @@ __global__ void k_bbox(const double4* __restrict__ X, const double4* __restrict_
             for (int d = 0; d < 3; ++d) { mn[d] = fmin(mn[d], e[d]); mx[d] = fmax(mx[d], e[d]); }
         }
     }
+    // warp -> block (shared memory) -> six atomics per block: the six addresses are shared by the whole grid
+    __shared__ double sm[32][6];
     for (int d = 0; d < 3; ++d) {
         for (int o = 16; o > 0; o >>= 1) {
             mn[d] = fmin(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o));
             mx[d] = fmax(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&out[d], dbl_ordered(mn[d]));
-            atomicMax(&out[3 + d], dbl_ordered(mx[d]));
-        }
+        if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5][d] = mn[d]; sm[threadIdx.x >> 5][3 + d] = mx[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double v = sm[0][threadIdx.x];
+        for (int w = 1; w < nw; ++w) v = threadIdx.x < 3 ? fmin(v, sm[w][threadIdx.x]) : fmax(v, sm[w][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&out[threadIdx.x], dbl_ordered(v));
+        else atomicMax(&out[threadIdx.x], dbl_ordered(v));
     }
 }
 
@@ -1838,7 +1845,6 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H, int which)
         // the previous build on the same grid are kept for a few calls: no histogram pass, no host round trip.
         ++sc.age;
         sl = sc.sl;
-        CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
     }
     else if (c->world > 1) {
         // this rank's slab along the axis with the most voxel layers, balanced on the number of hash entries
@@ -1863,7 +1869,6 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H, int which)
         };
         sl.s0 = bound(c->rank);
         sl.s1 = bound(c->rank + 1);
-        CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
         sc.valid = true; sc.age = 0; sc.gx = H.G.gx; sc.gy = H.G.gy; sc.gz = H.G.gz; sc.nP = nP; sc.sl = sl;
     }
     const long gridCells = (long)H.G.gx * H.G.gy * H.G.gz;
@@ -1908,6 +1913,8 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H, int which)
     u32 nE;
     {
         cipc_ctx::Scope s1(c, "hb_count_scan");
+        // per-primitive entry counts clipped to this rank's slab (the dense path counts per cell and never reads them)
+        if (c->world > 1) CIPC_LAUNCH(k_clip_counts, div_up(nP, TB), TB, 0, c->st, nP, c->boxLo.p, c->boxHi.p, sl, c->cnt.p);
         device_excl_scan(c->cnt.p, c->cnt.p, nP, c->scanwk, c->st);
         CIPC_CUDA(cudaMemcpyAsync(&nE, c->scanwk.total.p, sizeof(u32), cudaMemcpyDeviceToHost, c->st));
     }
