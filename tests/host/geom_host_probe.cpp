@@ -95,6 +95,12 @@ void probe_psd_jacobi(int n, double* H)
     else if (n == 9) psd_project_jacobi<9>(H);
     else psd_project_jacobi<12>(H);
 }
+// Z: n x n row-major symmetric in, eigenvectors (columns) out; d: eigenvalues
+int probe_sym_eig_ql(int n, double* Z, double* d)
+{
+    double e[16];
+    return sym_eig_ql(n, [&](int i, int j) -> double& { return Z[i * n + j]; }, d, e) ? 1 : 0;
+}
 void probe_barrier(int elastic, double d, double dHat, double k0, double* out3)
 {
     out3[0] = barrier_b(elastic, d, dHat, k0); out3[1] = barrier_g(elastic, d, dHat, k0); out3[2] = barrier_H(elastic, d, dHat, k0);

@@ -97,3 +97,29 @@ def test_dense_jacobi_projection(probe):
             probe.probe_psd_jacobi(n, _dp(B))
             w, V = np.linalg.eigh(A)
             assert np.linalg.norm(B - (V * np.maximum(w, 0)) @ V.T) <= 1e-12 * np.linalg.norm(A)
+
+
+def test_ql_eigensolver_matches_lapack(probe):
+    """eig.cuh sym_eig_ql (tridiagonalisation + implicit QL, the dense path's eigen-solver): eigenvalues, orthonormality and
+    reconstruction against numpy.linalg.eigh, including rank-deficient, repeated-eigenvalue, diagonal and zero matrices"""
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in (3, 6, 9):
+        for _ in range(300):
+            A = rng.normal(size=(n, n)) * 10.0 ** rng.integers(-6, 6); cases.append(A + A.T)
+        for r in range(0, n):  # rank r, indefinite
+            B = rng.normal(size=(n, max(r, 1))); sgn = np.diag(rng.choice([-1.0, 1.0], size=max(r, 1)))
+            cases.append((B @ sgn @ B.T) * (r > 0))
+        Q = np.linalg.qr(rng.normal(size=(n, n)))[0]
+        cases.append(Q @ np.diag([2.0] * (n - 1) + [-1.0]) @ Q.T)  # repeated eigenvalue
+        cases.append(np.diag(rng.normal(size=n))); cases.append(np.eye(n)); cases.append(np.zeros((n, n)))
+        T = np.diag(rng.normal(size=n)) + np.diag(rng.normal(size=n - 1), 1); cases.append(T + T.T)  # already tridiagonal
+    for A in cases:
+        n = len(A)
+        Z = np.ascontiguousarray(A, dtype=np.float64).copy(); d = np.zeros(n)
+        assert probe.probe_sym_eig_ql(n, _dp(Z), _dp(d)) == 1
+        w = np.linalg.eigvalsh(A)
+        scale = max(np.abs(w).max(), 1e-300)
+        assert np.abs(np.sort(d) - w).max() <= 1e-13 * scale
+        assert np.abs(Z.T @ Z - np.eye(n)).max() <= 1e-13
+        assert np.abs(Z @ np.diag(d) @ Z.T - A).max() <= 1e-13 * scale
