@@ -1396,8 +1396,11 @@ __global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const do
 }
 // dense path (mollified stencils; also usable for every stencil as a cross-check: idx == nullptr)
 constexpr int DENSE_BD = 64;                              // threads per block of the dense path
-constexpr int DENSE_SMEM = (45 + 81) * DENSE_BD * 8;       // upper triangle of the 9x9 matrix + eigenvectors per thread
-__global__ void __launch_bounds__(DENSE_BD) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
+constexpr int DENSE_SMEM = 81 * DENSE_BD * 8;              // the 9x9 matrix the eigen-solver works on, per thread
+#ifndef DENSE_MINB
+#define DENSE_MINB 4
+#endif
+__global__ void __launch_bounds__(DENSE_BD, DENSE_MINB) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
     const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
     const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip, int blkMode)
 {

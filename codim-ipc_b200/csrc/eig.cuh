@@ -203,16 +203,15 @@ CIPC_HD bool sym_eig_ql(int n, ZAcc Z, double* d, double* e)
 // outside the barrier's support).  Every block annihilates rigid translations (H t = 0 for t = (c,c,..,c)), so it
 // is first compressed with an orthonormal Helmert basis Q of the translation-free subspace:  M = Q H Q^T is
 // (N-3) x (N-3), H+ = Q^T M+ Q.  The cyclic Jacobi iteration then runs on M with matrix and eigenvectors held in
-// SHARED memory (upper triangle of M + full eigenvector matrix, element e of thread t at sm[e*BD + t]: bank-conflict
-// free, 63 KB per 64 threads -> three CTAs per SM), instead of thread-local
-// arrays that spill to L1/L2.  H: N x N row-major (N = 3*nb) in local memory, replaced by its PSD projection.
+// SHARED memory (element e of thread t at sm[e*BD + t]: bank-conflict free, 41 KB per 64 threads -> four CTAs per SM,
+// register-limited), instead of thread-local arrays that spill to L1/L2.  H: N x N row-major (N = 3*nb) in local memory, replaced by its PSD projection.
 __device__ inline void psd_project_reduced_smem(double* H, int nb, double* sm, int tid, int BD)
 {
     const int N = 3 * nb, K = N - 3;
-    double* A = sm;                 // upper triangle of the symmetric K x K matrix (capacity 45)
-    double* V = sm + 45 * BD;       // K*K eigenvectors (capacity 81)
+    double A[45];                   // upper triangle of the symmetric K x K matrix: thread-local (written once, read a few times)
+    double* V = sm;                 // K*K matrix / eigenvectors: the array the eigen-solver works on stays in shared memory
     auto tri = [&](int i, int j) { const int a = i < j ? i : j, b = i < j ? j : i; return a * (2 * K - a + 1) / 2 + (b - a); };
-#define SA(i, j) A[tri((i), (j)) * BD + tid]
+#define SA(i, j) A[tri((i), (j))]
 #define SV(i, j) V[((i) * K + (j)) * BD + tid]
     // Helmert rows h_k (k = 1..nb-1): k entries 1/sqrt(k(k+1)), then -k/sqrt(k(k+1)), then zeros
     double hc[3], hd[3];
