@@ -1402,11 +1402,11 @@ constexpr int DENSE_SMEM = 81 * DENSE_BD * 8;              // the 9x9 matrix the
 #endif
 __global__ void __launch_bounds__(DENSE_BD, DENSE_MINB) k_barrier_hessian(const double4* __restrict__ X, const double4* __restrict__ X0,
     const int4* __restrict__ cs, const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n,
-    const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip, int blkMode)
+    const u32* __restrict__ nDev, BarrierParams bp, int projectSPD, cipc_triplet* trip, int blkMode, u32 first = 0)
 {
     extern __shared__ double dense_sm[];
     if (nDev) n = *nDev; // list length produced on the device (fallbacks of the factor kernels)
-    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    for (u32 k = first + blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const u32 i = idx ? idx[k] : k;
         double H[144];
         int vids[4], nb;
@@ -1576,6 +1576,8 @@ struct cipc_ctx {
     std::unique_ptr<cipc_multi> multi; // cipc_create_multi: this context only fans calls out to multi->sub (multidev.h)
     u32 nPassLast = 0;                 // stencils of the last constraint set that needed no de-duplication (PT / EE / mollified)
     cudaStream_t st = nullptr, ownSt = nullptr;
+    cudaStream_t sideSt = nullptr;                 // dense-path launches that overlap the fused Hessian kernels (fork / join by events)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaEvent_t userEv[64] = {};
     std::string err;
     // topology
@@ -2619,6 +2621,9 @@ int cipc_create(int device, int rank, int world, cipc_ctx** out)
         CIPC_CUDA(cudaSetDevice(device));
         CIPC_CUDA(cudaStreamCreateWithFlags(&c->ownSt, cudaStreamNonBlocking));
         c->st = c->ownSt;
+        CIPC_CUDA(cudaStreamCreateWithFlags(&c->sideSt, cudaStreamNonBlocking));
+        CIPC_CUDA(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        CIPC_CUDA(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
         c->partial.reserve(RED_GRID, c->st);
         c->scal.reserve(16, c->st);
         c->bbox.reserve(6, c->st);
@@ -2664,6 +2669,9 @@ void cipc_destroy(cipc_ctx* ctx)
     for (auto e : ctx->evPool) cudaEventDestroy(e);
     for (auto e : ctx->userEv) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->ownSt);
+    if (ctx->sideSt) { cudaStreamSynchronize(ctx->sideSt); cudaStreamDestroy(ctx->sideSt); }
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     delete ctx;
 }
 const char* cipc_last_error(cipc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -3087,6 +3095,15 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     }
 #define CIPC_FUSED(CLS, B) CIPC_LAUNCH((k_hessian_fused<CLS, B>), div_up(nk[CLS], FUSED_BD), FUSED_BD, FusedShape<CLS>::SMEM, c->st, c->X.p, c->cs.p, \
     c->info.p, c->tripOff.p, c->clsIdx[CLS].p, nk[CLS], bp, outp, dl, dn, gOut)
+                    if (nk[3]) {
+                        // mollified stencils (the first nk[3] entries of the dense list, known now): a thread needs ~0.1 ms for one
+                        // dense block, so even a handful would be a serial tail behind the fused kernels -- they run beside them
+                        CIPC_CUDA(cudaEventRecord(c->evFork, c->st));
+                        CIPC_CUDA(cudaStreamWaitEvent(c->sideSt, c->evFork, 0));
+                        CIPC_LAUNCH(k_barrier_hessian, std::min(1184u, div_up(nk[3], DENSE_BD)), DENSE_BD, DENSE_SMEM, c->sideSt, c->X.p, c->X0.p, c->cs.p,
+                            c->info.p, c->tripOff.p, c->clsIdx[3].p, nk[3], (const u32*)nullptr, bp, projectSPD, outT, bm, 0u);
+                        CIPC_CUDA(cudaEventRecord(c->evJoin, c->sideSt));
+                    }
                     {
                         cipc_ctx::Scope sk(c, "k_hessian_fused0"); // the longest launch of the stage: PT/EE blocks
                         if (nk[0]) { if (blk) CIPC_FUSED(0, true); else CIPC_FUSED(0, false); }
@@ -3098,9 +3115,10 @@ static int barrier_hessian_impl(cipc_ctx* ctx, int elastic, double dHat2, const 
                     }
 #undef CIPC_FUSED
                     for (int k = 0; k < 4; ++k) c->nk[k] = nk[k];
-                    // mollified stencils + the ones the fused kernels rejected (list length read on the device): dense eigen path
-                    CIPC_LAUNCH(k_barrier_hessian, nk[3] ? 1184 : 148, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
-                        c->clsIdx[3].p, 0u, (const u32*)dn, bp, projectSPD, outT, bm);
+                    // the stencils the fused kernels rejected (appended behind the mollified ones, list length read on the device)
+                    CIPC_LAUNCH(k_barrier_hessian, 148, DENSE_BD, DENSE_SMEM, c->st, c->X.p, c->X0.p, c->cs.p, c->info.p, c->tripOff.p,
+                        c->clsIdx[3].p, 0u, (const u32*)dn, bp, projectSPD, outT, bm, nk[3]);
+                    if (nk[3]) CIPC_CUDA(cudaStreamWaitEvent(c->st, c->evJoin, 0));
                 }
                 else if (projectSPD) {
                     // (A) factor, (B) expand; stencils the factor kernels reject are appended to the dense list
