@@ -274,43 +274,6 @@ def parity_leg(ctx, sc, local, workload):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def bind_rank_to_gpu_node(local, world):
-    """N > 1: pin this rank's threads to its share of the cores of the NUMA node its GPU hangs off (sysfs), so that the
-    stage's ~10 host round trips and ~70 launches per step are not served from the far socket or from cores another rank
-    spins on.  Returns a description for the JSON line; does nothing when sysfs does not say (CIPC_BENCH_BIND=0 turns it off)."""
-    if os.environ.get("CIPC_BENCH_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
-        return None
-    try:
-        import torch
-
-        def node_of(i):
-            pr = torch.cuda.get_device_properties(i)
-            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-            with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
-                return int(f.read().strip())
-
-        nodes = [node_of(i) for i in range(world)]
-        node = nodes[local]
-        allowed = sorted(os.sched_getaffinity(0))
-        if node >= 0:
-            with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
-                cpus = []
-                for part in f.read().strip().split(","):
-                    lo, _, hi = part.partition("-")
-                    cpus += list(range(int(lo), int(hi or lo) + 1))
-            cpus = [c for c in cpus if c in allowed]
-        else:
-            cpus = allowed
-        peers = [i for i in range(world) if nodes[i] == node]  # ranks sharing the node split its cores evenly
-        share = max(1, len(cpus) // len(peers))
-        k = peers.index(local)
-        mine = cpus[k * share:(k + 1) * share] or cpus
-        os.sched_setaffinity(0, mine)
-        return {"gpu_numa_node": node, "cpus": "%d-%d (%d)" % (mine[0], mine[-1], len(mine))}
-    except Exception as e:  # no sysfs entry, container without the node files, ...
-        return {"unbound": str(e)[:80]}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -336,14 +299,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
-    binding = None
-    if world > 1:
-        # the library's host worker pool is created first, so its threads keep the whole machine (rank 0 uses them for the
-        # N-device end-to-end leg); the calling thread and everything created later (NCCL, torch) follow the binding
-        orig_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
-        warm = np.zeros(8 << 20, np.uint8)
-        cipc.load_library().cipc_hash_bytes(warm.ctypes.data, warm.nbytes)
-        binding = bind_rank_to_gpu_node(local, world)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -454,8 +409,6 @@ def main():
         dist.all_gather(tall, tl)
         scaling_breakdown = {"local_ms_per_rank": [round(float(x[0]), 4) for x in tall],
                              "collectives_only_ms": round(max(float(x[1]) for x in tall), 4)}
-        if binding is not None and orig_affinity:
-            os.sched_setaffinity(0, orig_affinity)  # the end-to-end leg on rank 0 drives all devices with helper threads: whole machine again
 
     # per-stage report (one extra untimed step)
     stages = {}
@@ -788,7 +741,6 @@ def main():
             "stages_ms": {k: (round(v, 4) if v is not None else None) for k, v in stages.items()}, "counters": counters,
             "friction_stages_ms": friction, "csr_stages_ms": csr}
     if scaling_breakdown is not None:
-        scaling_breakdown["host_binding_rank0"] = binding
         line["scaling_breakdown"] = scaling_breakdown
     if args.stage_report:
         print(json.dumps(line["stages_ms"], indent=1), file=sys.stderr)
