@@ -1326,6 +1326,9 @@ constexpr int FUSED_BD = 128;
 #ifndef FUSED_MINB
 #define FUSED_MINB 4
 #endif
+#ifndef FUSED_MINB12
+#define FUSED_MINB12 6 // PE / PP kernels: small factors, bound by the latency of the position gathers -> more resident warps
+#endif
 #ifndef FUSED_STASH
 #define FUSED_STASH 1
 #endif
@@ -1337,7 +1340,7 @@ template <int CLS> struct FusedShape {
 // BLK: the stencil's upper 3x3 blocks (9 doubles each, merge.cuh) are written instead of 16-byte triplets -- 720 instead of
 // 2304 bytes per PT/EE stencil -- and `off` counts blocks.
 template <int CLS, bool BLK>
-__global__ void __launch_bounds__(FUSED_BD, FUSED_MINB) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
+__global__ void __launch_bounds__(FUSED_BD, (CLS == 0 ? FUSED_MINB : FUSED_MINB12)) k_hessian_fused(const double4* __restrict__ X, const int4* __restrict__ cs,
     const double2* __restrict__ info, const u32* __restrict__ off, const u32* __restrict__ idx, u32 n, BarrierParams bp,
     void* __restrict__ outp, u32* denseList, u32* denseCount, double* gOut)
 {
