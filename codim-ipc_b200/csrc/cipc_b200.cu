@@ -1279,7 +1279,9 @@ __global__ void __launch_bounds__(256) k_hessian_expand_tiled(const double* __re
 // bytes per store instruction.
 // sR: per stencil, the NN global row indices 3 v[r/3] + r%3 (written by the factoring thread).  SIGNED: honour the header's
 // sign flag (friction only; the barrier factors are never negated).
-template <int NN, int NY, int YS, bool SIGNED>
+// ROWTAB = false: no table, the indices are formed from the header's vertex ids per triplet (friction: a pure store stream
+// that prefers the extra resident CTA the table's 6 KB would cost).
+template <int NN, int NY, int YS, bool SIGNED, bool ROWTAB = true>
 __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int* sH, const int* sR, u32 wq0, u32 g, u32 lane,
     cipc_triplet* __restrict__ trip)
 {
@@ -1309,7 +1311,8 @@ __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int
                 for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
                 if (SIGNED && neg) v = -v;
                 int4 w;
-                w.x = rows[r]; w.y = rows[c];
+                if (ROWTAB) { w.x = rows[r]; w.y = rows[c]; }
+                else { const int ri = r / 3, ci = c / 3; w.x = h[1 + ri] * 3 + (r - 3 * ri); w.y = h[1 + ci] * 3 + (c - 3 * ci); }
                 const long long bb = __double_as_longlong(v);
                 w.z = (int)(bb & 0xffffffffLL); w.w = (int)(bb >> 32);
                 __stcs(reinterpret_cast<int4*>(dst + e), w);

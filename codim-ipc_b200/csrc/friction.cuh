@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) k_friction_factor(const double4* __restri
 // The friction factors are cheap (no eigenproblem), so this kernel is a pure store stream.
 template <int CLS> struct FrFusedShape {
     static constexpr int NN = 3 * ((CLS == 0) ? 4 : (CLS == 1 ? 3 : 2)), YD = 2 * NN, YS = YD + 1;
-    static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32 + FUSED_BD * NN * 4;
+    static constexpr int SMEM = FUSED_BD * YS * 8 + FUSED_BD * 32;
 };
 template <int CLS, bool BLK>
 __global__ void __launch_bounds__(FUSED_BD) k_friction_fused(const double4* __restrict__ X, const double4* __restrict__ Xn,
@@ -282,7 +282,6 @@ __global__ void __launch_bounds__(FUSED_BD) k_friction_fused(const double4* __re
     extern __shared__ __align__(16) unsigned char fr_fused_sm[];
     double* sY = reinterpret_cast<double*>(fr_fused_sm);
     int* sH = reinterpret_cast<int*>(fr_fused_sm + FUSED_BD * YS * 8);
-    int* sR = sH + FUSED_BD * 8;
     const u32 q0 = blockIdx.x * FUSED_BD;
     const u32 g = min((u32)FUSED_BD, n - q0);
     if (threadIdx.x < g) {
@@ -294,17 +293,13 @@ __global__ void __launch_bounds__(FUSED_BD) k_friction_fused(const double4* __re
         h[0] = (int)off[i];
         h[5] = neg ? 1 : 0;
         if (BLK) h[6] = swap_mask<NN / 3>(h + 1);
-        else {
-#pragma unroll
-            for (int r = 0; r < NN; ++r) sR[threadIdx.x * NN + r] = 3 * h[1 + r / 3] + r % 3;
-        }
         double* y = sY + threadIdx.x * YS;
 #pragma unroll
         for (int k = 0; k < 2 * NN; ++k) y[k] = Y[k];
     }
     __syncwarp();
     if (BLK) warp_expand_blocks<NN / 3, 2, YS, true>(sY, sH, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<double*>(outp)); // upper blocks (merge.cuh)
-    else warp_expand_stencils<NN, 2, YS, true>(sY, sH, sR, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<cipc_triplet*>(outp));
+    else warp_expand_stencils<NN, 2, YS, true, false>(sY, sH, nullptr, threadIdx.x & ~31u, g, threadIdx.x & 31u, reinterpret_cast<cipc_triplet*>(outp));
 }
 
 } // namespace cipc
