@@ -682,7 +682,7 @@ def main():
     # FP64 side of the same kernel (it is co-limited): fp64 thread instructions per PT/EE stencil counted by ncu on this build
     # (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r2_fp64_ops_k_hessian_fused.csv) against the
     # non-tensor FP64 FMA rate measured on THIS box by tools/fp64_fma_probe (dependent DFMA chains, CUDA events)
-    FP64_OPS_4PT = {"dfma": 1865, "dmul": 1410, "dadd": 402}
+    FP64_OPS_4PT = {"dfma": 1865, "dmul": 1410, "dadd": 258}
     fp64_peak, fp64_src = 34.2, "recorded on this pool's B200 (tools/fp64_fma_probe, 2026-10-17)"
     probe = os.path.join(ROOT, "tools", "fp64_fma_probe")
     if os.path.exists(probe) and world == 1:
