@@ -355,11 +355,13 @@ __global__ void k_cell_fill(Topo T, GridDesc G, const u64* __restrict__ boxLo, c
     else if (g < T.nBN + T.nBE) { kind = 1; id = g - T.nBN; }
     else { kind = 2; id = g - T.nBN - T.nBE; }
     const u64 a = boxLo[g], b = boxHi[g];
-    const ulonglong2 f = fine[g];
-    const int l0[3] = {ux(a), uy(a), uz(a)}, fl[3] = {ux(f.x), uy(f.x), uz(f.x)}, fh[3] = {ux(f.y), uy(f.y), uz(f.y)};
+    const int l0[3] = {ux(a), uy(a), uz(a)};
     int l[3] = {l0[0], l0[1], l0[2]}, h[3] = {ux(b), uy(b), uz(b)};
     l[sl.axis] = max(l[sl.axis], sl.s0);
     h[sl.axis] = min(h[sl.axis], sl.s1 - 1);
+    if (l[sl.axis] > h[sl.axis]) return; // outside this rank's slab: leave before touching the fine coordinates
+    const ulonglong2 f = fine[g];
+    const int fl[3] = {ux(f.x), uy(f.x), uz(f.x)}, fh[3] = {ux(f.y), uy(f.y), uz(f.y)};
     for (int iz = l[2]; iz <= h[2]; ++iz)
         for (int iy = l[1]; iy <= h[1]; ++iy)
             for (int ix = l[0]; ix <= h[0]; ++ix) {
