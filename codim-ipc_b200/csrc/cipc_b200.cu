@@ -1886,7 +1886,11 @@ void build_cell_lists(cipc_ctx* c, HashInfo& H, int which)
     }
     const long gridCells = (long)H.G.gx * H.G.gy * H.G.gz;
     static const bool forceSort = getenv("CIPC_HASH_SORT") != nullptr; // cross-check switch: radix-sort path for every grid
-    if (gridCells <= DENSE_CELL_LIMIT && gridCells <= 4L * nP && !forceSort) {
+    // dense cell table for grids of up to 4 cells per primitive, and for ANY grid of up to 2M cells: scanning a table that
+    // size costs ~20 us, less than the radix-sort path's extra launches and round trip (sparse scenes such as a cloth over a
+    // large obstacle: cfg1 0.28 -> 0.23 ms per build, tools/dense_min_cells.sh)
+    static const long denseMinCells = getenv("CIPC_DENSE_MIN_CELLS") ? atol(getenv("CIPC_DENSE_MIN_CELLS")) : (2L << 20);
+    if (gridCells <= DENSE_CELL_LIMIT && gridCells <= std::max(4L * nP, denseMinCells) && !forceSort) {
         // dense cell table (grids with at most a few cells per primitive): count -> scan (= kind-range table) -> tasks ->
         // fill; one host round trip for the entry and task totals
         const u32 nCells = (u32)gridCells;
