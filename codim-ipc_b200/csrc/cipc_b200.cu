@@ -2843,6 +2843,7 @@ int cipc_set_topology(cipc_ctx* ctx, int nV, int nBN, const int32_t* BN, int nBE
         c->haveX = c->haveX0 = c->haveP = c->haveXn = c->haveXprev = false;
         c->tagX = c->tagX0 = c->tagP = c->tagXn = 0;
         c->slabCache[0].valid = c->slabCache[1].valid = false;
+        c->dedupLastRaw = c->dedupLastUnique = 0; // a new scene: no duplicate-ratio history for the merge table
         ++c->xVersion;
         c->nC = 0;
         c->nF = 0;
