@@ -1276,14 +1276,10 @@ __global__ void __launch_bounds__(256) k_hessian_expand_tiled(const double* __re
         if (STREAM) __stcs(dst, o); else *dst = o;
     }
 }
-#ifndef CIPC_EXPAND_COLS
-#define CIPC_EXPAND_COLS 1
-#endif
 // Expansion, warp by warp: a warp expands the (up to) 32 stencils whose factors its own lanes parked in shared memory
 // (stencil q of the CTA: factors at sY + q*YS, header {offset, v0..v3, sign} at sH + q*8).  No CTA barrier is involved:
-// warps stay decoupled, so one warp's store stream overlaps the others' arithmetic.  Lane l owns the fixed block entries
-// e = l + 32 j of every stencil; (row, col) decoding is hoisted out of the stencil loop and a warp writes 512 contiguous
-// bytes per store instruction.
+// warps stay decoupled, so one warp's store stream overlaps the others' arithmetic.  A lane owns one column of the block and
+// a group of its rows (see below).
 // sR: per stencil, the NN global row indices 3 v[r/3] + r%3 (written by the factoring thread).  SIGNED: honour the header's
 // sign flag (friction only; the barrier factors are never negated).
 // ROWTAB = false: no table, the indices are formed from the header's vertex ids per triplet (friction: a pure store stream
@@ -1292,7 +1288,6 @@ template <int NN, int NY, int YS, bool SIGNED, bool ROWTAB = true>
 __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int* sH, const int* sR, u32 wq0, u32 g, u32 lane,
     cipc_triplet* __restrict__ trip)
 {
-#if CIPC_EXPAND_COLS
     // Lane = (column c, row group): NG groups of NN lanes, a group owns RPG consecutive rows.  The lane's column of the
     // factors and its column index stay in registers for the whole stencil, so a triplet costs NY shared-memory loads (warp
     // broadcasts of y[k][r]) + 1 index load instead of 2 NY + 2; a store instruction writes NG runs of NN x 16 contiguous bytes.
@@ -1329,42 +1324,6 @@ __device__ __forceinline__ void warp_expand_stencils(const double* sY, const int
             __stcs(reinterpret_cast<int4*>(dst + j * NN), w);
         }
     }
-#else
-    constexpr int PER = NN * NN, NJ = (PER + 31) / 32;
-    int rI[NJ], cI[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int e = (int)lane + 32 * j;
-        rI[j] = e / NN; cI[j] = e - rI[j] * NN;
-    }
-    const u32 wn = (wq0 < g) ? min(32u, g - wq0) : 0u;
-    for (u32 qq = 0; qq < wn; ++qq) {
-        const int* h = sH + (wq0 + qq) * 8;
-        const u32 o = (u32)h[0];
-        if (o == 0xffffffffu) continue;
-        const double* y = sY + (wq0 + qq) * YS;
-        const int* rows = sR + (wq0 + qq) * NN;
-        const bool neg = SIGNED && h[5] != 0;
-        cipc_triplet* dst = trip + (size_t)o * 9;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int e = (int)lane + 32 * j;
-            if (NJ * 32 == PER || e < PER) {
-                const int r = rI[j], c = cI[j];
-                double v = 0.0;
-#pragma unroll
-                for (int k = 0; k < NY; ++k) v += y[k * NN + r] * y[k * NN + c];
-                if (SIGNED && neg) v = -v;
-                int4 w;
-                if (ROWTAB) { w.x = rows[r]; w.y = rows[c]; }
-                else { const int ri = r / 3, ci = c / 3; w.x = h[1 + ri] * 3 + (r - 3 * ri); w.y = h[1 + ci] * 3 + (c - 3 * ci); }
-                const long long bb = __double_as_longlong(v);
-                w.z = (int)(bb & 0xffffffffLL); w.w = (int)(bb >> 32);
-                __stcs(reinterpret_cast<int4*>(dst + e), w);
-            }
-        }
-    }
-#endif
 }
 // Fused factor + expansion for the device-resident triplet stream: a CTA of 128 threads factors 128 stencils (FP64
 // pipe, one stencil per thread), parks the factors in shared memory, and then all threads turn them into triplets with
