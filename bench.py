@@ -151,7 +151,7 @@ def cpu_samples(workload, n_warm, n_timed, budget_s=None):
         if i == 0 and budget_s is not None and t * (n_warm + n_timed) > budget_s:
             fit = max(4, int(budget_s / t))
             n_warm = max(1, min(n_warm, fit - 3)) if n_warm else 0
-            n_timed = max(3, min(n_timed, fit - n_warm))
+            n_timed = min(n_timed, max(3, fit - n_warm))  # cut down to what fits, never below 3 (nor above the request)
         if i >= n_warm:
             times.append(t)
         i += 1
