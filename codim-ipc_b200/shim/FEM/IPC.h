@@ -376,6 +376,35 @@ void Compute_Barrier_Hessian(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeA
     }
 }
 
+// ------------------------------------------------------------------ optional CSR hand-off
+// The contact part of the system matrix assembled ON THE DEVICE (duplicates summed, columns sorted) and delivered in the three
+// arrays the reference's CSR_MATRIX<T>::Construct_From_CSR takes (Math/CSR_MATRIX.h:33-47), instead of triplets that
+// Construct_From_Triplet / setFromTriplets would have to sort (Math/CSR_MATRIX.h:49-56, Shell/INC_POTENTIAL.h:373-394).  A caller
+// that wants it builds with -DCIPC_SHIM_CSR and replaces the Compute_Barrier_Hessian call next to INC_POTENTIAL.h:382 (see
+// INTEGRATION.md 4d):  ptr has 3 X.size + 1 entries.
+template <class T, int dim, bool elasticIPC = false>
+void Compute_Barrier_Hessian_CSR(MESH_NODE<T, dim>& X, MESH_NODE_ATTR<T, dim>& nodeAttr, const std::vector<VECTOR<int, dim + 1>>& constraintSet,
+    const std::vector<VECTOR<T, 2>>& stencilInfo, T dHat2, T kappa[], T thickness, bool projectSPD, std::vector<int>& ptr, std::vector<int>& col,
+    std::vector<T>& val)
+{
+    static_assert(cipc_shim::on_gpu<T, dim, false, elasticIPC>, "the CSR hand-off exists for the instantiation the CUDA path serves (double, dim = 3, OIPC)");
+    static_assert(sizeof(int) == sizeof(int32_t), "CSR index type");
+    (void)nodeAttr;
+    TIMER_FLAG("Compute_Barrier_Hessian_CSR");
+    cipc_shim::State& s = cipc_shim::state();
+    cipc_shim::upload_positions(s, X, cipc_set_positions, "cipc_set_positions");
+    cipc_shim::ensure_constraints(s, constraintSet, stencilInfo);
+    int64_t n = 0, nnz = 0;
+    cipc_shim::die(s.ctx, cipc_csr_begin(s.ctx), "cipc_csr_begin");
+    cipc_shim::die(s.ctx, cipc_barrier_hessian_dev(s.ctx, 0, dHat2, kappa, thickness, projectSPD ? 1 : 0, &n), "cipc_barrier_hessian_dev");
+    cipc_shim::die(s.ctx, cipc_csr_add(s.ctx), "cipc_csr_add");
+    cipc_shim::die(s.ctx, cipc_csr_finish(s.ctx, &nnz), "cipc_csr_finish");
+    cipc_shim::resize_uninitialized(ptr, (size_t)dim * X.size + 1);
+    cipc_shim::resize_uninitialized(col, (size_t)nnz);
+    cipc_shim::resize_uninitialized(val, (size_t)nnz);
+    cipc_shim::die(s.ctx, cipc_get_csr(s.ctx, ptr.data(), col.data(), val.data()), "cipc_get_csr");
+}
+
 // ------------------------------------------------------------------ FEM/IPC.h:1879-1890
 template <class T, int dim, bool shell = false, bool elasticIPC = false>
 void Compute_Intersection_Free_StepSize(MESH_NODE<T, dim>& X, const std::vector<int>& boundaryNode,

@@ -387,7 +387,9 @@ void ref_contact_stage(void* h, double dHat2, const double* kappa_in, double thi
 // difference (raw) / 0, [4] max per-block ||H - H_cpu||_F / ||H_cpu||_F (raw) or ||A x - A_cpu x|| / ||A_cpu x|| (merged),
 // [5] (row, col) mismatches (raw), [6] step_gpu, [7] step_cpu, [8] dist2 mismatches, [9] |minDist2 - cpu|,
 // [10] friction-set mismatches, [11] max closest-point / basis / normal-force error, [12] friction potential rel. error,
-// [13] friction gradient rel. error, [14] friction Hessian error (as [4]), [15] nC, [16] nF
+// [13] friction gradient rel. error, [14] friction Hessian error (as [4]), [15] nC, [16] nF,
+// [17] CSR hand-off (Compute_Barrier_Hessian_CSR): rel. error of A x against the CPU template's triplets, [18] structural
+// violations of the CSR arrays (row pointer length / end, unsorted or repeated or out-of-range columns)
 void shim_selfcheck(void* h, double dHat2, const double* kappa_in, double thickness, const double* searchDir, const double* Xn_in, double epsvh2,
     double mu, int rawTriplets, double* out)
 {
@@ -450,7 +452,7 @@ void shim_selfcheck(void* h, double dHat2, const double* kappa_in, double thickn
     };
     auto max_abs = [](const std::vector<double>& a) { double m = 0; for (double v : a) m = std::max(m, std::fabs(v)); return m; };
     auto max_diff = [](const std::vector<double>& a, const std::vector<double>& b) { double m = 0; for (size_t i = 0; i < a.size(); ++i) m = std::max(m, std::fabs(a[i] - b[i])); return m; };
-    for (int k = 0; k < 17; ++k) out[k] = 0;
+    for (int k = 0; k < 19; ++k) out[k] = 0;
 
     // ---- the six contact templates
     CS csG, csC;
@@ -484,6 +486,23 @@ void shim_selfcheck(void* h, double dHat2, const double* kappa_in, double thickn
             }
         }
         else out[4] = rel_vec(matvec(tG), matvec(tC));
+        // optional CSR hand-off: the same matrix, assembled on the device
+        std::vector<int> ptr, col;
+        std::vector<T> val;
+        Compute_Barrier_Hessian_CSR<T, 3, false>(s->X, s->nodeAttr, csG, infoG, dHat2, kappa, thickness, true, ptr, col, val);
+        std::vector<Eigen::Triplet<T>> tRef(tC.begin() + 3, tC.end());
+        std::vector<double> y(3 * (size_t)nV, 0.0);
+        double bad = (ptr.size() != 3 * (size_t)nV + 1) ? 1 : 0;
+        if (!bad) {
+            bad += ptr[0] != 0 || (size_t)ptr.back() != val.size() || col.size() != val.size();
+            for (int r = 0; r < 3 * nV && !bad; ++r)
+                for (int k = ptr[r]; k < ptr[r + 1]; ++k) {
+                    if (col[k] < 0 || col[k] >= 3 * nV || (k > ptr[r] && col[k] <= col[k - 1])) { ++bad; break; }
+                    y[r] += val[k] * std::cos(1.0 + 0.37 * col[k]);
+                }
+        }
+        out[17] = rel_vec(y, matvec(tRef));
+        out[18] = bad;
     }
     std::vector<T> p(searchDir, searchDir + 3 * (size_t)nV);
     T aG = 1, aC = 1;

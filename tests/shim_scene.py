@@ -40,8 +40,8 @@ class ShimScene(O.RefScene):
         return lib().ref_timer_parent(name.encode()).decode()
 
     def selfcheck(self, sc, Xn=None, epsvh2=1e-10, mu=0.4, raw=True):
-        """GPU templates vs the reference's *_CPU templates inside the one binary -> array of 17 error figures (shim_selfcheck)"""
-        out = np.zeros(17)
+        """GPU templates vs the reference's *_CPU templates inside the one binary -> array of 19 error figures (shim_selfcheck)"""
+        out = np.zeros(19)
         k = np.ascontiguousarray(sc["kappa"], np.float64); p = np.ascontiguousarray(sc["p"], np.float64)
         xn = np.ascontiguousarray(Xn, np.float64) if Xn is not None else None
         lib().shim_selfcheck(self.h, C.c_double(sc["dHat2"]), O._dp(k), C.c_double(sc["xi"]), O._dp(p), O._dp(xn) if xn is not None else None,

@@ -70,6 +70,7 @@ def test_shim_selfcheck_gpu_vs_cpu_templates_in_one_binary(mode):
         assert o[8] == 0 and o[9] == 0, (name, "dist2", o[8], o[9])
         assert o[16] > 0 and o[10] == 0, (name, "friction set", o[10])
         assert o[11] <= 1e-9 and o[12] <= 1e-9 and o[13] <= 1e-9 and o[14] <= 1e-9, (name, "friction terms", o[11:15])
+        assert o[18] == 0 and o[17] <= 1e-9, (name, "CSR hand-off (Compute_Barrier_Hessian_CSR)", o[17], o[18])
 
 
 @pytest.mark.parametrize("name", list(_cases()))
